@@ -1,0 +1,52 @@
+"""Oracle pinning: functional SA-M4C restatement vs goldens produced by the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sam4c_oracle as O
+from sam_textvqa_b200 import synth
+from tests._util import cfg1, golden_batch, load_golden, rel_err, sam4c_state_shapes
+
+
+@pytest.fixture(scope="module")
+def setup():
+    g = load_golden("sam4c_cfg1.npz")
+    mmt, tb = cfg1()
+    P = synth.seeded_state(sam4c_state_shapes(mmt, tb, V=500), 0)
+    return g, mmt, tb, P, golden_batch(g)
+
+
+def test_teacher_forced_scores_loss_and_grads(setup):
+    g, mmt, tb, P, batch = setup
+    P = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    scores, _, seq = O.forward(P, batch, mmt, tb, train=True)
+    assert rel_err(scores, g["tf/scores"]) < 2e-6
+    assert rel_err(seq, g["tf/mmt_seq_output"]) < 2e-5
+    loss = O.bce_with_mask_loss(scores, batch["targets"], batch["train_loss_mask"])
+    assert abs(loss.item() - float(g["tf/loss"])) < 1e-4 * float(g["tf/loss"])
+    loss.backward()
+    for k in g.files:
+        if k.startswith("grad/"):
+            got = P[k[5:]].grad
+            ref = torch.from_numpy(g[k])
+            if got.numel() > 70000:
+                got = got.flatten()[:: max(1, got.numel() // 4096)]
+            assert rel_err(got, ref) < 2e-4, k
+    # padded OCR slots are raw - 10000 (sa_m4c.py:879,893)
+    pad = batch["pad_ocr_mask"] == 0
+    assert (scores[:, :, 500:][pad[:, None, :].expand(-1, 12, -1)] < -9000).all()
+
+
+def test_greedy_decode_tokens(setup):
+    g, mmt, tb, P, batch = setup
+    with torch.no_grad():
+        scores, prev, _ = O.forward(P, batch, mmt, tb, train=False)
+    assert np.array_equal(prev.numpy(), g["greedy/prev_inds"])
+    assert rel_err(scores, g["greedy/scores"]) < 2e-5
+
+
+def test_text_rows_of_spatial_layer_are_dead(setup):
+    """Known-answer fact: with quadrants [1,2] every text query row is fully masked."""
+    g = load_golden("attn_unit.npz")
+    T = int(g["T"])
+    assert np.abs(g["ctx"][:, :T]).max() == 0.0
