@@ -1,0 +1,78 @@
+"""ctypes binding of libsamk.so (the C ABI declared in include/samk.h).
+
+The product path has no fallback: if the shared object is missing or a call fails, this
+raises.  `lib()` loads lazily so that CPU-only tooling (config, synthetic data, host logic
+tests) can import the package on a machine where the library has not been built yet.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsamk.so")
+
+c_void_p, c_int, c_ll, c_float, c_double, c_ull = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong,
+                                                   ctypes.c_float, ctypes.c_double, ctypes.c_ulonglong)
+
+DT_F32, DT_BF16 = 0, 1
+
+
+class GemmEpilogue(ctypes.Structure):
+    _fields_ = [
+        ("out", c_void_p), ("ldo", c_ll), ("out_dtype", c_int), ("atomic_add", c_int), ("alpha", c_float),
+        ("bias", c_void_p), ("pre", c_void_p), ("ldpre", c_ll), ("pre_dtype", c_int), ("act", c_int),
+        ("aux", c_void_p), ("ldaux", c_ll), ("aux_dtype", c_int), ("drop_p", c_float),
+        ("drop_seed", c_ull), ("drop_offset", c_ull), ("residual", c_void_p), ("ldres", c_ll),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol include/samk.h declares
+SIGNATURES = {
+    "samk_version": (c_int, []),
+    "samk_last_error": (ctypes.c_char_p, []),
+    "samk_sm_count": (c_int, []),
+    "samk_build_graph_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_int, c_void_p, c_void_p]),
+    "samk_build_graph_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_int, c_void_p, c_void_p]),
+    "samk_graph_default_sectors": (ctypes.POINTER(c_double), []),
+    "samk_pack_adj": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
+    "samk_unpack_bits": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
+    "samk_gemm_bf16": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_int, c_ll, c_int, c_int, c_int,
+                               ctypes.POINTER(GemmEpilogue), c_int, c_int, c_void_p]),
+}
+
+_LIB = None
+
+
+class SamkError(RuntimeError):
+    pass
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise SamkError(
+                "libsamk.so not found at %s -- build it with `python -m sam_textvqa_b200.build` "
+                "(there is no CPU or PyTorch fallback for the CUDA path)" % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = handle
+    return _LIB
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().samk_last_error()
+        raise SamkError("%s failed (%d): %s" % (what or "samk call", rc, (msg or b"").decode()))
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Raw device pointer of a tensor (None -> NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
