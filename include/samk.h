@@ -87,6 +87,87 @@ typedef struct samk_gemm_epilogue {
 int samk_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major, long long ldb,
                    int M, int N, int K, const samk_gemm_epilogue* ep, int split_k, int impl, void* stream);
 
+/* ---- HBM-bound row kernels ------------------------------------------------------------------
+ * fp32 -> bf16 operand cast; fp32 -> three bf16 planes (hi,hi,lo | hi,lo,hi) so that a plain bf16
+ * GEMM over the 3x longer K reproduces fp32 products to ~2^-16 ("bf16x3" parity mode). */
+int samk_cast_bf16(const float* x, long long ldx, void* y, long long ldy, int rows, int cols, void* stream);
+int samk_split3_bf16(const float* x, long long ldx, void* y, long long ldy, int rows, int cols, int order,
+                     int along_rows, void* stream);
+/* F.normalize(x, dim=-1) of sa_m4c.py:208-209,224-238 (normalize=0: plain copy/cast) */
+int samk_l2norm(const float* x, long long ldx, void* y, long long ldy, int y_dtype, int rows, int cols, int normalize,
+                void* stream);
+/* BertLayerNorm (sa_m4c.py:1016-1028; eps inside the sqrt, biased variance).  y fp32 and/or y2 in
+ * y2_dtype.  Backward: dx fp32; optional dxd = dropout_mask(dx) in dxd_dtype (gradient of the dense
+ * output under the dropout of BertSelfOutput/BertOutput); dgamma, dbeta, dbias (= colsum(dxd)) are
+ * ACCUMULATED (+=) into fp32 [cols] buffers. */
+int samk_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y, void* y2,
+                       int y2_dtype, int rows, int cols, void* stream);
+int samk_layernorm_bwd(const float* dy, const float* x, const float* gamma, float eps, float* dx, void* dxd,
+                       int dxd_dtype, float drop_p, unsigned long long seed, unsigned long long offset, float* dgamma,
+                       float* dbeta, float* dbias, int rows, int cols, void* stream);
+/* out = dropout(a + b) (b may be NULL); also the dropout backward with a = dout */
+int samk_dropout_add(const float* a, const float* b, float* out, void* out2, int out2_dtype, int rows, int cols,
+                     float drop_p, unsigned long long seed, unsigned long long offset, void* stream);
+/* out[c] += sum_r x[r,c] */
+int samk_colsum(const void* x, int x_dtype, long long ld, int rows, int cols, float* out, void* stream);
+/* BertEmbeddings of TextBert (sa_m4c.py:383): dropout(LN(word[id] + pos[t] + type[0])); backward
+ * accumulates into the five gradient buffers. */
+int samk_bert_embed_fwd(const long long* ids, const float* word, const float* pos, const float* type,
+                        const float* gamma, const float* beta, float eps, float* out, void* out2, int out2_dtype,
+                        int rows, int T, int cols, float drop_p, unsigned long long seed, unsigned long long offset,
+                        void* stream);
+int samk_bert_embed_bwd(const float* dout, const long long* ids, const float* word, const float* pos, const float* type,
+                        const float* gamma, float eps, float* dword, float* dpos, float* dtype, float* dgamma,
+                        float* dbeta, int rows, int T, int cols, float drop_p, unsigned long long seed,
+                        unsigned long long offset, void* stream);
+/* PrevPredEmbeddings.forward (sa_m4c.py:919-948) without the [B,V+R,768] concat: ln6 = device
+ * pointers {ans_g, ans_b, ocr_g, ocr_b, emb_g, emb_b} (HOST array of 6); grads10 = HOST array
+ * {d_cls_w, d_ocr_in, d_pos, d_type, d_ans_g, d_ans_b, d_ocr_g, d_ocr_b, d_emb_g, d_emb_b}, accumulated. */
+int samk_prevpred_fwd(const long long* prev, const float* cls_w, const float* ocr_in, const float* pos,
+                      const float* type, const float* const* ln6, float eps, float* out, int B, int D, int V, int R,
+                      int cols, float drop_p, unsigned long long seed, unsigned long long offset, void* stream);
+int samk_prevpred_bwd(const float* dout, const long long* prev, const float* cls_w, const float* ocr_in,
+                      const float* pos, const float* type, const float* const* ln6, float eps, float* const* grads10,
+                      int B, int D, int V, int R, int cols, float drop_p, unsigned long long seed,
+                      unsigned long long offset, void* stream);
+/* OcrPtrNet scoring (sa_m4c.py:891-893): out[b,t,col_off+r] = q[b,t].k[b,r]/sqrt(dq) + (1-mask[b,r])*-1e4 */
+int samk_ptr_scores_fwd(const float* q, const float* k, const long long* ocr_mask, float* out, long long ldo,
+                        int col_off, int B, int D, int R, int dq, void* stream);
+int samk_ptr_scores_bwd(const float* dscores, long long ldds, int col_off, const float* q, const float* k, float* dq_,
+                        float* dk_, int B, int D, int R, int dq, void* stream);
+/* M4CDecodingBCEWithMaskLoss (sam/task_utils.py:19-30): loss_out[0] = loss; dscores (optional) =
+ * d loss / d scores; scratch = 1 float. rows = B*D, ncls = V+R. */
+int samk_bce_loss(const float* scores, const float* targets, const float* loss_mask, float* dscores, float* loss_out,
+                  float* scratch, int rows, int ncls, void* stream);
+int samk_scale_inplace(float* x, long long n, const float* scale_dev, void* stream);
+
+/* ---- masked multi-head attention -------------------------------------------------------------
+ * Replaces SpatialBertSelfAttention.forward steps (1),(3)-(7) (sa_m4c.py:475-552, 562-598) and
+ * the BertSelfAttention of the 'n' layers / TextBert (sa_m4c.py:743, 391); the [B,L,L,H] masks are
+ * never materialised (see csrc/attn_mask.cuh for the boolean restatement).
+ *   qkv [B,L,3*H*64] (q|k|v), ctx [B,L,H*64], lse [B,H,L] fp32, key_valid uint8 [B,L],
+ *   rel_bits uint16 [B,A,A] (bit h = head h may attend i->j; NULL when spatial == 0),
+ *   quadrant_mask bit (3*seg_i+seg_j), seg 0/1/2 = text/entity/decoder (attention_mask_quadrants q
+ *   of the yml maps to bit q-1).  Backward: dctx -> dqkv (same layout), delta [B,H,L] scratch.
+ * impl 0 = product kernel for the dtype (bf16: tensor cores; f32: exact fp32), 1 = force the exact
+ * fp32 SIMT kernel (used as on-device cross-check). */
+typedef struct samk_attn_params {
+  const void* qkv; void* ctx; float* lse;
+  const void* dctx; void* dqkv; float* delta;
+  int dtype;                 /* SAMK_DT_* of qkv/ctx/dctx/dqkv */
+  int B, H, head_dim;
+  int T, A, D;
+  const uint8_t* key_valid;
+  const uint16_t* rel_bits;
+  unsigned int quadrant_mask;
+  int spatial;
+  float scale;
+  float drop_p;
+  unsigned long long drop_seed, drop_offset;
+} samk_attn_params;
+int samk_attn_fwd(const samk_attn_params* p, int impl, void* stream);
+int samk_attn_bwd(const samk_attn_params* p, int impl, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

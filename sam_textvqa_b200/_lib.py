@@ -25,6 +25,15 @@ class GemmEpilogue(ctypes.Structure):
     ]
 
 
+class AttnParams(ctypes.Structure):
+    _fields_ = [
+        ("qkv", c_void_p), ("ctx", c_void_p), ("lse", c_void_p), ("dctx", c_void_p), ("dqkv", c_void_p),
+        ("delta", c_void_p), ("dtype", c_int), ("B", c_int), ("H", c_int), ("head_dim", c_int), ("T", c_int),
+        ("A", c_int), ("D", c_int), ("key_valid", c_void_p), ("rel_bits", c_void_p), ("quadrant_mask", ctypes.c_uint),
+        ("spatial", c_int), ("scale", c_float), ("drop_p", c_float), ("drop_seed", c_ull), ("drop_offset", c_ull),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/samk.h declares
 SIGNATURES = {
     "samk_version": (c_int, []),
@@ -37,6 +46,30 @@ SIGNATURES = {
     "samk_unpack_bits": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "samk_gemm_bf16": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_int, c_ll, c_int, c_int, c_int,
                                ctypes.POINTER(GemmEpilogue), c_int, c_int, c_void_p]),
+    "samk_cast_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p]),
+    "samk_split3_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
+    "samk_l2norm": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
+    "samk_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "samk_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_float, c_ull,
+                                   c_ull, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "samk_dropout_add": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_ull, c_ull, c_void_p]),
+    "samk_colsum": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p]),
+    "samk_bert_embed_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
+                                    c_void_p, c_int, c_int, c_int, c_int, c_float, c_ull, c_ull, c_void_p]),
+    "samk_bert_embed_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_ull, c_ull,
+                                    c_void_p]),
+    "samk_prevpred_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
+                                  c_int, c_int, c_int, c_int, c_int, c_float, c_ull, c_ull, c_void_p]),
+    "samk_prevpred_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                                  c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_ull, c_ull, c_void_p]),
+    "samk_ptr_scores_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "samk_ptr_scores_bwd": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                    c_int, c_void_p]),
+    "samk_bce_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "samk_scale_inplace": (c_int, [c_void_p, c_ll, c_void_p, c_void_p]),
+    "samk_attn_fwd": (c_int, [ctypes.POINTER(AttnParams), c_int, c_void_p]),
+    "samk_attn_bwd": (c_int, [ctypes.POINTER(AttnParams), c_int, c_void_p]),
 }
 
 _LIB = None

@@ -1,0 +1,819 @@
+// HBM-bound row kernels of the SA-M4C path: operand casts / bf16x3 splits, L2 normalisation,
+// TF-style LayerNorm forward/backward (fused with the dropout mask and the bias-gradient column
+// sums of the dense layer in front of it), dropout-add, column sums, and the two embedding
+// blocks (TextBert embeddings, PrevPredEmbeddings).  One warp owns one row of <= 1024 floats.
+#include "common.cuh"
+#include "../../include/samk.h"
+
+namespace samk {
+
+constexpr int kRowThreads = 256;           // 8 warps per block
+constexpr int kMaxVec = 8;                 // float4 per lane -> cols <= 1024
+
+__device__ __forceinline__ void store_act(void* base, int bf16, size_t idx, float4 v) {
+  if (bf16) {
+    uint2 u = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = u;
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx) = v;
+  }
+}
+__device__ __forceinline__ float4 load_act(const void* base, int bf16, size_t idx) {
+  if (bf16) {
+    uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx);
+    float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.x));
+    float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+}
+
+__device__ __forceinline__ float4 drop4(float4 v, uint32_t thresh, float scale, uint64_t seed, uint64_t off,
+                                        uint64_t ctr) {
+  if (!thresh) return v;
+  uint4 r = dropout_bits4(seed, off, ctr);
+  v.x = r.x >= thresh ? v.x * scale : 0.f;
+  v.y = r.y >= thresh ? v.y * scale : 0.f;
+  v.z = r.z >= thresh ? v.z * scale : 0.f;
+  v.w = r.w >= thresh ? v.w * scale : 0.f;
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// casts
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld4(const float* p, int vec) {
+  if (vec) return *reinterpret_cast<const float4*>(p);
+  return make_float4(p[0], p[1], p[2], p[3]);
+}
+
+__global__ void cast_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy,
+                            int rows, int cols, int vec) {
+  const int c4 = cols >> 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)rows * c4; i += (size_t)gridDim.x * blockDim.x) {
+    int r = (int)(i / c4), c = (int)(i % c4) * 4;
+    float4 v = ld4(x + (size_t)r * ldx + c, vec);
+    *reinterpret_cast<uint2*>(y + (size_t)r * ldy + c) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+
+// x fp32 [rows, cols] -> three bf16 planes.  hi = bf16(x), lo = bf16(x - hi).
+// order 0: (hi,hi,lo)   order 1: (hi,lo,hi).   along_rows 0: y[r, s*cols + c]; 1: y[s*rows + r, c]
+__global__ void split3_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy,
+                              int rows, int cols, int order, int along_rows, int vec) {
+  const int c4 = cols >> 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)rows * c4; i += (size_t)gridDim.x * blockDim.x) {
+    int r = (int)(i / c4), c = (int)(i % c4) * 4;
+    float4 v = ld4(x + (size_t)r * ldx + c, vec);
+    float h0 = bf2f(__float2bfloat16_rn(v.x)), h1 = bf2f(__float2bfloat16_rn(v.y));
+    float h2 = bf2f(__float2bfloat16_rn(v.z)), h3 = bf2f(__float2bfloat16_rn(v.w));
+    uint2 hi = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
+    uint2 lo = make_uint2(pack_bf16(v.x - h0, v.y - h1), pack_bf16(v.z - h2, v.w - h3));
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      bool is_lo = order == 0 ? (s == 2) : (s == 1);
+      size_t o = along_rows ? ((size_t)(s * rows + r) * ldy + c) : ((size_t)r * ldy + (size_t)s * cols + c);
+      *reinterpret_cast<uint2*>(y + o) = is_lo ? lo : hi;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// F.normalize(x, dim=-1) (sa_m4c.py:208-209, 224-238): y = x / max(||x||_2, 1e-12)
+// ---------------------------------------------------------------------------------------------
+__global__ void l2norm_kernel(const float* __restrict__ x, long long ldx, void* __restrict__ y, long long ldy,
+                              int y_bf16, int rows, int cols, int normalize) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < rows; r += nwarps) {
+    const float* xr = x + (size_t)r * ldx;
+    float ss = 0.f;
+    for (int c = lane * 4; c < cols; c += 128) {
+      float4 v = *reinterpret_cast<const float4*>(xr + c);
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ss = warp_sum(ss);
+    const float inv = normalize ? 1.0f / fmaxf(sqrtf(ss), 1e-12f) : 1.0f;
+    for (int c = lane * 4; c < cols; c += 128) {
+      float4 v = *reinterpret_cast<const float4*>(xr + c);
+      v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+      store_act(y, y_bf16, (size_t)r * ldy + c, v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm, TF style (sa_m4c.py:1016-1028): y = g * (x-u)/sqrt(var+eps) + b, biased variance.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowThreads)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     float eps, float* __restrict__ y, void* __restrict__ y2, int y2_bf16, int rows, int cols) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < rows; r += nwarps) {
+    float4 v[kMaxVec];
+    int nvec = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      int c = 4 * (lane + 32 * i);
+      if (c < cols) { v[i] = *reinterpret_cast<const float4*>(x + (size_t)r * cols + c); nvec = i + 1; }
+      else v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // lanes past the row end contribute zeros to the sums; the variance pass must skip them
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
+    s = warp_sum(s);
+    const float mean = s / cols;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) if (i < nvec) {
+      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + b * b + c * c + d * d;
+    }
+    q = warp_sum(q);
+    const float rstd = 1.0f / sqrtf(q / cols + eps);
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) if (i < nvec) {
+      int c = 4 * (lane + 32 * i);
+      float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+      float4 o;
+      o.x = g.x * ((v[i].x - mean) * rstd) + b.x;
+      o.y = g.y * ((v[i].y - mean) * rstd) + b.y;
+      o.z = g.z * ((v[i].z - mean) * rstd) + b.z;
+      o.w = g.w * ((v[i].w - mean) * rstd) + b.w;
+      if (y) *reinterpret_cast<float4*>(y + (size_t)r * cols + c) = o;
+      if (y2) store_act(y2, y2_bf16, (size_t)r * cols + c, o);
+    }
+  }
+}
+
+// dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)); dgamma += dy*xhat; dbeta += dy.
+// Optional second output dxd = dropout_mask(dx) in the activation dtype (the gradient of the dense
+// output that sits under dropout in BertSelfOutput / BertOutput) and dbias += colsum(dxd).
+__global__ void __launch_bounds__(kRowThreads)
+layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                     float eps, float* __restrict__ dx, void* __restrict__ dxd, int dxd_bf16, uint32_t thresh,
+                     float scale, unsigned long long seed, unsigned long long off, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, float* __restrict__ dbias, int rows, int cols) {
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * (kRowThreads / 32) + wib;
+  const int nwarps = gridDim.x * (kRowThreads / 32);
+  float4 ag[kMaxVec], ab[kMaxVec], ad[kMaxVec];
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) ag[i] = ab[i] = ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint64_t row_groups = (uint64_t)((cols + 3) >> 2);
+  for (int r = warp; r < rows; r += nwarps) {
+    float4 v[kMaxVec], g[kMaxVec];
+    int nvec = 0;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      int c = 4 * (lane + 32 * i);
+      if (c < cols) { v[i] = *reinterpret_cast<const float4*>(x + (size_t)r * cols + c); nvec = i + 1; }
+      else v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+    s = warp_sum(s);
+    const float mean = s / cols;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) if (i < nvec) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+    q = warp_sum(q);
+    const float rstd = 1.0f / sqrtf(q / cols + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) if (i < nvec) {
+      int c = 4 * (lane + 32 * i);
+      float4 d = *reinterpret_cast<const float4*>(dy + (size_t)r * cols + c);
+      float4 gm = *reinterpret_cast<const float4*>(gamma + c);
+      v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;   // xhat
+      ag[i].x += d.x * v[i].x; ag[i].y += d.y * v[i].y; ag[i].z += d.z * v[i].z; ag[i].w += d.w * v[i].w;
+      ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+      g[i] = make_float4(gm.x * d.x, gm.y * d.y, gm.z * d.z, gm.w * d.w);
+      s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+      s2 += g[i].x * v[i].x + g[i].y * v[i].y + g[i].z * v[i].z + g[i].w * v[i].w;
+    }
+    s1 = warp_sum(s1) / cols;
+    s2 = warp_sum(s2) / cols;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) if (i < nvec) {
+      int c = 4 * (lane + 32 * i);
+      float4 o;
+      o.x = rstd * (g[i].x - s1 - v[i].x * s2);
+      o.y = rstd * (g[i].y - s1 - v[i].y * s2);
+      o.z = rstd * (g[i].z - s1 - v[i].z * s2);
+      o.w = rstd * (g[i].w - s1 - v[i].w * s2);
+      if (dx) *reinterpret_cast<float4*>(dx + (size_t)r * cols + c) = o;
+      if (dxd || dbias) {
+        float4 od = drop4(o, thresh, scale, seed, off, (uint64_t)r * row_groups + (uint64_t)(c >> 2));
+        if (dxd) store_act(dxd, dxd_bf16, (size_t)r * cols + c, od);
+        ad[i].x += od.x; ad[i].y += od.y; ad[i].z += od.z; ad[i].w += od.w;
+      }
+    }
+  }
+  // block reduction of the per-column partials, then one atomic per column per block
+  __shared__ float red[kRowThreads / 32][1024 + 4];
+  float* outs[3] = {dgamma, dbeta, dbias};
+#pragma unroll 1
+  for (int k = 0; k < 3; ++k) {
+    if (!outs[k]) continue;  // uniform
+    float4* src = k == 0 ? ag : (k == 1 ? ab : ad);
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      int c = 4 * (lane + 32 * i);
+      if (c < cols) *reinterpret_cast<float4*>(&red[wib][c]) = src[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < cols; c += kRowThreads) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kRowThreads / 32; ++w) t += red[w][c];
+      atomicAdd(outs[k] + c, t);
+    }
+    __syncthreads();
+  }
+}
+
+// out = dropout(a (+ b)); same kernel gives the backward (a = dout, b = null).
+__global__ void dropout_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                                   void* __restrict__ out2, int out2_bf16, int rows, int cols, uint32_t thresh,
+                                   float scale, unsigned long long seed, unsigned long long off) {
+  const int c4 = cols >> 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)rows * c4; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i / c4, c = (i % c4) * 4;
+    float4 v = *reinterpret_cast<const float4*>(a + r * cols + c);
+    if (b) {
+      float4 w = *reinterpret_cast<const float4*>(b + r * cols + c);
+      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
+    v = drop4(v, thresh, scale, seed, off, r * (uint64_t)c4 + (c >> 2));
+    if (out) *reinterpret_cast<float4*>(out + r * cols + c) = v;
+    if (out2) store_act(out2, out2_bf16, r * cols + c, v);
+  }
+}
+
+// out[c] += sum_r x[r, c]
+__global__ void colsum_kernel(const void* __restrict__ x, int x_bf16, long long ld, int rows, int cols,
+                              float* __restrict__ out) {
+  // block = 256 threads = 64 column-quads x 4 row lanes
+  const int cq = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int rl = threadIdx.x >> 6;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (cq * 4 < cols) {
+    for (int r = blockIdx.y * 4 + rl; r < rows; r += gridDim.y * 4) {
+      float4 v = load_act(x, x_bf16, (size_t)r * ld + cq * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  __shared__ float4 red[4][64];
+  red[rl][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (rl == 0 && cq * 4 < cols) {
+    float4 t = red[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) { float4 u = red[k][threadIdx.x]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+    atomicAdd(out + cq * 4 + 0, t.x); atomicAdd(out + cq * 4 + 1, t.y);
+    atomicAdd(out + cq * 4 + 2, t.z); atomicAdd(out + cq * 4 + 3, t.w);
+  }
+}
+
+// generic (any cols / ld / alignment) column sum: one warp per column
+__global__ void colsum_scalar_kernel(const void* __restrict__ x, int x_bf16, long long ld, int rows, int cols,
+                                     float* __restrict__ out) {
+  const int col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (col >= cols) return;
+  float acc = 0.f;
+  for (int r = lane; r < rows; r += 32) {
+    const size_t i = (size_t)r * ld + col;
+    acc += x_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[i]) : reinterpret_cast<const float*>(x)[i];
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) atomicAdd(out + col, acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row-LN helpers for the embedding blocks (warp per row, 768-wide typical)
+// ---------------------------------------------------------------------------------------------
+struct RowLN {
+  float4 xh[kMaxVec];  // xhat
+  float rstd;
+  int nvec;
+};
+
+__device__ __forceinline__ void row_ln_forward(float4* v, int cols, int lane, float eps, RowLN& st) {
+  float s = 0.f;
+  st.nvec = 0;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    if (4 * (lane + 32 * i) < cols) { st.nvec = i + 1; s += v[i].x + v[i].y + v[i].z + v[i].w; }
+  }
+  s = warp_sum(s);
+  const float mean = s / cols;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) if (i < st.nvec) {
+    st.xh[i] = make_float4(v[i].x - mean, v[i].y - mean, v[i].z - mean, v[i].w - mean);
+    q += st.xh[i].x * st.xh[i].x + st.xh[i].y * st.xh[i].y + st.xh[i].z * st.xh[i].z + st.xh[i].w * st.xh[i].w;
+  }
+  q = warp_sum(q);
+  st.rstd = 1.0f / sqrtf(q / cols + eps);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) if (i < st.nvec) {
+    st.xh[i].x *= st.rstd; st.xh[i].y *= st.rstd; st.xh[i].z *= st.rstd; st.xh[i].w *= st.rstd;
+  }
+}
+
+// given dy (per lane vectors) -> dx in place; accumulates dgamma/dbeta with atomics
+__device__ __forceinline__ void row_ln_backward(float4* d, const RowLN& st, const float* gamma, float* dgamma,
+                                                float* dbeta, int cols, int lane) {
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) if (i < st.nvec) {
+    int c = 4 * (lane + 32 * i);
+    float4 gm = *reinterpret_cast<const float4*>(gamma + c);
+    atomicAdd(dgamma + c + 0, d[i].x * st.xh[i].x); atomicAdd(dgamma + c + 1, d[i].y * st.xh[i].y);
+    atomicAdd(dgamma + c + 2, d[i].z * st.xh[i].z); atomicAdd(dgamma + c + 3, d[i].w * st.xh[i].w);
+    atomicAdd(dbeta + c + 0, d[i].x); atomicAdd(dbeta + c + 1, d[i].y);
+    atomicAdd(dbeta + c + 2, d[i].z); atomicAdd(dbeta + c + 3, d[i].w);
+    d[i] = make_float4(gm.x * d[i].x, gm.y * d[i].y, gm.z * d[i].z, gm.w * d[i].w);
+    s1 += d[i].x + d[i].y + d[i].z + d[i].w;
+    s2 += d[i].x * st.xh[i].x + d[i].y * st.xh[i].y + d[i].z * st.xh[i].z + d[i].w * st.xh[i].w;
+  }
+  s1 = warp_sum(s1) / cols;
+  s2 = warp_sum(s2) / cols;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) if (i < st.nvec) {
+    d[i].x = st.rstd * (d[i].x - s1 - st.xh[i].x * s2);
+    d[i].y = st.rstd * (d[i].y - s1 - st.xh[i].y * s2);
+    d[i].z = st.rstd * (d[i].z - s1 - st.xh[i].z * s2);
+    d[i].w = st.rstd * (d[i].w - s1 - st.xh[i].w * s2);
+  }
+}
+
+__device__ __forceinline__ void atomic_add4(float* p, float4 v) {
+  atomicAdd(p + 0, v.x); atomicAdd(p + 1, v.y); atomicAdd(p + 2, v.z); atomicAdd(p + 3, v.w);
+}
+
+// TextBert embeddings (sa_m4c.py:383 -> BertEmbeddings): dropout(LN(word[id] + pos[t] + type[0]))
+__global__ void __launch_bounds__(kRowThreads)
+bert_embed_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ word, const float* __restrict__ pos,
+                      const float* __restrict__ type, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      float eps, float* __restrict__ out, void* __restrict__ out2, int out2_bf16, int rows, int T,
+                      int cols, uint32_t thresh, float scale, unsigned long long seed, unsigned long long off) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < rows; r += nwarps) {
+    const long long id = ids[r];
+    const int t = r % T;
+    float4 v[kMaxVec];
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      int c = 4 * (lane + 32 * i);
+      if (c < cols) {
+        float4 a = *reinterpret_cast<const float4*>(word + (size_t)id * cols + c);
+        float4 b = *reinterpret_cast<const float4*>(pos + (size_t)t * cols + c);
+        float4 d = *reinterpret_cast<const float4*>(type + c);
+        v[i] = make_float4(a.x + b.x + d.x, a.y + b.y + d.y, a.z + b.z + d.z, a.w + b.w + d.w);
+      }
+    }
+    RowLN st;
+    row_ln_forward(v, cols, lane, eps, st);
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) if (i < st.nvec) {
+      int c = 4 * (lane + 32 * i);
+      float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+      float4 o = make_float4(g.x * st.xh[i].x + b.x, g.y * st.xh[i].y + b.y, g.z * st.xh[i].z + b.z, g.w * st.xh[i].w + b.w);
+      o = drop4(o, thresh, scale, seed, off, (uint64_t)r * (cols >> 2) + (c >> 2));
+      *reinterpret_cast<float4*>(out + (size_t)r * cols + c) = o;
+      if (out2) store_act(out2, out2_bf16, (size_t)r * cols + c, o);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kRowThreads)
+bert_embed_bwd_kernel(const float* __restrict__ dout, const long long* __restrict__ ids, const float* __restrict__ word,
+                      const float* __restrict__ pos, const float* __restrict__ type, const float* __restrict__ gamma,
+                      float eps, float* __restrict__ dword, float* __restrict__ dpos, float* __restrict__ dtype,
+                      float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int T, int cols, uint32_t thresh,
+                      float scale, unsigned long long seed, unsigned long long off) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < rows; r += nwarps) {
+    const long long id = ids[r];
+    const int t = r % T;
+    float4 v[kMaxVec], d[kMaxVec];
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      int c = 4 * (lane + 32 * i);
+      if (c < cols) {
+        float4 a = *reinterpret_cast<const float4*>(word + (size_t)id * cols + c);
+        float4 b = *reinterpret_cast<const float4*>(pos + (size_t)t * cols + c);
+        float4 e = *reinterpret_cast<const float4*>(type + c);
+        v[i] = make_float4(a.x + b.x + e.x, a.y + b.y + e.y, a.z + b.z + e.z, a.w + b.w + e.w);
+        d[i] = drop4(*reinterpret_cast<const float4*>(dout + (size_t)r * cols + c), thresh, scale, seed, off,
+                     (uint64_t)r * (cols >> 2) + (c >> 2));
+      }
+    }
+    RowLN st;
+    row_ln_forward(v, cols, lane, eps, st);
+    row_ln_backward(d, st, gamma, dgamma, dbeta, cols, lane);
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) if (i < st.nvec) {
+      int c = 4 * (lane + 32 * i);
+      if (id != 0) atomic_add4(dword + (size_t)id * cols + c, d[i]);  // padding_idx = 0 gets no gradient
+      atomic_add4(dpos + (size_t)t * cols + c, d[i]);
+      atomic_add4(dtype + c, d[i]);
+    }
+  }
+}
+
+// PrevPredEmbeddings (sa_m4c.py:919-948): row (b,t): idx = prev[b,t];
+//   raw = idx < V ? LN_ans(cls_w[idx]) : LN_ocr(ocr_in[b, idx-V]);  out = raw + dropout(LN_emb(pos[t] + type[idx>=V]))
+struct PrevPredParams {
+  const long long* prev; const float* cls_w; const float* ocr_in; const float* pos; const float* type;
+  const float* ans_g; const float* ans_b; const float* ocr_g; const float* ocr_b; const float* emb_g; const float* emb_b;
+  float eps; int B, D, V, R, cols; uint32_t thresh; float scale; unsigned long long seed, off;
+};
+
+__global__ void __launch_bounds__(kRowThreads)
+prevpred_fwd_kernel(PrevPredParams p, float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int cols = p.cols;
+  for (int r = warp; r < p.B * p.D; r += nwarps) {
+    const int b = r / p.D, t = r % p.D;
+    long long idx = p.prev[r];
+    idx = idx < 0 ? 0 : (idx >= p.V + p.R ? p.V + p.R - 1 : idx);   // reference would raise IndexError
+    const bool is_ocr = idx >= p.V;
+    const float* src = is_ocr ? p.ocr_in + ((size_t)b * p.R + (idx - p.V)) * cols : p.cls_w + (size_t)idx * cols;
+    const float* g1 = is_ocr ? p.ocr_g : p.ans_g;
+    const float* b1 = is_ocr ? p.ocr_b : p.ans_b;
+    float4 v[kMaxVec], e[kMaxVec];
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      int c = 4 * (lane + 32 * i);
+      if (c < cols) {
+        v[i] = *reinterpret_cast<const float4*>(src + c);
+        float4 a = *reinterpret_cast<const float4*>(p.pos + (size_t)t * cols + c);
+        float4 d = *reinterpret_cast<const float4*>(p.type + (size_t)(is_ocr ? 1 : 0) * cols + c);
+        e[i] = make_float4(a.x + d.x, a.y + d.y, a.z + d.z, a.w + d.w);
+      }
+    }
+    RowLN s1, s2;
+    row_ln_forward(v, cols, lane, p.eps, s1);
+    row_ln_forward(e, cols, lane, p.eps, s2);
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) if (i < s1.nvec) {
+      int c = 4 * (lane + 32 * i);
+      float4 ga = *reinterpret_cast<const float4*>(g1 + c), ba = *reinterpret_cast<const float4*>(b1 + c);
+      float4 ge = *reinterpret_cast<const float4*>(p.emb_g + c), be = *reinterpret_cast<const float4*>(p.emb_b + c);
+      float4 o2 = make_float4(ge.x * s2.xh[i].x + be.x, ge.y * s2.xh[i].y + be.y, ge.z * s2.xh[i].z + be.z, ge.w * s2.xh[i].w + be.w);
+      o2 = drop4(o2, p.thresh, p.scale, p.seed, p.off, (uint64_t)r * (cols >> 2) + (c >> 2));
+      float4 o = make_float4(ga.x * s1.xh[i].x + ba.x + o2.x, ga.y * s1.xh[i].y + ba.y + o2.y,
+                             ga.z * s1.xh[i].z + ba.z + o2.z, ga.w * s1.xh[i].w + ba.w + o2.w);
+      *reinterpret_cast<float4*>(out + (size_t)r * cols + c) = o;
+    }
+  }
+}
+
+struct PrevPredGrads {
+  float* d_cls_w; float* d_ocr_in; float* d_pos; float* d_type;
+  float* d_ans_g; float* d_ans_b; float* d_ocr_g; float* d_ocr_b; float* d_emb_g; float* d_emb_b;
+};
+
+__global__ void __launch_bounds__(kRowThreads)
+prevpred_bwd_kernel(PrevPredParams p, const float* __restrict__ dout, PrevPredGrads g) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int cols = p.cols;
+  for (int r = warp; r < p.B * p.D; r += nwarps) {
+    const int b = r / p.D, t = r % p.D;
+    long long idx = p.prev[r];
+    idx = idx < 0 ? 0 : (idx >= p.V + p.R ? p.V + p.R - 1 : idx);   // reference would raise IndexError
+    const bool is_ocr = idx >= p.V;
+    const size_t src_off = is_ocr ? ((size_t)b * p.R + (idx - p.V)) * cols : (size_t)idx * cols;
+    const float* src = (is_ocr ? p.ocr_in : p.cls_w) + src_off;
+    float4 v[kMaxVec], e[kMaxVec], d1[kMaxVec], d2[kMaxVec];
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      int c = 4 * (lane + 32 * i);
+      if (c < cols) {
+        v[i] = *reinterpret_cast<const float4*>(src + c);
+        float4 a = *reinterpret_cast<const float4*>(p.pos + (size_t)t * cols + c);
+        float4 d = *reinterpret_cast<const float4*>(p.type + (size_t)(is_ocr ? 1 : 0) * cols + c);
+        e[i] = make_float4(a.x + d.x, a.y + d.y, a.z + d.z, a.w + d.w);
+        d1[i] = *reinterpret_cast<const float4*>(dout + (size_t)r * cols + c);
+        d2[i] = drop4(d1[i], p.thresh, p.scale, p.seed, p.off, (uint64_t)r * (cols >> 2) + (c >> 2));
+      }
+    }
+    RowLN s1, s2;
+    row_ln_forward(v, cols, lane, p.eps, s1);
+    row_ln_forward(e, cols, lane, p.eps, s2);
+    row_ln_backward(d1, s1, is_ocr ? p.ocr_g : p.ans_g, is_ocr ? g.d_ocr_g : g.d_ans_g, is_ocr ? g.d_ocr_b : g.d_ans_b, cols, lane);
+    row_ln_backward(d2, s2, p.emb_g, g.d_emb_g, g.d_emb_b, cols, lane);
+    float* dsrc = (is_ocr ? g.d_ocr_in : g.d_cls_w) + src_off;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) if (i < s1.nvec) {
+      int c = 4 * (lane + 32 * i);
+      atomic_add4(dsrc + c, d1[i]);
+      atomic_add4(g.d_pos + (size_t)t * cols + c, d2[i]);
+      atomic_add4(g.d_type + (size_t)(is_ocr ? 1 : 0) * cols + c, d2[i]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pointer network scores (sa_m4c.py:878-897): out[b,t,V+r] = q[b,t,:].k[b,r,:]/sqrt(dq) + (1-mask[b,r])*-1e4
+// ---------------------------------------------------------------------------------------------
+__global__ void ptr_scores_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                      const long long* __restrict__ mask, float* __restrict__ out, long long ldo,
+                                      int col_off, int B, int D, int R, int dq, float inv_sqrt) {
+  // one warp per (b, t, r)
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int total = B * D * R;
+  if (warp >= total) return;
+  const int b = warp / (D * R), t = (warp / R) % D, r = warp % R;
+  const float* qr = q + ((size_t)b * D + t) * dq;
+  const float* kr = k + ((size_t)b * R + r) * dq;
+  float s = 0.f;
+  for (int c = lane * 4; c < dq; c += 128) {
+    float4 a = *reinterpret_cast<const float4*>(qr + c), w = *reinterpret_cast<const float4*>(kr + c);
+    s += a.x * w.x + a.y * w.y + a.z * w.z + a.w * w.w;
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    float m = (1.0f - (float)mask[(size_t)b * R + r]) * -10000.0f;
+    out[((size_t)b * D + t) * ldo + col_off + r] = s * inv_sqrt + m;
+  }
+}
+
+// dq[b,t,:] = inv * sum_r ds[b,t,r] k[b,r,:] ; dk[b,r,:] = inv * sum_t ds[b,t,r] q[b,t,:]
+__global__ void ptr_scores_bwd_kernel(const float* __restrict__ ds, long long ldds, int col_off,
+                                      const float* __restrict__ q, const float* __restrict__ k, float* __restrict__ dq_,
+                                      float* __restrict__ dk_, int B, int D, int R, int dq, float inv_sqrt) {
+  // one warp per output row: first B*D rows of dq then B*R rows of dk
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nq = B * D, nk = B * R;
+  if (warp >= nq + nk) return;
+  if (warp < nq) {
+    const int b = warp / D;
+    const float* dsr = ds + (size_t)warp * ldds + col_off;
+    for (int c = lane * 4; c < dq; c += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < R; ++r) {
+        float w = dsr[r] * inv_sqrt;
+        float4 kv = *reinterpret_cast<const float4*>(k + ((size_t)b * R + r) * dq + c);
+        acc.x += w * kv.x; acc.y += w * kv.y; acc.z += w * kv.z; acc.w += w * kv.w;
+      }
+      *reinterpret_cast<float4*>(dq_ + (size_t)warp * dq + c) = acc;
+    }
+  } else {
+    const int row = warp - nq, b = row / R, r = row % R;
+    for (int c = lane * 4; c < dq; c += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int t = 0; t < D; ++t) {
+        float w = ds[((size_t)b * D + t) * ldds + col_off + r] * inv_sqrt;
+        float4 qv = *reinterpret_cast<const float4*>(q + ((size_t)b * D + t) * dq + c);
+        acc.x += w * qv.x; acc.y += w * qv.y; acc.z += w * qv.z; acc.w += w * qv.w;
+      }
+      *reinterpret_cast<float4*>(dk_ + (size_t)row * dq + c) = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Masked BCE-with-logits (sam/task_utils.py:19-30), forward value and d(loss)/d(scores) in one pass:
+//   loss = sum_{b,t,v} mask[b,t] * bce(x, y) / max(sum(mask), 1)
+// ---------------------------------------------------------------------------------------------
+__global__ void bce_loss_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ mask,
+                                float* __restrict__ dx, float* __restrict__ loss_sum, const float* __restrict__ mask_sum,
+                                long long n, int ncls) {
+  float acc = 0.f;
+  const float inv_cnt = 1.0f / fmaxf(*mask_sum, 1.0f);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * blockDim.x) {
+    const float m = mask[i / ncls];
+    const float xv = x[i], yv = y[i];
+    const float l = fmaxf(xv, 0.f) - xv * yv + log1pf(__expf(-fabsf(xv)));
+    acc += m * l;
+    if (dx) dx[i] = m * (1.0f / (1.0f + __expf(-xv)) - yv) * inv_cnt;
+  }
+  acc = warp_sum(acc);
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) atomicAdd(loss_sum, t * inv_cnt);
+  }
+}
+
+__global__ void sum_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  float acc = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * blockDim.x) acc += x[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+__global__ void scale_kernel(float* __restrict__ x, long long n, const float* __restrict__ s) {
+  const float v = *s;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * blockDim.x) x[i] *= v;
+}
+
+static inline int grid_for(long long work, int per_block) {
+  long long g = (work + per_block - 1) / per_block;
+  int cap = 148 * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+static inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace samk
+
+using namespace samk;
+
+#define SAMK_REQUIRE(cond, msg) \
+  do { if (!(cond)) { set_error("%s: %s", __func__, msg); return SAMK_ERR_ARG; } } while (0)
+
+extern "C" {
+
+int samk_cast_bf16(const float* x, long long ldx, void* y, long long ldy, int rows, int cols, void* stream) {
+  SAMK_REQUIRE(x && y && rows >= 0 && cols >= 0, "bad argument");
+  SAMK_REQUIRE(cols % 4 == 0 && ldy % 4 == 0 && ((uintptr_t)y & 7) == 0, "cols/ldy must be multiples of 4");
+  if (!rows || !cols) return SAMK_OK;
+  cast_kernel<<<grid_for((long long)rows * cols / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, (__nv_bfloat16*)y, ldy, rows, cols, (ldx % 4 == 0 && al16(x)) ? 1 : 0);
+  return check_launch(__func__);
+}
+
+int samk_split3_bf16(const float* x, long long ldx, void* y, long long ldy, int rows, int cols, int order,
+                     int along_rows, void* stream) {
+  SAMK_REQUIRE(x && y && rows >= 0 && cols >= 0, "bad argument");
+  SAMK_REQUIRE(cols % 4 == 0 && ldy % 4 == 0 && ((uintptr_t)y & 7) == 0, "cols/ldy must be multiples of 4");
+  if (!rows || !cols) return SAMK_OK;
+  split3_kernel<<<grid_for((long long)rows * cols / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, (__nv_bfloat16*)y, ldy, rows, cols, order, along_rows, (ldx % 4 == 0 && al16(x)) ? 1 : 0);
+  return check_launch(__func__);
+}
+
+int samk_l2norm(const float* x, long long ldx, void* y, long long ldy, int y_dtype, int rows, int cols, int normalize,
+                void* stream) {
+  SAMK_REQUIRE(x && y && rows >= 0 && cols >= 0, "bad argument");
+  SAMK_REQUIRE(cols % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && al16(x) && ((uintptr_t)y & 7) == 0, "cols/ld must be multiples of 4");
+  if (!rows || !cols) return SAMK_OK;
+  l2norm_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, y_dtype == SAMK_DT_BF16, rows, cols, normalize);
+  return check_launch(__func__);
+}
+
+int samk_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y, void* y2,
+                       int y2_dtype, int rows, int cols, void* stream) {
+  SAMK_REQUIRE(x && gamma && beta && (y || y2) && rows >= 0, "bad argument");
+  SAMK_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 1024, "cols must be a multiple of 4, <= 1024");
+  if (!rows) return SAMK_OK;
+  layernorm_fwd_kernel<<<grid_for(rows, 8), kRowThreads, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, y, y2, y2_dtype == SAMK_DT_BF16, rows, cols);
+  return check_launch(__func__);
+}
+
+int samk_layernorm_bwd(const float* dy, const float* x, const float* gamma, float eps, float* dx, void* dxd,
+                       int dxd_dtype, float drop_p, unsigned long long seed, unsigned long long offset, float* dgamma,
+                       float* dbeta, float* dbias, int rows, int cols, void* stream) {
+  SAMK_REQUIRE(dy && x && gamma && rows >= 0, "bad argument");
+  SAMK_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 1024, "cols must be a multiple of 4, <= 1024");
+  if (!rows) return SAMK_OK;
+  int grid = grid_for(rows, 8 * 8);
+  if (grid > 296) grid = 296;
+  layernorm_bwd_kernel<<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(
+      dy, x, gamma, eps, dx, dxd, dxd_dtype == SAMK_DT_BF16, drop_p > 0.f ? drop_threshold(drop_p) : 0u,
+      drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f, seed, offset, dgamma, dbeta, dbias, rows, cols);
+  return check_launch(__func__);
+}
+
+int samk_dropout_add(const float* a, const float* b, float* out, void* out2, int out2_dtype, int rows, int cols,
+                     float drop_p, unsigned long long seed, unsigned long long offset, void* stream) {
+  SAMK_REQUIRE(a && (out || out2) && rows >= 0 && cols >= 0 && cols % 4 == 0, "bad argument");
+  if (!rows || !cols) return SAMK_OK;
+  dropout_add_kernel<<<grid_for((long long)rows * cols / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+      a, b, out, out2, out2_dtype == SAMK_DT_BF16, rows, cols, drop_p > 0.f ? drop_threshold(drop_p) : 0u,
+      drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f, seed, offset);
+  return check_launch(__func__);
+}
+
+int samk_colsum(const void* x, int x_dtype, long long ld, int rows, int cols, float* out, void* stream) {
+  SAMK_REQUIRE(x && out && rows >= 0 && cols >= 0, "bad argument");
+  if (!rows || !cols) return SAMK_OK;
+  const bool bf = x_dtype == SAMK_DT_BF16;
+  if (cols % 4 || ld % 4 || ((uintptr_t)x & (bf ? 7 : 15))) {
+    colsum_scalar_kernel<<<(cols * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, bf, ld, rows, cols, out);
+    return check_launch(__func__);
+  }
+  dim3 grid((cols / 4 + 63) / 64, 64);
+  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_dtype == SAMK_DT_BF16, ld, rows, cols, out);
+  return check_launch(__func__);
+}
+
+int samk_bert_embed_fwd(const long long* ids, const float* word, const float* pos, const float* type,
+                        const float* gamma, const float* beta, float eps, float* out, void* out2, int out2_dtype,
+                        int rows, int T, int cols, float drop_p, unsigned long long seed, unsigned long long offset,
+                        void* stream) {
+  SAMK_REQUIRE(ids && word && pos && type && gamma && beta && out, "null pointer");
+  SAMK_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 1024 && T > 0, "bad size");
+  if (!rows) return SAMK_OK;
+  bert_embed_fwd_kernel<<<grid_for(rows, 8), kRowThreads, 0, (cudaStream_t)stream>>>(
+      ids, word, pos, type, gamma, beta, eps, out, out2, out2_dtype == SAMK_DT_BF16, rows, T, cols,
+      drop_p > 0.f ? drop_threshold(drop_p) : 0u, drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f, seed, offset);
+  return check_launch(__func__);
+}
+
+int samk_bert_embed_bwd(const float* dout, const long long* ids, const float* word, const float* pos, const float* type,
+                        const float* gamma, float eps, float* dword, float* dpos, float* dtype, float* dgamma,
+                        float* dbeta, int rows, int T, int cols, float drop_p, unsigned long long seed,
+                        unsigned long long offset, void* stream) {
+  SAMK_REQUIRE(dout && ids && word && pos && type && gamma && dword && dpos && dtype && dgamma && dbeta, "null pointer");
+  SAMK_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 1024 && T > 0, "bad size");
+  if (!rows) return SAMK_OK;
+  bert_embed_bwd_kernel<<<grid_for(rows, 8), kRowThreads, 0, (cudaStream_t)stream>>>(
+      dout, ids, word, pos, type, gamma, eps, dword, dpos, dtype, dgamma, dbeta, rows, T, cols,
+      drop_p > 0.f ? drop_threshold(drop_p) : 0u, drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f, seed, offset);
+  return check_launch(__func__);
+}
+
+static int fill_prevpred(PrevPredParams& p, const long long* prev, const float* cls_w, const float* ocr_in,
+                         const float* pos, const float* type, const float* const* ln, float eps, int B, int D, int V,
+                         int R, int cols, float drop_p, unsigned long long seed, unsigned long long offset) {
+  p.prev = prev; p.cls_w = cls_w; p.ocr_in = ocr_in; p.pos = pos; p.type = type;
+  p.ans_g = ln[0]; p.ans_b = ln[1]; p.ocr_g = ln[2]; p.ocr_b = ln[3]; p.emb_g = ln[4]; p.emb_b = ln[5];
+  p.eps = eps; p.B = B; p.D = D; p.V = V; p.R = R; p.cols = cols;
+  p.thresh = drop_p > 0.f ? drop_threshold(drop_p) : 0u;
+  p.scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  p.seed = seed; p.off = offset;
+  return 0;
+}
+
+int samk_prevpred_fwd(const long long* prev, const float* cls_w, const float* ocr_in, const float* pos,
+                      const float* type, const float* const* ln6, float eps, float* out, int B, int D, int V, int R,
+                      int cols, float drop_p, unsigned long long seed, unsigned long long offset, void* stream) {
+  SAMK_REQUIRE(prev && cls_w && ocr_in && pos && type && ln6 && out, "null pointer");
+  SAMK_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 1024, "bad size");
+  if (!B || !D) return SAMK_OK;
+  PrevPredParams p;
+  fill_prevpred(p, prev, cls_w, ocr_in, pos, type, ln6, eps, B, D, V, R, cols, drop_p, seed, offset);
+  prevpred_fwd_kernel<<<grid_for((long long)B * D, 8), kRowThreads, 0, (cudaStream_t)stream>>>(p, out);
+  return check_launch(__func__);
+}
+
+int samk_prevpred_bwd(const float* dout, const long long* prev, const float* cls_w, const float* ocr_in,
+                      const float* pos, const float* type, const float* const* ln6, float eps, float* const* grads10,
+                      int B, int D, int V, int R, int cols, float drop_p, unsigned long long seed,
+                      unsigned long long offset, void* stream) {
+  SAMK_REQUIRE(dout && prev && cls_w && ocr_in && pos && type && ln6 && grads10, "null pointer");
+  SAMK_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 1024, "bad size");
+  if (!B || !D) return SAMK_OK;
+  PrevPredParams p;
+  fill_prevpred(p, prev, cls_w, ocr_in, pos, type, ln6, eps, B, D, V, R, cols, drop_p, seed, offset);
+  PrevPredGrads g;
+  g.d_cls_w = grads10[0]; g.d_ocr_in = grads10[1]; g.d_pos = grads10[2]; g.d_type = grads10[3];
+  g.d_ans_g = grads10[4]; g.d_ans_b = grads10[5]; g.d_ocr_g = grads10[6]; g.d_ocr_b = grads10[7];
+  g.d_emb_g = grads10[8]; g.d_emb_b = grads10[9];
+  prevpred_bwd_kernel<<<grid_for((long long)B * D, 8), kRowThreads, 0, (cudaStream_t)stream>>>(p, dout, g);
+  return check_launch(__func__);
+}
+
+int samk_ptr_scores_fwd(const float* q, const float* k, const long long* ocr_mask, float* out, long long ldo,
+                        int col_off, int B, int D, int R, int dq, void* stream) {
+  SAMK_REQUIRE(q && k && ocr_mask && out && dq % 4 == 0, "bad argument");
+  long long warps = (long long)B * D * R;
+  if (!warps) return SAMK_OK;
+  ptr_scores_fwd_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(q, k, ocr_mask, out, ldo, col_off, B, D, R, dq, 1.0f / sqrtf((float)dq));
+  return check_launch(__func__);
+}
+
+int samk_ptr_scores_bwd(const float* dscores, long long ldds, int col_off, const float* q, const float* k, float* dq_,
+                        float* dk_, int B, int D, int R, int dq, void* stream) {
+  SAMK_REQUIRE(dscores && q && k && dq_ && dk_ && dq % 4 == 0, "bad argument");
+  long long warps = (long long)B * (D + R);
+  if (!warps) return SAMK_OK;
+  ptr_scores_bwd_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(dscores, ldds, col_off, q, k, dq_, dk_, B, D, R, dq, 1.0f / sqrtf((float)dq));
+  return check_launch(__func__);
+}
+
+int samk_bce_loss(const float* scores, const float* targets, const float* loss_mask, float* dscores, float* loss_out,
+                  float* scratch, int rows, int ncls, void* stream) {
+  SAMK_REQUIRE(scores && targets && loss_mask && loss_out && scratch, "null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(loss_out, 0, sizeof(float), s);
+  cudaMemsetAsync(scratch, 0, sizeof(float), s);
+  if (!rows || !ncls) return SAMK_OK;
+  sum_kernel<<<grid_for(rows, 256), 256, 0, s>>>(loss_mask, rows, scratch);
+  bce_loss_kernel<<<grid_for((long long)rows * ncls, 1024), 256, 0, s>>>(scores, targets, loss_mask, dscores, loss_out, scratch, (long long)rows * ncls, ncls);
+  return check_launch(__func__);
+}
+
+int samk_scale_inplace(float* x, long long n, const float* scale_dev, void* stream) {
+  SAMK_REQUIRE(x && scale_dev, "null pointer");
+  if (!n) return SAMK_OK;
+  scale_kernel<<<grid_for(n, 1024), 256, 0, (cudaStream_t)stream>>>(x, n, scale_dev);
+  return check_launch(__func__);
+}
+
+}  // extern "C"

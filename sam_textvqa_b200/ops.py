@@ -1,0 +1,639 @@
+"""Operators of the SA-M4C hot path: thin Python over the C ABI of libsamk.so.
+
+Every function here launches hand-written CUDA kernels on the caller's current device and stream
+(`torch.cuda.current_stream()`); PyTorch only owns the memory and the autograd tape.  There is no
+fallback: CPU tensors are rejected and a missing library raises.
+
+Precision modes (``set_precision`` / env ``SAMK_PRECISION``):
+  "bf16"    activations that feed a contraction are stored in bf16, tcgen05 bf16 MMAs, fp32
+            accumulation / residual stream / LayerNorm / softmax.  The throughput mode.
+  "bf16x3"  activations stay fp32; every contraction runs as a 3-term bf16 split
+            (A_hi*B_hi + A_hi*B_lo + A_lo*B_hi, one tcgen05 GEMM over a 3x longer K) and attention
+            runs in exact fp32.  The parity mode: logits within 1e-3 of the fp32 reference.
+"""
+import ctypes
+import math
+import os
+
+import torch
+
+from . import _lib
+from ._lib import DT_BF16, DT_F32, GemmEpilogue, check, lib, ptr, stream_ptr
+
+_PRECISION = os.environ.get("SAMK_PRECISION", "bf16")
+_GEMM_IMPL = int(os.environ.get("SAMK_GEMM_IMPL", "0"))
+_ATTN_IMPL = int(os.environ.get("SAMK_ATTN_IMPL", "0"))
+launch_count = 0  # kernels launched through this module (bench.py reports it)
+
+
+def set_precision(mode):
+    global _PRECISION
+    if mode not in ("bf16", "bf16x3"):
+        raise ValueError("precision must be 'bf16' or 'bf16x3'")
+    _PRECISION = mode
+
+
+def get_precision():
+    return _PRECISION
+
+
+def act_dtype():
+    return torch.bfloat16 if _PRECISION == "bf16" else torch.float32
+
+
+def _dt(t):
+    if t.dtype == torch.bfloat16:
+        return DT_BF16
+    if t.dtype == torch.float32:
+        return DT_F32
+    raise TypeError("unsupported dtype %s" % t.dtype)
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.SamkError("samk ops need CUDA tensors (no CPU path); got a tensor on %s" % t.device)
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+# ---- dropout stream ------------------------------------------------------------------------------
+class _Rng(object):
+    def __init__(self):
+        self.seed = 0x5A17C0DE
+        self.offset = 0
+
+    def next(self):
+        self.offset += 1
+        return self.seed, self.offset
+
+
+_rng = _Rng()
+
+
+def manual_seed(seed):
+    _rng.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    _rng.offset = 0
+
+
+# ---- operand preparation ---------------------------------------------------------------------------
+def _ceil8(n):
+    return (n + 7) // 8 * 8
+
+
+def cast_bf16(x2d):
+    """fp32 [rows, cols] (row stride arbitrary, unit column stride) -> bf16 [rows, ceil8(cols)] buffer."""
+    rows, cols = x2d.shape
+    assert x2d.stride(1) == 1 and cols % 4 == 0
+    y = torch.empty(rows, _ceil8(cols), dtype=torch.bfloat16, device=x2d.device)
+    check(lib().samk_cast_bf16(ptr(x2d), x2d.stride(0), ptr(y), y.stride(0), rows, cols, stream_ptr()), "cast_bf16")
+    _count()
+    return y
+
+
+def _split3(x2d, order, along_rows):
+    rows, cols = x2d.shape
+    assert x2d.stride(1) == 1 and cols % 4 == 0
+    if along_rows:
+        y = torch.empty(3 * rows, _ceil8(cols), dtype=torch.bfloat16, device=x2d.device)
+    else:
+        y = torch.empty(rows, _ceil8(3 * cols), dtype=torch.bfloat16, device=x2d.device)
+    check(lib().samk_split3_bf16(ptr(x2d), x2d.stride(0), ptr(y), y.stride(0), rows, cols, order, along_rows,
+                                 stream_ptr()), "split3")
+    _count()
+    return y
+
+
+class Operand(object):
+    """A GEMM operand ready for the tensor-core kernel: bf16 storage, leading dimension, K multiplier."""
+    __slots__ = ("t", "ld", "kmul")
+
+    def __init__(self, t, ld, kmul):
+        self.t, self.ld, self.kmul = t, ld, kmul
+
+
+def operand(x2d, role, mn_major):
+    """x2d: logical [rows(MN), K] if not mn_major else stored [K, MN].  role 'a' or 'b'."""
+    _cuda(x2d)
+    if x2d.dtype == torch.bfloat16:
+        if _PRECISION != "bf16":
+            raise _lib.SamkError("bf16 activation reached a bf16x3 contraction")
+        assert x2d.stride(1) == 1 and x2d.stride(0) % 8 == 0 and x2d.data_ptr() % 16 == 0
+        return Operand(x2d, x2d.stride(0), 1)
+    if _PRECISION == "bf16":
+        y = cast_bf16(x2d)
+        return Operand(y, y.stride(0), 1)
+    y = _split3(x2d, 0 if role == "a" else 1, 1 if mn_major else 0)
+    return Operand(y, y.stride(0), 3)
+
+
+_weight_cache = {}
+
+
+def weight_operand(params, mn_major):
+    """Cached operand for one weight (or the row-concatenation of several, e.g. fused q|k|v).
+
+    params: list of [n_i, K] fp32 parameters.  The cache is keyed on the parameters' storage and
+    version counters, so an optimizer step (in-place update) invalidates it."""
+    layout = bool(mn_major) and _PRECISION != "bf16"   # plain bf16 copies serve both majors
+    slot = (tuple(p.data_ptr() for p in params), tuple(tuple(p.shape) + tuple(p.stride()) for p in params), layout)
+    stamp = (tuple(p._version for p in params), _PRECISION)
+    hit = _weight_cache.get(slot)
+    if hit is not None and hit[0] == stamp:
+        return hit[1]
+    with torch.no_grad():
+        w = params[0] if len(params) == 1 else torch.cat(list(params), dim=0)
+        op = operand(w.detach(), "b", mn_major)
+    _weight_cache[slot] = (stamp, op)
+    return op
+
+
+def clear_weight_cache():
+    _weight_cache.clear()
+
+
+# ---- GEMM -------------------------------------------------------------------------------------------
+def _pick_split_k(M, N, K, sms=148):
+    tiles = ((M + 127) // 128) * ((N + 255) // 256)
+    if tiles >= sms or K <= 1024:
+        return 1
+    kb = (K + 63) // 64
+    return int(max(1, min(kb // 8, (2 * sms) // tiles)))
+
+
+def gemm(a, a_mn, b, b_mn, M, N, K, out, bias=None, act=0, pre=None, aux=None, drop_p=0.0, drop=None,
+         residual=None, alpha=1.0, accumulate=False, split_k=None):
+    """out[M,N] = epilogue(alpha * A.B^T).  a, b: Operand.  out: fp32/bf16 2-D view (unit column stride)."""
+    assert a.kmul == b.kmul
+    ep = GemmEpilogue()
+    ep.out = out.data_ptr()
+    ep.ldo = out.stride(0)
+    ep.out_dtype = _dt(out)
+    ep.alpha = alpha
+    ep.bias = bias.data_ptr() if bias is not None else None
+    if pre is not None:
+        ep.pre, ep.ldpre, ep.pre_dtype = pre.data_ptr(), pre.stride(0), _dt(pre)
+    ep.act = act
+    if aux is not None:
+        ep.aux, ep.ldaux, ep.aux_dtype = aux.data_ptr(), aux.stride(0), _dt(aux)
+    if drop_p > 0.0:
+        ep.drop_p, ep.drop_seed, ep.drop_offset = drop_p, drop[0], drop[1]
+    if residual is not None:
+        ep.residual, ep.ldres = residual.data_ptr(), residual.stride(0)
+    Kk = K * a.kmul
+    if split_k is None:
+        split_k = _pick_split_k(M, N, Kk) if accumulate else 1
+    ep.atomic_add = 1 if (accumulate or split_k > 1) else 0
+    check(lib().samk_gemm_bf16(ptr(a.t), 1 if a_mn else 0, a.ld, ptr(b.t), 1 if b_mn else 0, b.ld, M, N, Kk,
+                               ctypes.byref(ep), split_k, _GEMM_IMPL, stream_ptr()), "gemm")
+    _count()
+    return out
+
+
+def colsum_into(x2d, out):
+    check(lib().samk_colsum(ptr(x2d), _dt(x2d), x2d.stride(0), x2d.shape[0], x2d.shape[1], ptr(out), stream_ptr()),
+          "colsum")
+    _count()
+
+
+# ---- simple differentiable ops -----------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b with fp32 output (input projections, pointer-net projections)."""
+
+    @staticmethod
+    def forward(ctx, x2d, weight, bias, kdim):
+        _cuda(x2d, weight)
+        M = x2d.shape[0]
+        N = weight.shape[0]
+        K = kdim
+        x_op = operand(x2d[:, :K] if x2d.shape[1] != K else x2d, "a", False)
+        w_op = weight_operand([weight[:, :K]] if weight.shape[1] != K else [weight], False)
+        y = torch.empty(M, N, dtype=torch.float32, device=x2d.device)
+        gemm(x_op, False, w_op, False, M, N, K, y, bias=bias)
+        ctx.save_for_backward(x2d, weight)
+        ctx.dims = (M, N, K)
+        ctx.x_needs_grad = x2d.requires_grad
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, weight = ctx.saved_tensors
+        M, N, K = ctx.dims
+        dy = dy.contiguous()
+        dy_act = dy if _PRECISION != "bf16" else cast_bf16(dy)[:, :N]
+        dy_k = operand(dy_act, "a", False)          # [M, N] K-major for dgrad
+        dy_mn = operand(dy_act, "a", True)          # stored [tokens, N]: MN-major for wgrad
+        xs = x2d[:, :K] if x2d.shape[1] != K else x2d
+        x_mn = operand(xs, "b", True)
+        dx = None
+        if ctx.x_needs_grad:
+            dx = torch.zeros_like(x2d, dtype=torch.float32) if x2d.shape[1] != K else torch.empty(
+                M, K, dtype=torch.float32, device=dy.device)
+            w_op = weight_operand([weight[:, :K]] if weight.shape[1] != K else [weight], True)
+            gemm(dy_k, False, w_op, True, M, K, N, dx[:, :K])
+        dW = torch.zeros_like(weight, dtype=torch.float32)
+        gemm(dy_mn, True, x_mn, True, N, K, M, dW[:, :K], accumulate=True)
+        db = torch.zeros(N, dtype=torch.float32, device=dy.device)
+        colsum_into(dy, db)
+        return dx, dW, db, None
+
+
+def linear(x2d, weight, bias, kdim=None):
+    return LinearFn.apply(x2d, weight, bias, weight.shape[1] if kdim is None else kdim)
+
+
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2d, gamma, beta, eps):
+        _cuda(x2d, gamma, beta)
+        x2d = x2d.contiguous()
+        y = torch.empty_like(x2d)
+        check(lib().samk_layernorm_fwd(ptr(x2d), ptr(gamma), ptr(beta), eps, ptr(y), None, 0, x2d.shape[0],
+                                       x2d.shape[1], stream_ptr()), "layernorm_fwd")
+        _count()
+        ctx.save_for_backward(x2d, gamma)
+        ctx.eps = eps
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, gamma = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(x2d)
+        dg = torch.zeros_like(gamma)
+        db = torch.zeros_like(gamma)
+        check(lib().samk_layernorm_bwd(ptr(dy), ptr(x2d), ptr(gamma), ctx.eps, ptr(dx), None, 0, 0.0, 0, 0, ptr(dg),
+                                       ptr(db), None, x2d.shape[0], x2d.shape[1], stream_ptr()), "layernorm_bwd")
+        _count()
+        return dx, dg, db, None
+
+
+def layer_norm(x2d, gamma, beta, eps):
+    return LayerNormFn.apply(x2d, gamma, beta, eps)
+
+
+class DropoutAddFn(torch.autograd.Function):
+    """dropout(a + b)"""
+
+    @staticmethod
+    def forward(ctx, a, b, p):
+        _cuda(a, b)
+        a = a.contiguous()
+        b = b.contiguous()
+        out = torch.empty_like(a)
+        ctx.p = p
+        ctx.drop = _rng.next() if p > 0 else (0, 0)
+        rows, cols = a.numel() // a.shape[-1], a.shape[-1]
+        check(lib().samk_dropout_add(ptr(a), ptr(b), ptr(out), None, 0, rows, cols, p, ctx.drop[0], ctx.drop[1],
+                                     stream_ptr()), "dropout_add")
+        _count()
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        if ctx.p <= 0:
+            return dout, dout, None
+        d = torch.empty_like(dout)
+        rows, cols = dout.numel() // dout.shape[-1], dout.shape[-1]
+        check(lib().samk_dropout_add(ptr(dout), None, ptr(d), None, 0, rows, cols, ctx.p, ctx.drop[0], ctx.drop[1],
+                                     stream_ptr()), "dropout_bwd")
+        _count()
+        return d, d, None
+
+
+def dropout_add(a, b, p):
+    return DropoutAddFn.apply(a, b, float(p))
+
+
+def l2norm_into(x3d, out2d, col_off, normalize):
+    """out2d[:, col_off:col_off+d] = F.normalize(x) (or a plain copy/cast); no gradient (inputs are data)."""
+    _cuda(x3d, out2d)
+    x2d = x3d.reshape(-1, x3d.shape[-1])
+    assert x2d.stride(1) == 1
+    dst = out2d[:, col_off:col_off + x2d.shape[1]]
+    check(lib().samk_l2norm(ptr(x2d), x2d.stride(0), ptr(dst), out2d.stride(0), _dt(out2d), x2d.shape[0],
+                            x2d.shape[1], 1 if normalize else 0, stream_ptr()), "l2norm")
+    _count()
+
+
+# ---- embeddings ---------------------------------------------------------------------------------------
+class BertEmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, word, pos, type_, gamma, beta, eps, p):
+        _cuda(ids, word)
+        ids = ids.contiguous()
+        B, T = ids.shape
+        d = word.shape[1]
+        out = torch.empty(B * T, d, dtype=torch.float32, device=word.device)
+        ctx.drop = _rng.next() if p > 0 else (0, 0)
+        ctx.p, ctx.eps = p, eps
+        check(lib().samk_bert_embed_fwd(ptr(ids), ptr(word), ptr(pos), ptr(type_), ptr(gamma), ptr(beta), eps,
+                                        ptr(out), None, 0, B * T, T, d, p, ctx.drop[0], ctx.drop[1], stream_ptr()),
+              "bert_embed_fwd")
+        _count()
+        ctx.save_for_backward(ids, word, pos, type_, gamma)
+        return out.view(B, T, d)
+
+    @staticmethod
+    def backward(ctx, dout):
+        ids, word, pos, type_, gamma = ctx.saved_tensors
+        B, T = ids.shape
+        d = word.shape[1]
+        dout = dout.contiguous()
+        dword, dpos, dtype_ = torch.zeros_like(word), torch.zeros_like(pos), torch.zeros_like(type_)
+        dg, db = torch.zeros_like(gamma), torch.zeros_like(gamma)
+        check(lib().samk_bert_embed_bwd(ptr(dout), ptr(ids), ptr(word), ptr(pos), ptr(type_), ptr(gamma), ctx.eps,
+                                        ptr(dword), ptr(dpos), ptr(dtype_), ptr(dg), ptr(db), B * T, T, d, ctx.p,
+                                        ctx.drop[0], ctx.drop[1], stream_ptr()), "bert_embed_bwd")
+        _count()
+        return None, dword, dpos, dtype_, dg, db, None, None
+
+
+class PrevPredFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, prev, cls_w, ocr_in, pos, type_, ag, ab, og, ob, eg, eb, eps, p):
+        _cuda(prev, cls_w, ocr_in)
+        prev = prev.contiguous()
+        ocr_in = ocr_in.contiguous()
+        B, D = prev.shape
+        V, d = cls_w.shape
+        R = ocr_in.shape[1]
+        out = torch.empty(B, D, d, dtype=torch.float32, device=cls_w.device)
+        ctx.drop = _rng.next() if p > 0 else (0, 0)
+        ctx.p, ctx.eps, ctx.dims = p, eps, (B, D, V, R, d)
+        ln6 = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in (ag, ab, og, ob, eg, eb)])
+        check(lib().samk_prevpred_fwd(ptr(prev), ptr(cls_w), ptr(ocr_in), ptr(pos), ptr(type_), ln6, eps, ptr(out),
+                                      B, D, V, R, d, p, ctx.drop[0], ctx.drop[1], stream_ptr()), "prevpred_fwd")
+        _count()
+        ctx.save_for_backward(prev, cls_w, ocr_in, pos, type_, ag, ab, og, ob, eg, eb)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        prev, cls_w, ocr_in, pos, type_, ag, ab, og, ob, eg, eb = ctx.saved_tensors
+        B, D, V, R, d = ctx.dims
+        dout = dout.contiguous()
+        grads = [torch.zeros_like(t) for t in (cls_w, ocr_in, pos, type_, ag, ab, og, ob, eg, eb)]
+        ln6 = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in (ag, ab, og, ob, eg, eb)])
+        g10 = (ctypes.c_void_p * 10)(*[t.data_ptr() for t in grads])
+        check(lib().samk_prevpred_bwd(ptr(dout), ptr(prev), ptr(cls_w), ptr(ocr_in), ptr(pos), ptr(type_), ln6,
+                                      ctx.eps, g10, B, D, V, R, d, ctx.p, ctx.drop[0], ctx.drop[1], stream_ptr()),
+              "prevpred_bwd")
+        _count()
+        return (None,) + tuple(grads) + (None, None)
+
+
+# ---- attention ------------------------------------------------------------------------------------------
+def _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, dctx=None, dqkv=None, delta=None):
+    B, L, H, T, A, D = dims
+    ap = _lib.AttnParams()
+    ap.qkv, ap.ctx, ap.lse = qkv.data_ptr(), ctx_t.data_ptr(), lse.data_ptr()
+    if dctx is not None:
+        ap.dctx, ap.dqkv, ap.delta = dctx.data_ptr(), dqkv.data_ptr(), delta.data_ptr()
+    ap.dtype = _dt(qkv)
+    ap.B, ap.H, ap.head_dim = B, H, 64
+    ap.T, ap.A, ap.D = T, A, D
+    ap.key_valid = valid.data_ptr()
+    ap.rel_bits = rel.data_ptr() if (spatial and rel is not None) else None
+    ap.quadrant_mask = quad_mask if spatial else 0
+    ap.spatial = 1 if spatial else 0
+    ap.scale = 1.0 / math.sqrt(64.0)
+    ap.drop_p = p
+    ap.drop_seed, ap.drop_offset = drop
+    return ap
+
+
+def attention_fwd(qkv, valid, rel, dims, spatial, quad_mask, p, drop):
+    B, L, H, T, A, D = dims
+    ctx_t = torch.empty(B * L, H * 64, dtype=qkv.dtype, device=qkv.device)
+    lse = torch.empty(B, H, L, dtype=torch.float32, device=qkv.device)
+    ap = _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop)
+    check(lib().samk_attn_fwd(ctypes.byref(ap), _ATTN_IMPL, stream_ptr()), "attn_fwd")
+    _count()
+    return ctx_t, lse
+
+
+def attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop):
+    B, L, H, T, A, D = dims
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty_like(lse)
+    ap = _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, dctx, dqkv, delta)
+    check(lib().samk_attn_bwd(ctypes.byref(ap), _ATTN_IMPL, stream_ptr()), "attn_bwd")
+    _count(2)
+    return dqkv
+
+
+# ---- one post-LN BERT block (plain or spatial) -------------------------------------------------------------
+class BertLayerFn(torch.autograd.Function):
+    """BertLayer / SpatialBertLayer (sa_m4c.py:660-684 and the third-party BertLayer):
+       a = LN(dropout(W_o . attn(x) + b_o) + x);  out = LN(dropout(W_2 . gelu(W_1 a + b_1) + b_2) + a)
+
+    params order: q.w q.b k.w k.b v.w v.b  o.w o.b ln1.g ln1.b  i.w i.b  o2.w o2.b ln2.g ln2.b
+    """
+
+    @staticmethod
+    def forward(ctx, x, valid, rel, cfg, *P):
+        (dims, spatial, quad_mask, p_attn, p_hid, eps) = cfg
+        B, L, H, T, A, D = dims
+        qw, qb, kw, kb, vw, vb, ow, ob, g1, b1, iw, ib, o2w, o2b, g2, b2 = P
+        _cuda(x, valid, qw)
+        dev = x.device
+        adt = act_dtype()
+        M, d, F = B * L, x.shape[-1], iw.shape[0]
+        x2 = x.contiguous().view(M, d)
+        drops = [_rng.next() if pp > 0 else (0, 0) for pp in (p_attn, p_hid, p_hid)]
+
+        x_op = operand(x2, "a", False)
+        wqkv = weight_operand([qw, kw, vw], False)
+        bqkv = torch.cat([qb, kb, vb]).detach()
+        qkv = torch.empty(M, 3 * d, dtype=adt, device=dev)
+        gemm(x_op, False, wqkv, False, M, 3 * d, d, qkv, bias=bqkv)
+        ctx_t, lse = attention_fwd(qkv, valid, rel, dims, spatial, quad_mask, p_attn, drops[0])
+
+        y1 = torch.empty(M, d, dtype=torch.float32, device=dev)
+        gemm(operand(ctx_t, "a", False), False, weight_operand([ow], False), False, M, d, d, y1, bias=ob,
+             drop_p=p_hid, drop=drops[1], residual=x2)
+        a = torch.empty(M, d, dtype=torch.float32, device=dev)
+        a_act = torch.empty(M, d, dtype=adt, device=dev) if adt != torch.float32 else None
+        check(lib().samk_layernorm_fwd(ptr(y1), ptr(g1), ptr(b1), eps, ptr(a), ptr(a_act), DT_BF16, M, d,
+                                       stream_ptr()), "ln1")
+        _count()
+        a_in = a_act if a_act is not None else a
+        h = torch.empty(M, F, dtype=adt, device=dev)
+        g = torch.empty(M, F, dtype=adt, device=dev)
+        gemm(operand(a_in, "a", False), False, weight_operand([iw], False), False, M, F, d, g, bias=ib, act=1, pre=h)
+        y2 = torch.empty(M, d, dtype=torch.float32, device=dev)
+        gemm(operand(g, "a", False), False, weight_operand([o2w], False), False, M, d, F, y2, bias=o2b, drop_p=p_hid,
+             drop=drops[2], residual=a)
+        out = torch.empty(M, d, dtype=torch.float32, device=dev)
+        check(lib().samk_layernorm_fwd(ptr(y2), ptr(g2), ptr(b2), eps, ptr(out), None, 0, M, d, stream_ptr()), "ln2")
+        _count()
+
+        ctx.cfg, ctx.drops = cfg, drops
+        ctx.save_for_backward(x2, valid, rel, qkv, ctx_t, lse, y1, a_in, h, g, y2, *P)
+        return out.view(B, L, d)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (dims, spatial, quad_mask, p_attn, p_hid, eps) = ctx.cfg
+        B, L, H, T, A, D = dims
+        x2, valid, rel, qkv, ctx_t, lse, y1, a_in, h, g, y2 = ctx.saved_tensors[:11]
+        qw, qb, kw, kb, vw, vb, ow, ob, g1, b1, iw, ib, o2w, o2b, g2, b2 = ctx.saved_tensors[11:]
+        dev = dout.device
+        adt = act_dtype()
+        M, d, F = B * L, x2.shape[1], iw.shape[0]
+        dout = dout.contiguous().view(M, d)
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+
+        # ---- LN2 backward (+ dropout mask of the FFN output, + b_2 gradient)
+        dy2 = torch.empty(M, d, dtype=torch.float32, device=dev)      # grad wrt (dropout(dense)+a)
+        dY2 = torch.empty(M, d, dtype=adt, device=dev)                 # grad wrt dense output
+        dg2, db2, do2b = z(d), z(d), z(d)
+        check(lib().samk_layernorm_bwd(ptr(dout), ptr(y2), ptr(g2), eps, ptr(dy2), ptr(dY2), _dt(dY2), p_hid,
+                                       ctx.drops[2][0], ctx.drops[2][1], ptr(dg2), ptr(db2), ptr(do2b), M, d,
+                                       stream_ptr()), "ln2_bwd")
+        _count()
+        # ---- FFN2: dgrad (fused with GELU') and wgrad
+        dY2_k = operand(dY2, "a", False)
+        dh = torch.empty(M, F, dtype=adt, device=dev)
+        gemm(dY2_k, False, weight_operand([o2w], True), True, M, F, d, dh, act=2, aux=h)
+        do2w = z(d, F)
+        gemm(operand(dY2, "a", True), True, operand(g, "b", True), True, d, F, M, do2w, accumulate=True)
+        # ---- FFN1
+        dib = z(F)
+        colsum_into(dh, dib)
+        da = torch.empty(M, d, dtype=torch.float32, device=dev)
+        gemm(operand(dh, "a", False), False, weight_operand([iw], True), True, M, d, F, da, residual=dy2)
+        diw = z(F, d)
+        gemm(operand(dh, "a", True), True, operand(a_in, "b", True), True, F, d, M, diw, accumulate=True)
+        # ---- LN1 backward (+ dropout mask of the attention output dense, + b_o gradient)
+        dy1 = torch.empty(M, d, dtype=torch.float32, device=dev)
+        dY1 = torch.empty(M, d, dtype=adt, device=dev)
+        dg1, db1, dob = z(d), z(d), z(d)
+        check(lib().samk_layernorm_bwd(ptr(da), ptr(y1), ptr(g1), eps, ptr(dy1), ptr(dY1), _dt(dY1), p_hid,
+                                       ctx.drops[1][0], ctx.drops[1][1], ptr(dg1), ptr(db1), ptr(dob), M, d,
+                                       stream_ptr()), "ln1_bwd")
+        _count()
+        # ---- attention output dense
+        dctx = torch.empty(M, d, dtype=adt, device=dev)
+        gemm(operand(dY1, "a", False), False, weight_operand([ow], True), True, M, d, d, dctx)
+        dow = z(d, d)
+        gemm(operand(dY1, "a", True), True, operand(ctx_t, "b", True), True, d, d, M, dow, accumulate=True)
+        # ---- attention core
+        dqkv = attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p_attn, ctx.drops[0])
+        dbqkv = z(3 * d)
+        colsum_into(dqkv, dbqkv)
+        # ---- fused q|k|v projection
+        dx = torch.empty(M, d, dtype=torch.float32, device=dev)
+        gemm(operand(dqkv, "a", False), False, weight_operand([qw, kw, vw], True), True, M, d, 3 * d, dx, residual=dy1)
+        dwqkv = z(3 * d, d)
+        gemm(operand(dqkv, "a", True), True, operand(x2, "b", True), True, 3 * d, d, M, dwqkv, accumulate=True)
+
+        grads = (dwqkv[:d], dbqkv[:d], dwqkv[d:2 * d], dbqkv[d:2 * d], dwqkv[2 * d:], dbqkv[2 * d:],
+                 dow, dob, dg1, db1, diw, dib, do2w, do2b, dg2, db2)
+        return (dx.view(B, L, d), None, None, None) + grads
+
+
+# ---- output heads + loss -------------------------------------------------------------------------------------
+class OutputFn(torch.autograd.Function):
+    """scores = cat[classifier(dec), OcrPtrNet(dec, ocr, mask)] written into one [B,D,V+R] buffer
+    (sa_m4c.py:270-278, 878-897)."""
+
+    @staticmethod
+    def forward(ctx, dec, ocr, ocr_mask, cw, cb, qw, qb, kw, kb):
+        _cuda(dec, ocr, cw)
+        B, D, d = dec.shape
+        R = ocr.shape[1]
+        V, dq = cw.shape[0], qw.shape[0]
+        dev = dec.device
+        dec2 = dec.contiguous().view(B * D, d)
+        ocr2 = ocr.contiguous().view(B * R, d)
+        ocr_mask = ocr_mask.contiguous()
+        scores = torch.empty(B * D, V + R, dtype=torch.float32, device=dev)
+        dec_op = operand(dec2, "a", False)
+        gemm(dec_op, False, weight_operand([cw], False), False, B * D, V, d, scores[:, :V], bias=cb)
+        q = torch.empty(B * D, dq, dtype=torch.float32, device=dev)
+        k = torch.empty(B * R, dq, dtype=torch.float32, device=dev)
+        gemm(dec_op, False, weight_operand([qw], False), False, B * D, dq, d, q, bias=qb)
+        gemm(operand(ocr2, "a", False), False, weight_operand([kw], False), False, B * R, dq, d, k, bias=kb)
+        check(lib().samk_ptr_scores_fwd(ptr(q), ptr(k), ptr(ocr_mask), ptr(scores), V + R, V, B, D, R, dq,
+                                        stream_ptr()), "ptr_scores_fwd")
+        _count()
+        ctx.dims = (B, D, R, V, d, dq)
+        ctx.save_for_backward(dec2, ocr2, q, k, cw, qw, kw)
+        return scores.view(B, D, V + R)
+
+    @staticmethod
+    def backward(ctx, ds):
+        dec2, ocr2, q, k, cw, qw, kw = ctx.saved_tensors
+        B, D, R, V, d, dq = ctx.dims
+        dev = ds.device
+        ds = ds.contiguous().view(B * D, V + R)
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        dq_ = torch.empty_like(q)
+        dk_ = torch.empty_like(k)
+        check(lib().samk_ptr_scores_bwd(ptr(ds), V + R, V, ptr(q), ptr(k), ptr(dq_), ptr(dk_), B, D, R, dq,
+                                        stream_ptr()), "ptr_scores_bwd")
+        _count()
+        dsv = ds[:, :V]
+        if _PRECISION == "bf16":
+            dsv = cast_bf16(dsv)[:, :V]
+            dq_a, dk_a = cast_bf16(dq_), cast_bf16(dk_)
+        else:
+            dq_a, dk_a = dq_, dk_
+        # classifier
+        ddec = torch.empty(B * D, d, dtype=torch.float32, device=dev)
+        gemm(operand(dsv, "a", False), False, weight_operand([cw], True), True, B * D, d, V, ddec)
+        dcw = z(V, d)
+        gemm(operand(dsv, "a", True), True, operand(dec2, "b", True), True, V, d, B * D, dcw, accumulate=True)
+        dcb = z(V)
+        colsum_into(ds[:, :V], dcb)
+        # pointer query / key projections
+        ddec2 = torch.empty(B * D, d, dtype=torch.float32, device=dev)
+        gemm(operand(dq_a, "a", False), False, weight_operand([qw], True), True, B * D, d, dq, ddec2, residual=ddec)
+        dqw = z(dq, d)
+        gemm(operand(dq_a, "a", True), True, operand(dec2, "b", True), True, dq, d, B * D, dqw, accumulate=True)
+        dqb = z(dq)
+        colsum_into(dq_, dqb)
+        docr = torch.empty(B * R, d, dtype=torch.float32, device=dev)
+        gemm(operand(dk_a, "a", False), False, weight_operand([kw], True), True, B * R, d, dq, docr)
+        dkw = z(dq, d)
+        gemm(operand(dk_a, "a", True), True, operand(ocr2, "b", True), True, dq, d, B * R, dkw, accumulate=True)
+        dkb = z(dq)
+        colsum_into(dk_, dkb)
+        return ddec2.view(B, D, d), docr.view(B, R, d), None, dcw, dcb, dqw, dqb, dkw, dkb
+
+
+class BceLossFn(torch.autograd.Function):
+    """M4CDecodingBCEWithMaskLoss (sam/task_utils.py:19-30): forward value and gradient in one pass."""
+
+    @staticmethod
+    def forward(ctx, scores, targets, loss_mask):
+        _cuda(scores, targets, loss_mask)
+        scores = scores.contiguous()
+        targets = targets.contiguous()
+        loss_mask = loss_mask.contiguous().float()
+        rows, ncls = scores.numel() // scores.shape[-1], scores.shape[-1]
+        loss = torch.empty(2, dtype=torch.float32, device=scores.device)
+        ds = torch.empty_like(scores)
+        check(lib().samk_bce_loss(ptr(scores), ptr(targets), ptr(loss_mask), ptr(ds), ptr(loss), ptr(loss[1:]), rows,
+                                  ncls, stream_ptr()), "bce_loss")
+        _count(2)
+        ctx.save_for_backward(ds)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, gout):
+        (ds,) = ctx.saved_tensors
+        g = gout.reshape(1).float().contiguous()
+        check(lib().samk_scale_inplace(ptr(ds), ds.numel(), ptr(g), stream_ptr()), "scale")
+        _count()
+        return ds, None, None
+
+
+def bce_with_mask_loss(scores, targets, loss_mask):
+    return BceLossFn.apply(scores, targets, loss_mask)
