@@ -48,6 +48,8 @@ const double* samk_graph_default_sectors(void);
 /* int8 [n_pairs, heads] head masks (the layout SAM4C.forward receives, sa_m4c.py:457) <-> uint16 bits */
 int samk_pack_adj(const int8_t* adj, uint16_t* bits, long long n_pairs, int heads, void* stream);
 int samk_unpack_bits(const uint16_t* bits, int8_t* adj, long long n_pairs, int heads, void* stream);
+/* relation types 0..12 -> packed head bits for context c (torch_broadcast_adj_matrix + dataset max-chain) */
+int samk_types_to_bits(const int8_t* types, uint16_t* bits, long long n, int context, void* stream);
 
 /* ---- dense contractions (tcgen05) -----------------------------------------------------------
  * C[M,N] = epilogue( alpha * sum_k A(m,k) * B(n,k) ), bf16 operands, fp32 accumulation in TMEM.

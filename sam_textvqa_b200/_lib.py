@@ -44,6 +44,7 @@ SIGNATURES = {
     "samk_graph_default_sectors": (ctypes.POINTER(c_double), []),
     "samk_pack_adj": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "samk_unpack_bits": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
+    "samk_types_to_bits": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "samk_gemm_bf16": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_int, c_ll, c_int, c_int, c_int,
                                ctypes.POINTER(GemmEpilogue), c_int, c_int, c_void_p]),
     "samk_cast_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p]),

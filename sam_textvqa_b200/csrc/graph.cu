@@ -159,6 +159,12 @@ __global__ void pack_adj_kernel(const int8_t* __restrict__ adj, uint16_t* __rest
   bits[e] = (uint16_t)v;
 }
 
+// relation types -> packed head bits for a context (closed form of the dataset's max-chain)
+__global__ void types_to_bits_kernel(const int8_t* __restrict__ types, uint16_t* __restrict__ bits, size_t n, int radius) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) bits[e] = head_bits(types[e], radius);
+}
+
 // packed bits -> int8 [.., 12] (for handing reference-layout masks back to callers)
 __global__ void unpack_bits_kernel(const uint16_t* __restrict__ bits, int8_t* __restrict__ adj, size_t n, int H) {
   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -169,8 +175,9 @@ __global__ void unpack_bits_kernel(const uint16_t* __restrict__ bits, int8_t* __
 template <class T>
 static int launch_graph(const T* boxes, int8_t* types, int8_t* shared, uint16_t* bits, int B, int N,
                         double dist_thr, int context, const double* sectors, cudaStream_t stream) {
-  if (!boxes || !types || B < 0 || N < 0) { set_error("samk_build_graph: null pointer / negative size"); return SAMK_ERR_ARG; }
+  if (B < 0 || N < 0) { set_error("samk_build_graph: negative size"); return SAMK_ERR_ARG; }
   if (B == 0 || N == 0) return SAMK_OK;
+  if (!boxes || !types) { set_error("samk_build_graph: null pointer"); return SAMK_ERR_ARG; }
   if (N > kMaxBoxesSmem) { set_error("samk_build_graph: N=%d exceeds %d", N, kMaxBoxesSmem); return SAMK_ERR_UNSUPPORTED; }
   if (context < 1 || context > 9 || !(context & 1)) { set_error("samk_build_graph: context must be 1,3,5,7,9"); return SAMK_ERR_ARG; }
   SectorTable st;
@@ -211,6 +218,13 @@ int samk_pack_adj(const int8_t* adj, uint16_t* bits, long long n_pairs, int head
   if (n_pairs <= 0) return SAMK_OK;
   samk::pack_adj_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(adj, bits, (size_t)n_pairs, heads);
   return samk::check_launch("samk_pack_adj");
+}
+
+int samk_types_to_bits(const int8_t* types, uint16_t* bits, long long n, int context, void* stream) {
+  if (!types || !bits || context < 1 || context > 9 || !(context & 1)) { samk::set_error("samk_types_to_bits: bad argument"); return SAMK_ERR_ARG; }
+  if (n <= 0) return SAMK_OK;
+  samk::types_to_bits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(types, bits, (size_t)n, (context - 1) / 2);
+  return samk::check_launch("samk_types_to_bits");
 }
 
 int samk_unpack_bits(const uint16_t* bits, int8_t* adj, long long n_pairs, int heads, void* stream) {

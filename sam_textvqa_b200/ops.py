@@ -24,6 +24,7 @@ _PRECISION = os.environ.get("SAMK_PRECISION", "bf16")
 _GEMM_IMPL = int(os.environ.get("SAMK_GEMM_IMPL", "0"))
 _ATTN_IMPL = int(os.environ.get("SAMK_ATTN_IMPL", "0"))
 launch_count = 0  # kernels launched through this module (bench.py reports it)
+gemm_profile = None  # bench.py: list collecting (start_event, end_event, algorithmic_flops) per GEMM launch
 
 
 def set_precision(mode):
@@ -187,8 +188,14 @@ def gemm(a, a_mn, b, b_mn, M, N, K, out, bias=None, act=0, pre=None, aux=None, d
     if split_k is None:
         split_k = _pick_split_k(M, N, Kk) if accumulate else 1
     ep.atomic_add = 1 if (accumulate or split_k > 1) else 0
+    if gemm_profile is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     check(lib().samk_gemm_bf16(ptr(a.t), 1 if a_mn else 0, a.ld, ptr(b.t), 1 if b_mn else 0, b.ld, M, N, Kk,
                                ctypes.byref(ep), split_k, _GEMM_IMPL, stream_ptr()), "gemm")
+    if gemm_profile is not None:
+        ev1.record()
+        gemm_profile.append((ev0, ev1, 2.0 * M * N * K))
     _count()
     return out
 

@@ -1,0 +1,255 @@
+"""GPU parity of the individual kernels (through the C ABI) against torch fp32 / the SIMT cross-check."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from sam_textvqa_b200 import synth
+from tests._util import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from sam_textvqa_b200 import ops as _ops
+    return _ops
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (200, 136, 72), (1000, 768, 768), (768, 3072, 1184)])
+def test_tcgen05_gemm_all_operand_majors(ops, a_mn, b_mn, shape):
+    from sam_textvqa_b200._lib import GemmEpilogue, check, lib, ptr, stream_ptr
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(DEV).bfloat16()
+    B = (torch.randn(N, K, generator=g) * 0.5).to(DEV).bfloat16()
+    As = A.t().contiguous() if a_mn else A
+    Bs = B.t().contiguous() if b_mn else B
+    outs = []
+    for impl in (0, 1):
+        out = torch.zeros(M, N, device=DEV)
+        ep = GemmEpilogue()
+        ep.out, ep.ldo, ep.out_dtype, ep.alpha = out.data_ptr(), N, 0, 1.0
+        check(lib().samk_gemm_bf16(ptr(As), a_mn, As.stride(0), ptr(Bs), b_mn, Bs.stride(0), M, N, K,
+                                   ctypes.byref(ep), 1, impl, stream_ptr()))
+        outs.append(out)
+    ref = A.float() @ B.float().t()
+    assert rel_err(outs[0], ref) < 1e-5          # fp32 accumulation of exact bf16 products
+    assert rel_err(outs[0], outs[1]) < 1e-5      # tensor-core kernel == SIMT cross-check
+
+
+def test_gemm_fused_epilogues_and_split_k(ops):
+    M, N, K = 1024, 768, 1024
+    x = torch.randn(M, K, device=DEV)
+    w = 0.05 * torch.randn(N, K, device=DEV)
+    b = torch.randn(N, device=DEV)
+    res = torch.randn(M, N, device=DEV)
+    xo, wo = ops.operand(x, "a", False), ops.operand(w, "b", False)
+    xr, wr = xo.t.float()[:, :K], wo.t.float()[:, :K]
+    base = xr @ wr.t() + b
+    pre = torch.empty(M, N, device=DEV)
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm(xo, False, wo, False, M, N, K, out, bias=b, act=1, pre=pre)
+    assert rel_err(pre, base) < 1e-5 and rel_err(out, torch.nn.functional.gelu(base)) < 1e-5
+    ops.gemm(xo, False, wo, False, M, N, K, out, bias=b, residual=res)
+    assert rel_err(out, base + res) < 1e-5
+    h = torch.randn(M, N, device=DEV)
+    ops.gemm(xo, False, wo, False, M, N, K, out, act=2, aux=h)
+    hh = h.clone().requires_grad_(True)
+    torch.nn.functional.gelu(hh).sum().backward()
+    assert rel_err(out, (xr @ wr.t()) * hh.grad) < 1e-5
+    acc = torch.ones(M, N, device=DEV)
+    ops.gemm(xo, False, wo, False, M, N, K, acc, accumulate=True, split_k=4)
+    assert rel_err(acc, xr @ wr.t() + 1.0) < 1e-5
+    # dropout epilogue: keep-rate and scaling, identical mask for identical (seed, offset)
+    o1, o2 = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+    ops.gemm(xo, False, wo, False, M, N, K, o1, bias=b, drop_p=0.1, drop=(123, 7))
+    ops.gemm(xo, False, wo, False, M, N, K, o2, bias=b, drop_p=0.1, drop=(123, 7))
+    assert torch.equal(o1, o2)
+    kept = o1 != 0
+    assert abs(kept.float().mean().item() - 0.9) < 5e-3
+    assert rel_err(o1[kept], (base / 0.9)[kept]) < 1e-5
+
+
+def test_bf16x3_split_reaches_fp32_accuracy(ops):
+    ops.set_precision("bf16x3")
+    try:
+        x = torch.randn(512, 768, device=DEV, requires_grad=True)
+        w = (0.05 * torch.randn(768, 768, device=DEV)).requires_grad_(True)
+        b = torch.randn(768, device=DEV, requires_grad=True)
+        y = ops.linear(x, w, b)
+        ref = (x.double() @ w.double().t() + b.double())
+        assert rel_err(y, ref) < 2e-5
+        gy = torch.randn_like(y)
+        gx, gw, gb = torch.autograd.grad((y * gy).sum(), (x, w, b))
+        rx, rw, rb = torch.autograd.grad((ref * gy.double()).sum(), (x, w, b))
+        assert rel_err(gx, rx) < 2e-5 and rel_err(gw, rw) < 2e-5 and rel_err(gb, rb) < 1e-5
+    finally:
+        ops.set_precision("bf16")
+
+
+def test_layernorm_forward_backward(ops):
+    x = torch.randn(1111, 768, device=DEV, requires_grad=True)
+    g = (1 + 0.1 * torch.randn(768, device=DEV)).requires_grad_(True)
+    b = (0.1 * torch.randn(768, device=DEV)).requires_grad_(True)
+    y = ops.layer_norm(x, g, b, 1e-12)
+    ref = torch.nn.functional.layer_norm(x, (768,), g, b, 1e-12)
+    assert rel_err(y, ref) < 1e-5
+    w = torch.randn_like(y)
+    got = torch.autograd.grad((y * w).sum(), (x, g, b))
+    want = torch.autograd.grad((ref * w).sum(), (x, g, b))
+    for a, r in zip(got, want):
+        assert rel_err(a, r) < 1e-5
+
+
+def _attn_reference(qkv, valid, adj, T, A, D, quadrants):
+    """Explicit boolean-mask softmax in torch (fp64)."""
+    B, L = valid.shape
+    H = 12
+    q3 = qkv.view(B, L, 3, H, 64).double()
+    qq, kk, vv = (q3[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    ext = valid.double()[:, None, :].repeat(1, L, 1)
+    if D:
+        ext[:, -D:, -D:] = torch.tril(torch.ones(D, D, device=qkv.device, dtype=torch.double))
+    allow = (ext[:, None] > 0).expand(B, H, L, L).clone()
+    if adj is not None:
+        m = torch.ones(B, L, L, H, device=qkv.device)
+        m[:, T:T + A, T:T + A] = adj.float()
+        if 1 in quadrants:
+            m[:, :T, :T] = 0
+        if 2 in quadrants:
+            m[:, :T, T:T + A] = 0
+        allow &= m.permute(0, 3, 1, 2) > 0
+    s = (qq @ kk.transpose(-1, -2)) / 8.0
+    p = torch.softmax(s.masked_fill(~allow, float("-inf")), -1)
+    p = torch.where(allow.any(-1, keepdim=True), p, torch.zeros_like(p))
+    return (p @ vv).permute(0, 2, 1, 3).reshape(B, L, H * 64)
+
+
+def test_attention_matches_reference_module_golden(ops):
+    """ctx of the unmodified reference SpatialBertSelfAttention (tests/golden/attn_unit.npz)."""
+    from sam_textvqa_b200.sa_m4c import pack_relation_bits
+    g = load_golden("attn_unit.npz")
+    T, A, D = int(g["T"]), int(g["A"]), int(g["D"])
+    hidden = torch.from_numpy(g["hidden"]).to(DEV)
+    B, L, d = hidden.shape
+    sd = synth.seeded_state([("%s.%s" % (n, s), (768, 768) if s == "weight" else (768,))
+                             for n in ("query", "key", "value") for s in ("weight", "bias")], 3)
+    W = torch.cat([sd["query.weight"], sd["key.weight"], sd["value.weight"]]).to(DEV).double()
+    bias = torch.cat([sd["query.bias"], sd["key.bias"], sd["value.bias"]]).to(DEV).double()
+    qkv = (hidden.view(B * L, d).double() @ W.t() + bias).float().contiguous()
+    bits = pack_relation_bits(torch.from_numpy(g["adj"]), torch.device(DEV))
+    valid = torch.from_numpy(g["valid"]).to(DEV).to(torch.uint8).contiguous()
+    dims = (B, L, 12, T, A, D)
+    ctx, _ = ops.attention_fwd(qkv, valid, bits, dims, True, 0b11, 0.0, (0, 0))
+    want = torch.from_numpy(g["ctx"]).to(DEV)
+    assert rel_err(ctx.view(B, L, d), want) < 2e-5
+    assert ctx.view(B, L, d)[:, :T].abs().max().item() == 0.0        # dead text rows are exactly zero
+    ctx16, _ = ops.attention_fwd(qkv.bfloat16(), valid, bits, dims, True, 0b11, 0.0, (0, 0))
+    assert rel_err(ctx16.float().view(B, L, d), want) < 2e-2
+
+
+@pytest.mark.parametrize("spatial", [True, False])
+@pytest.mark.parametrize("L_cfg", [(20, 30, 12), (20, 150, 12), (5, 0, 0), (20, 300, 12)])
+def test_attention_forward_backward_vs_torch(ops, spatial, L_cfg):
+    T, A, D = L_cfg
+    if spatial and A == 0:
+        pytest.skip("spatial layers need entities")
+    B, L = 2, T + A + D
+    g = torch.Generator().manual_seed(L)
+    qkv = torch.randn(B * L, 3 * 768, generator=g).to(DEV)
+    valid = (torch.rand(B, L, generator=g) < 0.8).to(torch.uint8).to(DEV)
+    valid[:, 0] = 1
+    if D:
+        valid[:, -D:] = 0
+    rs = np.random.RandomState(L)
+    types = torch.from_numpy(rs.randint(0, 13, (B, max(A, 1), max(A, 1))).astype(np.int8))
+    if A:
+        types[0, 3] = 0
+    adj = synth.expand_types_to_heads(types, 3).to(DEV) if A else None
+    from sam_textvqa_b200.sa_m4c import pack_relation_bits
+    bits = pack_relation_bits(adj, torch.device(DEV)) if (spatial and A) else None
+    dims = (B, L, 12, T, A, D)
+    ctx, lse = ops.attention_fwd(qkv, valid, bits, dims, spatial, 0b11 if spatial else 0, 0.0, (0, 0))
+    q = qkv.clone().requires_grad_(True)
+    ref = _attn_reference(q, valid, adj if spatial else None, T, A, D, (1, 2) if spatial else ())
+    assert rel_err(ctx.view(B, L, 768), ref) < 2e-5
+    w = torch.randn(B, L, 768, generator=g).to(DEV)
+    (gref,) = torch.autograd.grad((ref * w.double()).sum(), q)
+    dqkv = ops.attention_bwd(w.view(B * L, 768).contiguous(), qkv, ctx, lse, valid, bits, dims, spatial,
+                             0b11 if spatial else 0, 0.0, (0, 0))
+    assert rel_err(dqkv, gref) < 5e-5
+
+
+def test_attention_dropout_is_consistent_between_forward_and_backward(ops):
+    """With dropout, d(ctx . w)/d(qkv) from the kernel must match finite differences of the kernel's own
+    forward under the same (seed, offset) mask."""
+    T, A, D = 8, 16, 4
+    B, L = 1, T + A + D
+    g = torch.Generator().manual_seed(5)
+    qkv = (0.5 * torch.randn(B * L, 3 * 768, generator=g)).to(DEV)
+    valid = torch.ones(B, L, dtype=torch.uint8, device=DEV)
+    valid[:, -D:] = 0
+    dims = (B, L, 12, T, A, D)
+    drop = (99, 3)
+    w = torch.randn(B * L, 768, generator=g).to(DEV)
+    ctx, lse = ops.attention_fwd(qkv, valid, None, dims, False, 0, 0.3, drop)
+    dqkv = ops.attention_bwd(w, qkv, ctx, lse, valid, None, dims, False, 0, 0.3, drop)
+    direction = torch.randn(B * L, 3 * 768, generator=g).to(DEV)
+    eps = 1e-2
+    f = lambda t: (ops.attention_fwd(t, valid, None, dims, False, 0, 0.3, drop)[0].double() * w.double()).sum()
+    fd = (f(qkv + eps * direction) - f(qkv - eps * direction)) / (2 * eps)
+    an = (dqkv.double() * direction.double()).sum()
+    assert abs(fd.item() - an.item()) < 2e-2 * max(1.0, abs(an.item()))
+    assert (ctx == 0).float().mean().item() < 0.05       # rows still populated
+
+
+def test_embeddings_prevpred_pointer_and_loss_vs_torch(ops):
+    B, T, D, R, V, d = 3, 20, 12, 50, 200, 768
+    g = torch.Generator().manual_seed(0)
+    mk = lambda *s: (0.1 * torch.randn(*s, generator=g)).to(DEV).requires_grad_(True)
+    # TextBert embeddings
+    ids = torch.randint(0, 1000, (B, T), generator=g).to(DEV)
+    ids[0, -3:] = 0
+    word, pos, typ, ga, be = mk(1000, d), mk(512, d), mk(2, d), mk(d), mk(d)
+    y = ops.BertEmbedFn.apply(ids, word, pos, typ, ga, be, 1e-12, 0.0)
+    ref = torch.nn.functional.layer_norm(word[ids] + pos[:T][None] + typ[0], (d,), ga, be, 1e-12)
+    assert rel_err(y, ref) < 1e-5
+    w = torch.randn_like(ref)
+    got = torch.autograd.grad((y * w).sum(), (word, pos, typ, ga, be))
+    # padding_idx=0 rows get no gradient in nn.Embedding
+    ref2 = torch.nn.functional.layer_norm(torch.nn.functional.embedding(ids, word, padding_idx=0) + pos[:T][None] + typ[0], (d,), ga, be, 1e-12)
+    want = torch.autograd.grad((ref2 * w).sum(), (word, pos, typ, ga, be))
+    for a, r in zip(got, want):
+        assert rel_err(a, r) < 2e-5
+    # PrevPredEmbeddings
+    prev = torch.randint(0, V + R, (B, D), generator=g).to(DEV)
+    cls_w, ocr_in, ppos, ptyp = mk(V, d), mk(B, R, d), mk(100, d), mk(5, d)
+    lns = [mk(d) for _ in range(6)]
+    out = ops.PrevPredFn.apply(prev, cls_w, ocr_in, ppos, ptyp, *lns, 1e-12, 0.0)
+    ln = lambda x, gg, bb: torch.nn.functional.layer_norm(x, (d,), gg, bb, 1e-12)
+    table = torch.cat([ln(cls_w, lns[0], lns[1])[None].expand(B, -1, -1), ln(ocr_in, lns[2], lns[3])], 1)
+    raw = torch.gather(table, 1, prev[..., None].expand(-1, -1, d))
+    refp = raw + ln(ppos[:D][None] + ptyp[(prev >= V).long()], lns[4], lns[5])
+    assert rel_err(out, refp) < 1e-5
+    w = torch.randn_like(refp)
+    allp = [cls_w, ocr_in, ppos, ptyp] + lns
+    got = torch.autograd.grad((out * w).sum(), allp)
+    want = torch.autograd.grad((refp * w).sum(), allp)
+    for a, r in zip(got, want):
+        assert rel_err(a, r) < 2e-5
+    # masked BCE loss (sam/task_utils.py:19-30)
+    scores = (3 * torch.randn(B, D, V + R, generator=g)).to(DEV).requires_grad_(True)
+    targets = (torch.rand(B, D, V + R, generator=g) < 0.01).float().to(DEV)
+    mask = (torch.rand(B, D, generator=g) < 0.7).float().to(DEV)
+    loss = ops.bce_with_mask_loss(scores, targets, mask)
+    refl = (torch.nn.functional.binary_cross_entropy_with_logits(scores, targets, reduction="none") * mask[..., None]).sum() / mask.sum().clamp(min=1)
+    assert abs(loss.item() - refl.item()) < 1e-4 * abs(refl.item())
+    (gs,) = torch.autograd.grad(loss * 2.0, scores)
+    (rs_,) = torch.autograd.grad(refl * 2.0, scores)
+    assert rel_err(gs, rs_) < 1e-5
+    zero_mask_loss = ops.bce_with_mask_loss(scores, targets, torch.zeros_like(mask))
+    assert zero_mask_loss.item() == 0.0
