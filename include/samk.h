@@ -166,9 +166,15 @@ typedef struct samk_attn_params {
   float scale;
   float drop_p;
   unsigned long long drop_seed, drop_offset;
+  const uint32_t* allow_bits; /* tensor-core path: [B, spatial?H:1, L, ceil(L/32)] from samk_attn_build_mask */
+  float* dq_accum;            /* tensor-core backward: fp32 [B*L, H*64] scratch for the dQ reduction */
 } samk_attn_params;
 int samk_attn_fwd(const samk_attn_params* p, int impl, void* stream);
 int samk_attn_bwd(const samk_attn_params* p, int impl, void* stream);
+/* allow-bit matrix shared by all layers of one kind in a step: bit (j&31) of word [b][h|0][i][j>>5] set
+ * iff query i may attend key j (key validity, decoder causality, quadrants, relation bits). */
+long long samk_attn_mask_words(int B, int H, int T, int A, int D, int spatial);
+int samk_attn_build_mask(const samk_attn_params* p, uint32_t* allow_bits, void* stream);
 
 #ifdef __cplusplus
 }

@@ -42,4 +42,15 @@ __device__ __forceinline__ bool attn_allowed(const AttnMask& m, int b, int h, in
   return ok;
 }
 
+__device__ __forceinline__ bool sample_any_valid(const AttnMask& m, int b, int* sflag) {
+  // block-wide: does sample b have a valid encoder key
+  if (threadIdx.x == 0) *sflag = 0;
+  __syncthreads();
+  int f = 0;
+  for (int j = threadIdx.x; j < m.T + m.A; j += blockDim.x) f |= m.valid[(size_t)b * m.L + j] != 0;
+  if (f) atomicOr(sflag, 1);
+  __syncthreads();
+  return *sflag != 0;
+}
+
 }  // namespace samk

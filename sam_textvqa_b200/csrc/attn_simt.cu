@@ -49,17 +49,6 @@ __device__ __forceinline__ float attn_keep(const AttnArgs& a, int b, int h, int 
   return w >= a.drop_thresh ? a.drop_scale : 0.0f;
 }
 
-__device__ __forceinline__ bool sample_any_valid(const AttnMask& m, int b, int* sflag) {
-  // block-wide: does sample b have a valid encoder key
-  if (threadIdx.x == 0) *sflag = 0;
-  __syncthreads();
-  int f = 0;
-  for (int j = threadIdx.x; j < m.T + m.A; j += blockDim.x) f |= m.valid[(size_t)b * m.L + j] != 0;
-  if (f) atomicOr(sflag, 1);
-  __syncthreads();
-  return *sflag != 0;
-}
-
 // load rows [r0, r0+nrows) x 64 of one head slice into smem[nrows][65] (zero rows past L)
 __device__ __forceinline__ void load_tile(float (*dst)[DH + 1], const void* src, int bf16, size_t base, long long ld,
                                           int r0, int nrows, int L) {
@@ -409,13 +398,3 @@ int attn_simt_bwd(const samk_attn_params* p, cudaStream_t stream) {
 
 }  // namespace samk
 
-extern "C" {
-int samk_attn_fwd(const samk_attn_params* p, int impl, void* stream) {
-  (void)impl;
-  return samk::attn_simt_fwd(p, (cudaStream_t)stream);
-}
-int samk_attn_bwd(const samk_attn_params* p, int impl, void* stream) {
-  (void)impl;
-  return samk::attn_simt_bwd(p, (cudaStream_t)stream);
-}
-}

@@ -395,13 +395,15 @@ class PrevPredFn(torch.autograd.Function):
 
 
 # ---- attention ------------------------------------------------------------------------------------------
-def _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, dctx=None, dqkv=None, delta=None):
+def _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, dctx=None, dqkv=None, delta=None,
+                 allow=None, dq_accum=None):
     B, L, H, T, A, D = dims
     ap = _lib.AttnParams()
-    ap.qkv, ap.ctx, ap.lse = qkv.data_ptr(), ctx_t.data_ptr(), lse.data_ptr()
+    if qkv is not None:
+        ap.qkv, ap.ctx, ap.lse = qkv.data_ptr(), ctx_t.data_ptr(), lse.data_ptr()
+        ap.dtype = _dt(qkv)
     if dctx is not None:
         ap.dctx, ap.dqkv, ap.delta = dctx.data_ptr(), dqkv.data_ptr(), delta.data_ptr()
-    ap.dtype = _dt(qkv)
     ap.B, ap.H, ap.head_dim = B, H, 64
     ap.T, ap.A, ap.D = T, A, D
     ap.key_valid = valid.data_ptr()
@@ -411,26 +413,52 @@ def _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop,
     ap.scale = 1.0 / math.sqrt(64.0)
     ap.drop_p = p
     ap.drop_seed, ap.drop_offset = drop
+    ap.allow_bits = allow.data_ptr() if allow is not None else None
+    ap.dq_accum = dq_accum.data_ptr() if dq_accum is not None else None
     return ap
 
 
-def attention_fwd(qkv, valid, rel, dims, spatial, quad_mask, p, drop):
+def uses_tensor_core_attention(dtype):
+    return dtype == torch.bfloat16 and _ATTN_IMPL == 0
+
+
+def build_attn_mask(valid, rel, dims, spatial, quad_mask):
+    """Packed allow-bits [B, H|1, L, ceil(L/32)] for the tensor-core attention (built once per step and
+    mask kind, shared by every layer and by the backward pass)."""
     B, L, H, T, A, D = dims
+    words = lib().samk_attn_mask_words(B, H, T, A, D, 1 if spatial else 0)
+    allow = torch.empty(max(int(words), 1), dtype=torch.int32, device=valid.device)
+    ap = _attn_params(None, None, None, valid, rel, dims, spatial, quad_mask, 0.0, (0, 0))
+    check(lib().samk_attn_build_mask(ctypes.byref(ap), ptr(allow), stream_ptr()), "attn_build_mask")
+    _count()
+    return allow
+
+
+def attention_fwd(qkv, valid, rel, dims, spatial, quad_mask, p, drop, allow=None):
+    B, L, H, T, A, D = dims
+    if uses_tensor_core_attention(qkv.dtype) and allow is None:
+        allow = build_attn_mask(valid, rel, dims, spatial, quad_mask)
     ctx_t = torch.empty(B * L, H * 64, dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty(B, H, L, dtype=torch.float32, device=qkv.device)
-    ap = _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop)
+    ap = _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, allow=allow)
     check(lib().samk_attn_fwd(ctypes.byref(ap), _ATTN_IMPL, stream_ptr()), "attn_fwd")
     _count()
     return ctx_t, lse
 
 
-def attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop):
+def attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, allow=None):
     B, L, H, T, A, D = dims
+    dq_accum = None
+    if uses_tensor_core_attention(qkv.dtype):
+        if allow is None:
+            allow = build_attn_mask(valid, rel, dims, spatial, quad_mask)
+        dq_accum = torch.empty(B * L, H * 64, dtype=torch.float32, device=qkv.device)
     dqkv = torch.empty_like(qkv)
     delta = torch.empty_like(lse)
-    ap = _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, dctx, dqkv, delta)
+    ap = _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, dctx, dqkv, delta,
+                      allow=allow, dq_accum=dq_accum)
     check(lib().samk_attn_bwd(ctypes.byref(ap), _ATTN_IMPL, stream_ptr()), "attn_bwd")
-    _count(2)
+    _count(4 if dq_accum is not None else 2)
     return dqkv
 
 
@@ -444,7 +472,7 @@ class BertLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, valid, rel, cfg, *P):
-        (dims, spatial, quad_mask, p_attn, p_hid, eps) = cfg
+        (dims, spatial, quad_mask, p_attn, p_hid, eps, mask_cache) = cfg
         B, L, H, T, A, D = dims
         qw, qb, kw, kb, vw, vb, ow, ob, g1, b1, iw, ib, o2w, o2b, g2, b2 = P
         _cuda(x, valid, qw)
@@ -459,7 +487,15 @@ class BertLayerFn(torch.autograd.Function):
         bqkv = torch.cat([qb, kb, vb]).detach()
         qkv = torch.empty(M, 3 * d, dtype=adt, device=dev)
         gemm(x_op, False, wqkv, False, M, 3 * d, d, qkv, bias=bqkv)
-        ctx_t, lse = attention_fwd(qkv, valid, rel, dims, spatial, quad_mask, p_attn, drops[0])
+        allow = None
+        if uses_tensor_core_attention(adt):
+            mkey = (bool(spatial), quad_mask if spatial else 0, rel.data_ptr() if (spatial and rel is not None) else 0, dims)
+            allow = mask_cache.get(mkey) if mask_cache is not None else None
+            if allow is None:
+                allow = build_attn_mask(valid, rel, dims, spatial, quad_mask)
+                if mask_cache is not None:
+                    mask_cache[mkey] = allow
+        ctx_t, lse = attention_fwd(qkv, valid, rel, dims, spatial, quad_mask, p_attn, drops[0], allow)
 
         y1 = torch.empty(M, d, dtype=torch.float32, device=dev)
         gemm(operand(ctx_t, "a", False), False, weight_operand([ow], False), False, M, d, d, y1, bias=ob,
@@ -480,16 +516,16 @@ class BertLayerFn(torch.autograd.Function):
         check(lib().samk_layernorm_fwd(ptr(y2), ptr(g2), ptr(b2), eps, ptr(out), None, 0, M, d, stream_ptr()), "ln2")
         _count()
 
-        ctx.cfg, ctx.drops = cfg, drops
-        ctx.save_for_backward(x2, valid, rel, qkv, ctx_t, lse, y1, a_in, h, g, y2, *P)
+        ctx.cfg, ctx.drops = cfg[:6], drops
+        ctx.save_for_backward(x2, valid, rel, qkv, ctx_t, lse, y1, a_in, h, g, y2, allow, *P)
         return out.view(B, L, d)
 
     @staticmethod
     def backward(ctx, dout):
         (dims, spatial, quad_mask, p_attn, p_hid, eps) = ctx.cfg
         B, L, H, T, A, D = dims
-        x2, valid, rel, qkv, ctx_t, lse, y1, a_in, h, g, y2 = ctx.saved_tensors[:11]
-        qw, qb, kw, kb, vw, vb, ow, ob, g1, b1, iw, ib, o2w, o2b, g2, b2 = ctx.saved_tensors[11:]
+        x2, valid, rel, qkv, ctx_t, lse, y1, a_in, h, g, y2, allow = ctx.saved_tensors[:12]
+        qw, qb, kw, kb, vw, vb, ow, ob, g1, b1, iw, ib, o2w, o2b, g2, b2 = ctx.saved_tensors[12:]
         dev = dout.device
         adt = act_dtype()
         M, d, F = B * L, x2.shape[1], iw.shape[0]
@@ -531,7 +567,7 @@ class BertLayerFn(torch.autograd.Function):
         dow = z(d, d)
         gemm(operand(dY1, "a", True), True, operand(ctx_t, "b", True), True, d, d, M, dow, accumulate=True)
         # ---- attention core
-        dqkv = attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p_attn, ctx.drops[0])
+        dqkv = attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p_attn, ctx.drops[0], allow)
         dbqkv = z(3 * d)
         colsum_into(dqkv, dbqkv)
         # ---- fused q|k|v projection

@@ -157,8 +157,9 @@ class BertLayer(nn.Module):
                 self.output.dense.weight, self.output.dense.bias, self.output.LayerNorm.weight,
                 self.output.LayerNorm.bias)
 
-    def forward(self, hidden, key_valid, rel_bits, seg):
-        """hidden [B,L,d] fp32; key_valid uint8 [B,L]; rel_bits uint16 [B,A,A] or None; seg = (T,A,D)."""
+    def forward(self, hidden, key_valid, rel_bits, seg, mask_cache=None):
+        """hidden [B,L,d] fp32; key_valid uint8 [B,L]; rel_bits uint16 [B,A,A] or None; seg = (T,A,D);
+        mask_cache: dict shared by the layers of one forward pass (packed allow-bits per mask kind)."""
         B, L, _ = hidden.shape
         s = self.attention.self
         T, A, D = seg
@@ -166,7 +167,7 @@ class BertLayer(nn.Module):
         train = self.training
         cfg = (dims, self.spatial, getattr(s, "quadrant_bits", 0),
                float(s.attention_probs_dropout_prob) if train else 0.0,
-               float(self.hidden_dropout_prob) if train else 0.0, float(self.layer_norm_eps))
+               float(self.hidden_dropout_prob) if train else 0.0, float(self.layer_norm_eps), mask_cache)
         return ops.BertLayerFn.apply(hidden, key_valid, rel_bits if self.spatial else None, cfg, *self._params())
 
 
@@ -214,8 +215,9 @@ class TextBert(nn.Module):
         x = self.embeddings(ids)
         valid = batch_dict["question_mask"].to(torch.uint8).contiguous()
         T = ids.shape[1]
+        cache = {}
         for layer in self.encoder.layer:
-            x = layer(x, valid, None, (T, 0, 0))
+            x = layer(x, valid, None, (T, 0, 0), cache)
         return x
 
 
@@ -267,11 +269,12 @@ class BertSpatialEncoder(nn.Module):
 
     def forward(self, hidden, key_valid, rel_lookup, seg):
         normal_iter, spatial_iter = iter(self.normal_layers), iter(self.spatial_layers)
+        cache = {}
         for layer_type, mix_type in zip(self.layer_type_list, self.mix_list):
             if layer_type == "n":
-                hidden = next(normal_iter)(hidden, key_valid, None, seg)
+                hidden = next(normal_iter)(hidden, key_valid, None, seg, cache)
             elif layer_type == "s":
-                hidden = next(spatial_iter)(hidden, key_valid, rel_lookup(self.matrix_type_map[mix_type]), seg)
+                hidden = next(spatial_iter)(hidden, key_valid, rel_lookup(self.matrix_type_map[mix_type]), seg, cache)
             else:
                 raise ValueError
         return hidden

@@ -253,3 +253,39 @@ def test_embeddings_prevpred_pointer_and_loss_vs_torch(ops):
     assert rel_err(gs, rs_) < 1e-5
     zero_mask_loss = ops.bce_with_mask_loss(scores, targets, torch.zeros_like(mask))
     assert zero_mask_loss.item() == 0.0
+
+
+@pytest.mark.parametrize("case", [(2, 20, 150, 12, True, 0.0), (2, 20, 150, 12, False, 0.0), (3, 20, 0, 0, False, 0.0),
+                                  (2, 20, 86, 12, True, 0.1), (2, 20, 200, 12, True, 0.0), (1, 20, 442, 12, False, 0.1),
+                                  (1, 20, 1004, 12, True, 0.0)])
+def test_tcgen05_attention_matches_exact_fp32_kernel(ops, case):
+    """bf16 tensor-core attention (fwd + bwd, masks, dead rows, dropout, multi-tile online softmax up to
+    L=1036) against the exact-fp32 SIMT kernel on the same bf16-representable inputs and Philox masks."""
+    from sam_textvqa_b200.sa_m4c import pack_relation_bits
+    B, T, A, D, spatial, p = case
+    L = T + A + D
+    g = torch.Generator().manual_seed(L)
+    qkv16 = (0.7 * torch.randn(B * L, 2304, generator=g)).to(DEV).bfloat16()
+    qkv32 = qkv16.float()
+    valid = (torch.rand(B, L, generator=g) < 0.85).to(torch.uint8).to(DEV)
+    valid[:, 0] = 1
+    if D:
+        valid[:, -D:] = 0
+    bits = None
+    if spatial:
+        types = torch.from_numpy(np.random.RandomState(L).randint(0, 13, (B, A, A)).astype(np.int8))
+        types[0, 3] = 0
+        bits = pack_relation_bits(synth.expand_types_to_heads(types, 3), torch.device(DEV))
+    dims, quad, drop = (B, L, 12, T, A, D), (0b11 if spatial else 0), (77, 5)
+    ctx_ref, lse_ref = ops.attention_fwd(qkv32, valid, bits, dims, spatial, quad, p, drop)
+    ctx, lse = ops.attention_fwd(qkv16, valid, bits, dims, spatial, quad, p, drop)
+    assert rel_err(ctx.float(), ctx_ref) < 8e-3                    # bf16 rounding of P and of the output
+    assert torch.equal(torch.isinf(lse), torch.isinf(lse_ref))     # dead rows agree
+    fin = torch.isfinite(lse_ref)
+    assert (lse[fin] - lse_ref[fin]).abs().max().item() < 1e-4
+    if spatial:
+        assert ctx.view(B, L, 768)[:, :T].abs().max().item() == 0.0
+    w16 = torch.randn(B * L, 768, generator=g).to(DEV).bfloat16()
+    dq_ref = ops.attention_bwd(w16.float(), qkv32, ctx_ref, lse_ref, valid, bits, dims, spatial, quad, p, drop)
+    dq = ops.attention_bwd(w16, qkv16, ctx, lse, valid, bits, dims, spatial, quad, p, drop)
+    assert rel_err(dq.float(), dq_ref) < 1e-2
