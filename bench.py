@@ -216,6 +216,11 @@ def run_samk(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item() / steps
 
+    if args.profile_only:      # for `ncu` launch lists: 1 warm-up + 2 steps, nothing else
+        for _ in range(3):
+            step(resident, resident_adj)
+        torch.cuda.synchronize()
+        return
     for _ in range(max(args.warmup, 3)):
         step(resident, resident_adj)
     sampler = ClockSampler(local) if rank == 0 else None
@@ -292,6 +297,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=16, help="bounded CPU sample size")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-only", action="store_true", help="run 3 bare steps and exit (for ncu launch lists)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -73,7 +73,8 @@ typedef struct samk_gemm_epilogue {
   void* pre;             /* [M,N] pre-activation copy or NULL */
   long long ldpre;
   int pre_dtype;
-  int act;               /* 0 none, 1 erf-GELU (sa_m4c.py:985-991), 2 multiply by GELU'(aux) */
+  int act;               /* 0 none, 1 erf-GELU (sa_m4c.py:985-991), 2 multiply by GELU'(aux),
+                            3 out = GELU(v) and pre = GELU'(v) (forward FFN1), 4 multiply by aux (backward FFN2 dgrad) */
   const void* aux;       /* [M,N] for act 2 */
   long long ldaux;
   int aux_dtype;
@@ -101,12 +102,14 @@ int samk_l2norm(const float* x, long long ldx, void* y, long long ldy, int y_dty
 /* BertLayerNorm (sa_m4c.py:1016-1028; eps inside the sqrt, biased variance).  y fp32 and/or y2 in
  * y2_dtype.  Backward: dx fp32; optional dxd = dropout_mask(dx) in dxd_dtype (gradient of the dense
  * output under the dropout of BertSelfOutput/BertOutput); dgamma, dbeta, dbias (= colsum(dxd)) are
- * ACCUMULATED (+=) into fp32 [cols] buffers. */
+ * ACCUMULATED (+=) into fp32 [cols] buffers (each may be NULL). */
 int samk_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y, void* y2,
                        int y2_dtype, int rows, int cols, void* stream);
 int samk_layernorm_bwd(const float* dy, const float* x, const float* gamma, float eps, float* dx, void* dxd,
                        int dxd_dtype, float drop_p, unsigned long long seed, unsigned long long offset, float* dgamma,
-                       float* dbeta, float* dbias, int rows, int cols, void* stream);
+                       float* dbeta, float* dbias, float* partials, int rows, int cols, void* stream);
+/* floats of scratch for `partials` (NULL = reduce with atomics instead of the 2-stage reduction) */
+long long samk_layernorm_bwd_partials(int cols);
 /* out = dropout(a + b) (b may be NULL); also the dropout backward with a = dout */
 int samk_dropout_add(const float* a, const float* b, float* out, void* out2, int out2_dtype, int rows, int cols,
                      float drop_p, unsigned long long seed, unsigned long long offset, void* stream);

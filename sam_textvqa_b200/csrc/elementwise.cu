@@ -151,28 +151,37 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 // dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)); dgamma += dy*xhat; dbeta += dy.
 // Optional second output dxd = dropout_mask(dx) in the activation dtype (the gradient of the dense
 // output that sits under dropout in BertSelfOutput / BertOutput) and dbias += colsum(dxd).
+// The three column sums are accumulated per block in shared memory (conflict-free shared atomics:
+// a warp adds 32 x 4 consecutive columns per instruction), so the row loop keeps few registers and
+// many warps stay resident; block partials go to `partials` (or global atomics when it is NULL).
 __global__ void __launch_bounds__(kRowThreads)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                      float eps, float* __restrict__ dx, void* __restrict__ dxd, int dxd_bf16, uint32_t thresh,
                      float scale, unsigned long long seed, unsigned long long off, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta, float* __restrict__ dbias, int rows, int cols) {
+                     float* __restrict__ dbeta, float* __restrict__ dbias, float* __restrict__ partials, int rows,
+                     int cols) {
+  extern __shared__ float acc_s[];   // [3][cols]
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warp = blockIdx.x * (kRowThreads / 32) + wib;
   const int nwarps = gridDim.x * (kRowThreads / 32);
-  float4 ag[kMaxVec], ab[kMaxVec], ad[kMaxVec];
-#pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) ag[i] = ab[i] = ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = threadIdx.x; c < 3 * cols; c += kRowThreads) acc_s[c] = 0.f;
+  __syncthreads();
+  float* sg = acc_s; float* sb = acc_s + cols; float* sd = acc_s + 2 * cols;
+  const bool want_d = dxd != nullptr || dbias != nullptr;
   const uint64_t row_groups = (uint64_t)((cols + 3) >> 2);
   for (int r = warp; r < rows; r += nwarps) {
-    float4 v[kMaxVec], g[kMaxVec];
+    float4 v[kMaxVec], d[kMaxVec];
     int nvec = 0;
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) {
       int c = 4 * (lane + 32 * i);
-      if (c < cols) { v[i] = *reinterpret_cast<const float4*>(x + (size_t)r * cols + c); nvec = i + 1; }
-      else v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      s += v[i].x + v[i].y + v[i].z + v[i].w;
+      if (c < cols) {
+        v[i] = *reinterpret_cast<const float4*>(x + (size_t)r * cols + c);
+        d[i] = *reinterpret_cast<const float4*>(dy + (size_t)r * cols + c);
+        nvec = i + 1;
+        s += v[i].x + v[i].y + v[i].z + v[i].w;
+      }
     }
     s = warp_sum(s);
     const float mean = s / cols;
@@ -188,14 +197,18 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) if (i < nvec) {
       int c = 4 * (lane + 32 * i);
-      float4 d = *reinterpret_cast<const float4*>(dy + (size_t)r * cols + c);
       float4 gm = *reinterpret_cast<const float4*>(gamma + c);
       v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;   // xhat
-      ag[i].x += d.x * v[i].x; ag[i].y += d.y * v[i].y; ag[i].z += d.z * v[i].z; ag[i].w += d.w * v[i].w;
-      ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
-      g[i] = make_float4(gm.x * d.x, gm.y * d.y, gm.z * d.z, gm.w * d.w);
-      s1 += g[i].x + g[i].y + g[i].z + g[i].w;
-      s2 += g[i].x * v[i].x + g[i].y * v[i].y + g[i].z * v[i].z + g[i].w * v[i].w;
+      if (dgamma) {
+        atomicAdd(sg + c, d[i].x * v[i].x); atomicAdd(sg + c + 1, d[i].y * v[i].y);
+        atomicAdd(sg + c + 2, d[i].z * v[i].z); atomicAdd(sg + c + 3, d[i].w * v[i].w);
+      }
+      if (dbeta) {
+        atomicAdd(sb + c, d[i].x); atomicAdd(sb + c + 1, d[i].y); atomicAdd(sb + c + 2, d[i].z); atomicAdd(sb + c + 3, d[i].w);
+      }
+      d[i] = make_float4(gm.x * d[i].x, gm.y * d[i].y, gm.z * d[i].z, gm.w * d[i].w);
+      s1 += d[i].x + d[i].y + d[i].z + d[i].w;
+      s2 += d[i].x * v[i].x + d[i].y * v[i].y + d[i].z * v[i].z + d[i].w * v[i].w;
     }
     s1 = warp_sum(s1) / cols;
     s2 = warp_sum(s2) / cols;
@@ -203,38 +216,48 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     for (int i = 0; i < kMaxVec; ++i) if (i < nvec) {
       int c = 4 * (lane + 32 * i);
       float4 o;
-      o.x = rstd * (g[i].x - s1 - v[i].x * s2);
-      o.y = rstd * (g[i].y - s1 - v[i].y * s2);
-      o.z = rstd * (g[i].z - s1 - v[i].z * s2);
-      o.w = rstd * (g[i].w - s1 - v[i].w * s2);
+      o.x = rstd * (d[i].x - s1 - v[i].x * s2);
+      o.y = rstd * (d[i].y - s1 - v[i].y * s2);
+      o.z = rstd * (d[i].z - s1 - v[i].z * s2);
+      o.w = rstd * (d[i].w - s1 - v[i].w * s2);
       if (dx) *reinterpret_cast<float4*>(dx + (size_t)r * cols + c) = o;
-      if (dxd || dbias) {
+      if (want_d) {
         float4 od = drop4(o, thresh, scale, seed, off, (uint64_t)r * row_groups + (uint64_t)(c >> 2));
         if (dxd) store_act(dxd, dxd_bf16, (size_t)r * cols + c, od);
-        ad[i].x += od.x; ad[i].y += od.y; ad[i].z += od.z; ad[i].w += od.w;
+        if (dbias) { atomicAdd(sd + c, od.x); atomicAdd(sd + c + 1, od.y); atomicAdd(sd + c + 2, od.z); atomicAdd(sd + c + 3, od.w); }
       }
     }
   }
-  // block reduction of the per-column partials, then one atomic per column per block
-  __shared__ float red[kRowThreads / 32][1024 + 4];
+  __syncthreads();
   float* outs[3] = {dgamma, dbeta, dbias};
 #pragma unroll 1
   for (int k = 0; k < 3; ++k) {
-    if (!outs[k]) continue;  // uniform
-    float4* src = k == 0 ? ag : (k == 1 ? ab : ad);
-#pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
-      int c = 4 * (lane + 32 * i);
-      if (c < cols) *reinterpret_cast<float4*>(&red[wib][c]) = src[i];
-    }
-    __syncthreads();
+    if (!outs[k]) continue;
     for (int c = threadIdx.x; c < cols; c += kRowThreads) {
-      float t = 0.f;
-#pragma unroll
-      for (int w = 0; w < kRowThreads / 32; ++w) t += red[w][c];
-      atomicAdd(outs[k] + c, t);
+      if (partials) partials[((size_t)blockIdx.x * 3 + k) * cols + c] = acc_s[k * cols + c];
+      else atomicAdd(outs[k] + c, acc_s[k * cols + c]);
     }
-    __syncthreads();
+  }
+}
+
+// out_k[c] += sum over blocks of partials[blk][k][c]; block = 32 columns x 8 block-lanes
+__global__ void ln_bwd_finalize_kernel(const float* __restrict__ partials, int nblk, int cols, float* dgamma,
+                                       float* dbeta, float* dbias) {
+  __shared__ float red[8][33];
+  const int k = blockIdx.y;
+  float* out = k == 0 ? dgamma : (k == 1 ? dbeta : dbias);
+  if (!out) return;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
+  float t = 0.f;
+  if (c < cols)
+    for (int b = g; b < nblk; b += 8) t += partials[((size_t)b * 3 + k) * cols + c];
+  red[g][threadIdx.x & 31] = t;
+  __syncthreads();
+  if (g == 0 && c < cols) {
+    float u = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) u += red[w][threadIdx.x];
+    out[c] += u;
   }
 }
 
@@ -677,17 +700,22 @@ int samk_layernorm_fwd(const float* x, const float* gamma, const float* beta, fl
 
 int samk_layernorm_bwd(const float* dy, const float* x, const float* gamma, float eps, float* dx, void* dxd,
                        int dxd_dtype, float drop_p, unsigned long long seed, unsigned long long offset, float* dgamma,
-                       float* dbeta, float* dbias, int rows, int cols, void* stream) {
+                       float* dbeta, float* dbias, float* partials, int rows, int cols, void* stream) {
   SAMK_REQUIRE(dy && x && gamma && rows >= 0, "bad argument");
   SAMK_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 1024, "cols must be a multiple of 4, <= 1024");
   if (!rows) return SAMK_OK;
-  int grid = grid_for(rows, 8 * 8);
-  if (grid > 296) grid = 296;
-  layernorm_bwd_kernel<<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(
+  int grid = grid_for(rows, 8 * 4);
+  if (grid > 592) grid = 592;   // partials workspace is sized for 592 blocks (samk_layernorm_bwd_partials)
+  layernorm_bwd_kernel<<<grid, kRowThreads, 3 * cols * sizeof(float), (cudaStream_t)stream>>>(
       dy, x, gamma, eps, dx, dxd, dxd_dtype == SAMK_DT_BF16, drop_p > 0.f ? drop_threshold(drop_p) : 0u,
-      drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f, seed, offset, dgamma, dbeta, dbias, rows, cols);
+      drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f, seed, offset, dgamma, dbeta, dbias, partials, rows, cols);
+  int rc = check_launch(__func__);
+  if (rc || !partials) return rc;
+  ln_bwd_finalize_kernel<<<dim3((cols + 31) / 32, 3), 256, 0, (cudaStream_t)stream>>>(partials, grid, cols, dgamma, dbeta, dbias);
   return check_launch(__func__);
 }
+
+long long samk_layernorm_bwd_partials(int cols) { return 592LL * 3 * cols; }
 
 int samk_dropout_add(const float* a, const float* b, float* out, void* out2, int out2_dtype, int rows, int cols,
                      float drop_p, unsigned long long seed, unsigned long long offset, void* stream) {
@@ -707,7 +735,11 @@ int samk_colsum(const void* x, int x_dtype, long long ld, int rows, int cols, fl
     colsum_scalar_kernel<<<(cols * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, bf, ld, rows, cols, out);
     return check_launch(__func__);
   }
-  dim3 grid((cols / 4 + 63) / 64, 64);
+  const int gx = (cols / 4 + 63) / 64;
+  int gy = (148 * 4 + gx - 1) / gx;
+  if (gy > (rows + 3) / 4) gy = (rows + 3) / 4;
+  if (gy < 1) gy = 1;
+  dim3 grid(gx, gy);
   colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_dtype == SAMK_DT_BF16, ld, rows, cols, out);
   return check_launch(__func__);
 }

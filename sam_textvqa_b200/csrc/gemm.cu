@@ -11,6 +11,7 @@
 // (A = dY, B = X, contraction over tokens) without materialising transposes.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -20,8 +21,8 @@ namespace samk {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kGemmThreads = 192;
-constexpr int kEpiWarp0 = 2;
+constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter, each takes half the columns
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 
 struct EpiArgs {
   void* out; long long ldo; int out_bf16; int atomic_add; float alpha;
@@ -36,6 +37,8 @@ struct EpiArgs {
 // Apply the epilogue to `cnt` (<=32, multiple handled generally) consecutive columns of one row.
 __device__ __forceinline__ void epilogue_row_chunk(const EpiArgs& ep, float* v, int row, int col0, int cnt, int N) {
   const bool full = (cnt == 32) && ep.vec_ok;
+  float pre_v[32];
+  float* const v_in = v;
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] *= ep.alpha;
   if (ep.bias) {
@@ -46,10 +49,22 @@ __device__ __forceinline__ void epilogue_row_chunk(const EpiArgs& ep, float* v, 
         v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
       }
     } else {
-      for (int i = 0; i < cnt; ++i) v[i] += ep.bias[col0 + i];
+      _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) v[i] += ep.bias[col0 + i];
+    }
+  }
+  if (ep.act == 3) {
+    // out = gelu(v), pre = gelu'(v): one erf and one exp serve both (backward then only multiplies)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float x = v[i];
+      const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+      const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+      pre_v[i] = cdf + x * pdf;
+      v[i] = x * cdf;
     }
   }
   if (ep.pre) {
+    const float* v = (ep.act == 3) ? pre_v : v_in;
     if (ep.pre_bf16) {
       __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.pre) + (size_t)row * ep.ldpre + col0;
       if (full) {
@@ -58,7 +73,7 @@ __device__ __forceinline__ void epilogue_row_chunk(const EpiArgs& ep, float* v, 
           *reinterpret_cast<uint4*>(p + i) = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]),
                                                         pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
       } else {
-        for (int i = 0; i < cnt; ++i) p[i] = __float2bfloat16_rn(v[i]);
+        _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) p[i] = __float2bfloat16_rn(v[i]);
       }
     } else {
       float* p = reinterpret_cast<float*>(ep.pre) + (size_t)row * ep.ldpre + col0;
@@ -66,13 +81,35 @@ __device__ __forceinline__ void epilogue_row_chunk(const EpiArgs& ep, float* v, 
 #pragma unroll
         for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       } else {
-        for (int i = 0; i < cnt; ++i) p[i] = v[i];
+        _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) p[i] = v[i];
       }
     }
   }
   if (ep.act == 1) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+  } else if (ep.act == 4) {
+    if (ep.aux_bf16) {
+      const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (size_t)row * ep.ldaux + col0;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 u = *reinterpret_cast<const uint4*>(p + i);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 f = __bfloat1622float2(h[j]);
+            v[i + 2 * j] *= f.x;
+            v[i + 2 * j + 1] *= f.y;
+          }
+        }
+      } else {
+        _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) v[i] *= __bfloat162float(p[i]);
+      }
+    } else {
+      const float* p = reinterpret_cast<const float*>(ep.aux) + (size_t)row * ep.ldaux + col0;
+      _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) v[i] *= p[i];
+    }
   } else if (ep.act == 2) {
     if (ep.aux_bf16) {
       const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (size_t)row * ep.ldaux + col0;
@@ -89,11 +126,11 @@ __device__ __forceinline__ void epilogue_row_chunk(const EpiArgs& ep, float* v, 
           }
         }
       } else {
-        for (int i = 0; i < cnt; ++i) v[i] *= dgelu_erf(__bfloat162float(p[i]));
+        _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) v[i] *= dgelu_erf(__bfloat162float(p[i]));
       }
     } else {
       const float* p = reinterpret_cast<const float*>(ep.aux) + (size_t)row * ep.ldaux + col0;
-      for (int i = 0; i < cnt; ++i) v[i] *= dgelu_erf(p[i]);
+      _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) v[i] *= dgelu_erf(p[i]);
     }
   }
   if (ep.drop_thresh) {
@@ -118,7 +155,7 @@ __device__ __forceinline__ void epilogue_row_chunk(const EpiArgs& ep, float* v, 
         v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
       }
     } else {
-      for (int i = 0; i < cnt; ++i) v[i] += p[i];
+      _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) v[i] += p[i];
     }
   }
   if (ep.atomic_add) {
@@ -128,7 +165,7 @@ __device__ __forceinline__ void epilogue_row_chunk(const EpiArgs& ep, float* v, 
       for (int i = 0; i < 32; i += 4)
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p + i), "f"(v[i]), "f"(v[i + 1]), "f"(v[i + 2]), "f"(v[i + 3]) : "memory");
     } else {
-      for (int i = 0; i < cnt; ++i) atomicAdd(p + i, v[i]);
+      _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) atomicAdd(p + i, v[i]);
     }
   } else if (ep.out_bf16) {
     __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldo + col0;
@@ -138,7 +175,7 @@ __device__ __forceinline__ void epilogue_row_chunk(const EpiArgs& ep, float* v, 
         *reinterpret_cast<uint4*>(p + i) = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]),
                                                       pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
     } else {
-      for (int i = 0; i < cnt; ++i) p[i] = __float2bfloat16_rn(v[i]);
+      _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) p[i] = __float2bfloat16_rn(v[i]);
     }
   } else {
     float* p = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col0;
@@ -146,7 +183,7 @@ __device__ __forceinline__ void epilogue_row_chunk(const EpiArgs& ep, float* v, 
 #pragma unroll
       for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     } else {
-      for (int i = 0; i < cnt; ++i) p[i] = v[i];
+      _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) p[i] = v[i];
     }
   }
 }
@@ -160,7 +197,11 @@ template <int BN> struct GemmCfg {
   static constexpr int kTmemCols = 2 * BN;  // 256 or 512: power of two
 };
 
-template <int BN, int A_MN, int B_MN>
+// CL = cluster size along M (1 or 2).  With CL = 2 the two CTAs of a cluster work on vertically adjacent
+// output tiles that need the same B tile: each CTA fetches half of it and TMA-multicasts it into both
+// shared memories, cutting the L2->SM operand traffic per flop by a third (the kernel is L2-bandwidth
+// bound at 128x256 tiles otherwise).  Slots are released to both producers with a multicast commit.
+template <int BN, int A_MN, int B_MN, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const EpiArgs ep, int M, int N, int K, int split_k) {
@@ -178,10 +219,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
 
   const int m_tiles = (M + BM - 1) / BM;
+  const int m_groups = (m_tiles + CL - 1) / CL;     // a cluster takes CL vertically adjacent tiles
   const int n_tiles = (N + BN - 1) / BN;
   const int kb_total = (K + BK - 1) / BK;
   const int kb_per = (kb_total + split_k - 1) / split_k;
-  const int num_work = m_tiles * n_tiles * split_k;
+  const int num_work = m_groups * n_tiles * split_k;
+  const int cta_rank = CL > 1 ? (int)ptx::cluster_ctarank() : 0;
+  const int work0 = blockIdx.x / CL, work_stride = gridDim.x / CL;
+  constexpr uint16_t kMcastMask = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
@@ -189,15 +234,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < Cfg::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-      for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], 4); }
+      for (int s = 0; s < Cfg::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], CL); }
+      for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], kEpiWarps); }
       ptx::fence_barrier_init();
     }
     __syncwarp();
     ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();   // peer barriers must be initialised before remote arrivals / multicasts
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -205,10 +251,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      for (int w = work0; w < num_work; w += work_stride) {
         const int split = w % split_k;
         const int tile = w / split_k;
-        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        const int m0 = ((tile / n_tiles) * CL + cta_rank) * BM, n0 = (tile % n_tiles) * BN;
         const int kb0 = split * kb_per;
         const int kb1 = min(kb_total, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -222,11 +268,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
           }
-          if (B_MN) {
+          if (CL == 1) {
+            if (B_MN) {
 #pragma unroll
-            for (int g = 0; g < BN / 64; ++g) ptx::tma_load_2d(sb + g * (BK * 128), &tmB, &full_bar[stage], n0 + g * 64, kb * BK);
+              for (int g = 0; g < BN / 64; ++g) ptx::tma_load_2d(sb + g * (BK * 128), &tmB, &full_bar[stage], n0 + g * 64, kb * BK);
+            } else {
+              ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+            }
           } else {
-            ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+            // this CTA fetches its 1/CL share of the B tile and multicasts it to the whole cluster
+            if (B_MN) {
+#pragma unroll
+              for (int g = 0; g < BN / 64 / CL; ++g) {
+                const int gg = cta_rank * (BN / 64 / CL) + g;
+                ptx::tma_load_2d_mcast(sb + gg * (BK * 128), &tmB, &full_bar[stage], n0 + gg * 64, kb * BK, kMcastMask);
+              }
+            } else {
+              ptx::tma_load_2d_mcast(sb + cta_rank * (BN / CL) * 128, &tmB, &full_bar[stage], kb * BK,
+                                     n0 + cta_rank * (BN / CL), kMcastMask);
+            }
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
@@ -237,7 +297,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN, B_MN);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+    for (int w = work0; w < num_work; w += work_stride) {
       const int split = w % split_k;
       const int kb0 = split * kb_per;
       const int kb1 = min(kb_total, kb0 + kb_per);
@@ -258,7 +318,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                         : ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024);
             ptx::umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          ptx::umma_commit(&empty_bar[stage]);                 // smem slot free once these MMAs retire
+          if (CL == 1) ptx::umma_commit(&empty_bar[stage]);      // smem slot free once these MMAs retire
+          else ptx::umma_commit_mcast(&empty_bar[stage], kMcastMask);   // ... in every CTA that multicasts into it
           if (kb == kb1 - 1) ptx::umma_commit(&tfull_bar[acc]);  // accumulator ready
         }
         __syncwarp();
@@ -270,12 +331,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue =====================
-    const int lane_grp = warp & 3;  // TMEM lane quarter this warp may access
+    const int lane_grp = warp & 3;          // TMEM lane quarter this warp may access (warp id % 4)
+    const int col_half = (warp - 2) >> 2;   // which half of the tile's columns this warp drains
     int acc = 0; uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+    for (int w = work0; w < num_work; w += work_stride) {
       const int split = w % split_k;
       const int tile = w / split_k;
-      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      const int m0 = ((tile / n_tiles) * CL + cta_rank) * BM, n0 = (tile % n_tiles) * BN;
       const int kb0 = split * kb_per;
       const bool has_k = min(kb_total, kb0 + kb_per) > kb0;
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
@@ -283,7 +345,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int row = m0 + lane_grp * 32 + lane;
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(lane_grp * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = col_half * (BN / 64); c < (col_half + 1) * (BN / 64); ++c) {
         const int col0 = n0 + c * 32;
         if (col0 >= N) break;  // warp-uniform
         uint32_t r[32];
@@ -293,8 +355,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = has_k ? __uint_as_float(r[i]) : 0.f;
-          const int cnt = min(32, N - col0);
-          epilogue_row_chunk(ep, v, row, col0, cnt, N);
+          epilogue_row_chunk(ep, v, row, col0, min(32, N - col0), N);
         }
       }
       ptx::tc_fence_before();
@@ -305,7 +366,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();   // no CTA may exit while its peer can still signal its barriers
+  else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
@@ -389,11 +451,11 @@ int sm_count() {
   return g_sm_count;
 }
 
-template <int BN, int A_MN, int B_MN>
+template <int BN, int A_MN, int B_MN, int CL>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiArgs& ep, int M, int N, int K, int split_k,
                      cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CL>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) {
@@ -402,13 +464,38 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiArgs
     }
     attr_set = true;
   }
-  const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
-  const int work = m_tiles * n_tiles * split_k;
-  int grid = sm_count();
-  if (grid <= 0) grid = 148;
-  if (work < grid) grid = work;
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, ep, M, N, K, split_k);
+  const int m_groups = ((M + BM - 1) / BM + CL - 1) / CL, n_tiles = (N + BN - 1) / BN;
+  const int work = m_groups * n_tiles * split_k;
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  int clusters = sms / CL;
+  if (work < clusters) clusters = work;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CL);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, M, N, K, split_k);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("samk_gemm_bf16: cluster launch failed: %s", cudaGetErrorString(e));
+    return SAMK_ERR_CUDA;
+  }
   return check_launch("samk_gemm_bf16");
+}
+
+static int g_gemm_cluster = -1;
+static int gemm_cluster() {
+  if (g_gemm_cluster < 0) {
+    const char* s = getenv("SAMK_GEMM_CLUSTER");
+    g_gemm_cluster = (s && s[0] == '2') ? 2 : 1;
+  }
+  return g_gemm_cluster;
 }
 
 }  // namespace samk
@@ -436,7 +523,8 @@ extern "C" int samk_gemm_bf16(const void* A, int a_mn, long long lda, const void
   ep.drop_scale = e->drop_p > 0.f ? 1.0f / (1.0f - e->drop_p) : 1.0f;
   ep.seed = e->drop_seed; ep.offset = e->drop_offset;
   ep.residual = e->residual; ep.ldres = e->ldres;
-  if (ep.act == 2 && !ep.aux) { set_error("samk_gemm_bf16: act=2 needs aux"); return SAMK_ERR_ARG; }
+  if ((ep.act == 2 || ep.act == 4) && !ep.aux) { set_error("samk_gemm_bf16: act=2/4 needs aux"); return SAMK_ERR_ARG; }
+  if (ep.act == 3 && !ep.pre) { set_error("samk_gemm_bf16: act=3 needs pre"); return SAMK_ERR_ARG; }
   auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
   ep.vec_ok = (N % 4 == 0) && al16(ep.out) && (ep.ldo % 8 == 0) && (!ep.bias || al16(ep.bias)) &&
               (!ep.pre || (al16(ep.pre) && ep.ldpre % 8 == 0)) && (!ep.aux || (al16(ep.aux) && ep.ldaux % 8 == 0)) &&
@@ -462,11 +550,16 @@ extern "C" int samk_gemm_bf16(const void* A, int a_mn, long long lda, const void
   if (a_mn) rc = make_tmap_bf16_2d(&ta, A, K, M, lda, 64, BK);
   else rc = make_tmap_bf16_2d(&ta, A, M, K, lda, BK, BM);
   if (rc) return rc;
+  const int cl = gemm_cluster();
   if (b_mn) rc = make_tmap_bf16_2d(&tb, B, K, N, ldb, 64, BK);
-  else rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, BK, bn);
+  else rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, BK, bn / cl);     // each cluster CTA fetches bn/cl rows of B
   if (rc) return rc;
 
-#define SAMK_LAUNCH(BN_, AM_, BM_) return launch_tc<BN_, AM_, BM_>(ta, tb, ep, M, N, K, split_k, stream)
+#define SAMK_LAUNCH(BN_, AM_, BM_)                                                        \
+  do {                                                                                    \
+    if (cl == 2) return launch_tc<BN_, AM_, BM_, 2>(ta, tb, ep, M, N, K, split_k, stream); \
+    return launch_tc<BN_, AM_, BM_, 1>(ta, tb, ep, M, N, K, split_k, stream);              \
+  } while (0)
   if (bn == 256) {
     if (!a_mn && !b_mn) SAMK_LAUNCH(256, 0, 0);
     if (!a_mn && b_mn) SAMK_LAUNCH(256, 0, 1);

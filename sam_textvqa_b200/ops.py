@@ -61,6 +61,43 @@ def _count(n=1):
     launch_count += n
 
 
+# ---- gradient targets ---------------------------------------------------------------------------------
+direct_grad_accumulation = True   # write weight gradients straight into existing fp32 .grad buffers
+
+
+def _gbuf(p):
+    """(buffer, direct): where the gradient of parameter p is accumulated.  When p.grad already exists
+    (e.g. views of dp.FlatGradBuffer) the kernels add into it and autograd gets None for that input;
+    otherwise a zeroed buffer is returned to autograd."""
+    g = p.grad if p.is_leaf else None
+    if (direct_grad_accumulation and g is not None and g.dtype == torch.float32 and g.is_contiguous()
+            and g.shape == p.shape and g.device == p.device):
+        return g, True
+    return torch.zeros_like(p, dtype=torch.float32), False
+
+
+def _ret(buf_direct):
+    return None if buf_direct[1] else buf_direct[0]
+
+
+_ln_ws = {}
+
+
+def _ln_partials(dev, cols):
+    key = (dev, cols)
+    if key not in _ln_ws:
+        _ln_ws[key] = torch.empty(int(lib().samk_layernorm_bwd_partials(cols)), dtype=torch.float32, device=dev)
+    return _ln_ws[key]
+
+
+def _ln_bwd(dy, x, gamma, eps, dx, dxd, p, drop, dg, db, dbias, rows, cols):
+    check(lib().samk_layernorm_bwd(ptr(dy), ptr(x), ptr(gamma), eps, ptr(dx), ptr(dxd),
+                                   _dt(dxd) if dxd is not None else 0, p, drop[0], drop[1], ptr(dg), ptr(db),
+                                   ptr(dbias), ptr(_ln_partials(dy.device, cols)), rows, cols, stream_ptr()),
+          "layernorm_bwd")
+    _count(2)
+
+
 # ---- dropout stream ------------------------------------------------------------------------------
 class _Rng(object):
     def __init__(self):
@@ -221,6 +258,7 @@ class LinearFn(torch.autograd.Function):
         y = torch.empty(M, N, dtype=torch.float32, device=x2d.device)
         gemm(x_op, False, w_op, False, M, N, K, y, bias=bias)
         ctx.save_for_backward(x2d, weight)
+        ctx.bias_ref = bias
         ctx.dims = (M, N, K)
         ctx.x_needs_grad = x2d.requires_grad
         return y
@@ -241,11 +279,11 @@ class LinearFn(torch.autograd.Function):
                 M, K, dtype=torch.float32, device=dy.device)
             w_op = weight_operand([weight[:, :K]] if weight.shape[1] != K else [weight], True)
             gemm(dy_k, False, w_op, True, M, K, N, dx[:, :K])
-        dW = torch.zeros_like(weight, dtype=torch.float32)
-        gemm(dy_mn, True, x_mn, True, N, K, M, dW[:, :K], accumulate=True)
-        db = torch.zeros(N, dtype=torch.float32, device=dy.device)
-        colsum_into(dy, db)
-        return dx, dW, db, None
+        ctx_bias = ctx.bias_ref
+        dW, db = _gbuf(weight), _gbuf(ctx_bias)
+        gemm(dy_mn, True, x_mn, True, N, K, M, dW[0][:, :K], accumulate=True)
+        colsum_into(dy, db[0])
+        return dx, _ret(dW), _ret(db), None
 
 
 def linear(x2d, weight, bias, kdim=None):
@@ -262,6 +300,7 @@ class LayerNormFn(torch.autograd.Function):
                                        x2d.shape[1], stream_ptr()), "layernorm_fwd")
         _count()
         ctx.save_for_backward(x2d, gamma)
+        ctx.beta_ref = beta
         ctx.eps = eps
         return y
 
@@ -270,12 +309,9 @@ class LayerNormFn(torch.autograd.Function):
         x2d, gamma = ctx.saved_tensors
         dy = dy.contiguous()
         dx = torch.empty_like(x2d)
-        dg = torch.zeros_like(gamma)
-        db = torch.zeros_like(gamma)
-        check(lib().samk_layernorm_bwd(ptr(dy), ptr(x2d), ptr(gamma), ctx.eps, ptr(dx), None, 0, 0.0, 0, 0, ptr(dg),
-                                       ptr(db), None, x2d.shape[0], x2d.shape[1], stream_ptr()), "layernorm_bwd")
-        _count()
-        return dx, dg, db, None
+        dg, db = _gbuf(gamma), _gbuf(ctx.beta_ref)
+        _ln_bwd(dy, x2d, gamma, ctx.eps, dx, None, 0.0, (0, 0), dg[0], db[0], None, x2d.shape[0], x2d.shape[1])
+        return dx, _ret(dg), _ret(db), None
 
 
 def layer_norm(x2d, gamma, beta, eps):
@@ -343,6 +379,7 @@ class BertEmbedFn(torch.autograd.Function):
               "bert_embed_fwd")
         _count()
         ctx.save_for_backward(ids, word, pos, type_, gamma)
+        ctx.beta_ref = beta
         return out.view(B, T, d)
 
     @staticmethod
@@ -351,13 +388,12 @@ class BertEmbedFn(torch.autograd.Function):
         B, T = ids.shape
         d = word.shape[1]
         dout = dout.contiguous()
-        dword, dpos, dtype_ = torch.zeros_like(word), torch.zeros_like(pos), torch.zeros_like(type_)
-        dg, db = torch.zeros_like(gamma), torch.zeros_like(gamma)
+        gs = [_gbuf(t) for t in (word, pos, type_, gamma, ctx.beta_ref)]
         check(lib().samk_bert_embed_bwd(ptr(dout), ptr(ids), ptr(word), ptr(pos), ptr(type_), ptr(gamma), ctx.eps,
-                                        ptr(dword), ptr(dpos), ptr(dtype_), ptr(dg), ptr(db), B * T, T, d, ctx.p,
-                                        ctx.drop[0], ctx.drop[1], stream_ptr()), "bert_embed_bwd")
+                                        ptr(gs[0][0]), ptr(gs[1][0]), ptr(gs[2][0]), ptr(gs[3][0]), ptr(gs[4][0]),
+                                        B * T, T, d, ctx.p, ctx.drop[0], ctx.drop[1], stream_ptr()), "bert_embed_bwd")
         _count()
-        return None, dword, dpos, dtype_, dg, db, None, None
+        return (None,) + tuple(_ret(g) for g in gs) + (None, None)
 
 
 class PrevPredFn(torch.autograd.Function):
@@ -384,14 +420,16 @@ class PrevPredFn(torch.autograd.Function):
         prev, cls_w, ocr_in, pos, type_, ag, ab, og, ob, eg, eb = ctx.saved_tensors
         B, D, V, R, d = ctx.dims
         dout = dout.contiguous()
-        grads = [torch.zeros_like(t) for t in (cls_w, ocr_in, pos, type_, ag, ab, og, ob, eg, eb)]
+        gs = [_gbuf(t) if t.is_leaf else (torch.zeros_like(t), False)
+              for t in (cls_w, ocr_in, pos, type_, ag, ab, og, ob, eg, eb)]
+        grads = [g[0] for g in gs]
         ln6 = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in (ag, ab, og, ob, eg, eb)])
         g10 = (ctypes.c_void_p * 10)(*[t.data_ptr() for t in grads])
         check(lib().samk_prevpred_bwd(ptr(dout), ptr(prev), ptr(cls_w), ptr(ocr_in), ptr(pos), ptr(type_), ln6,
                                       ctx.eps, g10, B, D, V, R, d, ctx.p, ctx.drop[0], ctx.drop[1], stream_ptr()),
               "prevpred_bwd")
         _count()
-        return (None,) + tuple(grads) + (None, None)
+        return (None,) + tuple(_ret(g) for g in gs) + (None, None)
 
 
 # ---- attention ------------------------------------------------------------------------------------------
@@ -508,7 +546,7 @@ class BertLayerFn(torch.autograd.Function):
         a_in = a_act if a_act is not None else a
         h = torch.empty(M, F, dtype=adt, device=dev)
         g = torch.empty(M, F, dtype=adt, device=dev)
-        gemm(operand(a_in, "a", False), False, weight_operand([iw], False), False, M, F, d, g, bias=ib, act=1, pre=h)
+        gemm(operand(a_in, "a", False), False, weight_operand([iw], False), False, M, F, d, g, bias=ib, act=3, pre=h)  # h := gelu'(pre-activation)
         y2 = torch.empty(M, d, dtype=torch.float32, device=dev)
         gemm(operand(g, "a", False), False, weight_operand([o2w], False), False, M, d, F, y2, bias=o2b, drop_p=p_hid,
              drop=drops[2], residual=a)
@@ -525,60 +563,47 @@ class BertLayerFn(torch.autograd.Function):
         (dims, spatial, quad_mask, p_attn, p_hid, eps) = ctx.cfg
         B, L, H, T, A, D = dims
         x2, valid, rel, qkv, ctx_t, lse, y1, a_in, h, g, y2, allow = ctx.saved_tensors[:12]
-        qw, qb, kw, kb, vw, vb, ow, ob, g1, b1, iw, ib, o2w, o2b, g2, b2 = ctx.saved_tensors[12:]
+        P = ctx.saved_tensors[12:]
+        qw, qb, kw, kb, vw, vb, ow, ob, g1, b1, iw, ib, o2w, o2b, g2, b2 = P
+        G = [_gbuf(p) for p in P]            # same order as P
+        (Gqw, Gqb, Gkw, Gkb, Gvw, Gvb, Gow, Gob, Gg1, Gb1, Giw, Gib, Go2w, Go2b, Gg2, Gb2) = [x[0] for x in G]
         dev = dout.device
         adt = act_dtype()
         M, d, F = B * L, x2.shape[1], iw.shape[0]
         dout = dout.contiguous().view(M, d)
-        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
 
         # ---- LN2 backward (+ dropout mask of the FFN output, + b_2 gradient)
         dy2 = torch.empty(M, d, dtype=torch.float32, device=dev)      # grad wrt (dropout(dense)+a)
         dY2 = torch.empty(M, d, dtype=adt, device=dev)                 # grad wrt dense output
-        dg2, db2, do2b = z(d), z(d), z(d)
-        check(lib().samk_layernorm_bwd(ptr(dout), ptr(y2), ptr(g2), eps, ptr(dy2), ptr(dY2), _dt(dY2), p_hid,
-                                       ctx.drops[2][0], ctx.drops[2][1], ptr(dg2), ptr(db2), ptr(do2b), M, d,
-                                       stream_ptr()), "ln2_bwd")
-        _count()
-        # ---- FFN2: dgrad (fused with GELU') and wgrad
-        dY2_k = operand(dY2, "a", False)
+        _ln_bwd(dout, y2, g2, eps, dy2, dY2, p_hid, ctx.drops[2], Gg2, Gb2, Go2b, M, d)
+        # ---- FFN2: dgrad (fused with the stored GELU') and wgrad
         dh = torch.empty(M, F, dtype=adt, device=dev)
-        gemm(dY2_k, False, weight_operand([o2w], True), True, M, F, d, dh, act=2, aux=h)
-        do2w = z(d, F)
-        gemm(operand(dY2, "a", True), True, operand(g, "b", True), True, d, F, M, do2w, accumulate=True)
+        gemm(operand(dY2, "a", False), False, weight_operand([o2w], True), True, M, F, d, dh, act=4, aux=h)
+        gemm(operand(dY2, "a", True), True, operand(g, "b", True), True, d, F, M, Go2w, accumulate=True)
         # ---- FFN1
-        dib = z(F)
-        colsum_into(dh, dib)
+        colsum_into(dh, Gib)
         da = torch.empty(M, d, dtype=torch.float32, device=dev)
         gemm(operand(dh, "a", False), False, weight_operand([iw], True), True, M, d, F, da, residual=dy2)
-        diw = z(F, d)
-        gemm(operand(dh, "a", True), True, operand(a_in, "b", True), True, F, d, M, diw, accumulate=True)
+        gemm(operand(dh, "a", True), True, operand(a_in, "b", True), True, F, d, M, Giw, accumulate=True)
         # ---- LN1 backward (+ dropout mask of the attention output dense, + b_o gradient)
         dy1 = torch.empty(M, d, dtype=torch.float32, device=dev)
         dY1 = torch.empty(M, d, dtype=adt, device=dev)
-        dg1, db1, dob = z(d), z(d), z(d)
-        check(lib().samk_layernorm_bwd(ptr(da), ptr(y1), ptr(g1), eps, ptr(dy1), ptr(dY1), _dt(dY1), p_hid,
-                                       ctx.drops[1][0], ctx.drops[1][1], ptr(dg1), ptr(db1), ptr(dob), M, d,
-                                       stream_ptr()), "ln1_bwd")
-        _count()
+        _ln_bwd(da, y1, g1, eps, dy1, dY1, p_hid, ctx.drops[1], Gg1, Gb1, Gob, M, d)
         # ---- attention output dense
         dctx = torch.empty(M, d, dtype=adt, device=dev)
         gemm(operand(dY1, "a", False), False, weight_operand([ow], True), True, M, d, d, dctx)
-        dow = z(d, d)
-        gemm(operand(dY1, "a", True), True, operand(ctx_t, "b", True), True, d, d, M, dow, accumulate=True)
+        gemm(operand(dY1, "a", True), True, operand(ctx_t, "b", True), True, d, d, M, Gow, accumulate=True)
         # ---- attention core
         dqkv = attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p_attn, ctx.drops[0], allow)
-        dbqkv = z(3 * d)
-        colsum_into(dqkv, dbqkv)
-        # ---- fused q|k|v projection
+        # ---- fused q|k|v projection: one dgrad, three wgrads (separate parameter gradients)
         dx = torch.empty(M, d, dtype=torch.float32, device=dev)
         gemm(operand(dqkv, "a", False), False, weight_operand([qw, kw, vw], True), True, M, d, 3 * d, dx, residual=dy1)
-        dwqkv = z(3 * d, d)
-        gemm(operand(dqkv, "a", True), True, operand(x2, "b", True), True, 3 * d, d, M, dwqkv, accumulate=True)
-
-        grads = (dwqkv[:d], dbqkv[:d], dwqkv[d:2 * d], dbqkv[d:2 * d], dwqkv[2 * d:], dbqkv[2 * d:],
-                 dow, dob, dg1, db1, diw, dib, do2w, do2b, dg2, db2)
-        return (dx.view(B, L, d), None, None, None) + grads
+        x_mn = operand(x2, "b", True)
+        for part, (Gw, Gb) in enumerate(((Gqw, Gqb), (Gkw, Gkb), (Gvw, Gvb))):
+            sl = dqkv[:, part * d:(part + 1) * d]
+            colsum_into(sl, Gb)
+            gemm(operand(sl, "a", True), True, x_mn, True, d, d, M, Gw, accumulate=True)
+        return (dx.view(B, L, d), None, None, None) + tuple(_ret(x) for x in G)
 
 
 # ---- output heads + loss -------------------------------------------------------------------------------------
@@ -607,16 +632,19 @@ class OutputFn(torch.autograd.Function):
                                         stream_ptr()), "ptr_scores_fwd")
         _count()
         ctx.dims = (B, D, R, V, d, dq)
+        ctx.bias_refs = (cb, qb, kb)
         ctx.save_for_backward(dec2, ocr2, q, k, cw, qw, kw)
         return scores.view(B, D, V + R)
 
     @staticmethod
     def backward(ctx, ds):
         dec2, ocr2, q, k, cw, qw, kw = ctx.saved_tensors
+        cb, qb, kb = ctx.bias_refs
         B, D, R, V, d, dq = ctx.dims
         dev = ds.device
         ds = ds.contiguous().view(B * D, V + R)
-        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        G = [_gbuf(p) for p in (cw, cb, qw, qb, kw, kb)]
+        Gcw, Gcb, Gqw, Gqb, Gkw, Gkb = [x[0] for x in G]
         dq_ = torch.empty_like(q)
         dk_ = torch.empty_like(k)
         check(lib().samk_ptr_scores_bwd(ptr(ds), V + R, V, ptr(q), ptr(k), ptr(dq_), ptr(dk_), B, D, R, dq,
@@ -628,27 +656,22 @@ class OutputFn(torch.autograd.Function):
             dq_a, dk_a = cast_bf16(dq_), cast_bf16(dk_)
         else:
             dq_a, dk_a = dq_, dk_
+        dec_mn, ocr_mn = operand(dec2, "b", True), operand(ocr2, "b", True)
         # classifier
         ddec = torch.empty(B * D, d, dtype=torch.float32, device=dev)
         gemm(operand(dsv, "a", False), False, weight_operand([cw], True), True, B * D, d, V, ddec)
-        dcw = z(V, d)
-        gemm(operand(dsv, "a", True), True, operand(dec2, "b", True), True, V, d, B * D, dcw, accumulate=True)
-        dcb = z(V)
-        colsum_into(ds[:, :V], dcb)
+        gemm(operand(dsv, "a", True), True, dec_mn, True, V, d, B * D, Gcw, accumulate=True)
+        colsum_into(ds[:, :V], Gcb)
         # pointer query / key projections
         ddec2 = torch.empty(B * D, d, dtype=torch.float32, device=dev)
         gemm(operand(dq_a, "a", False), False, weight_operand([qw], True), True, B * D, d, dq, ddec2, residual=ddec)
-        dqw = z(dq, d)
-        gemm(operand(dq_a, "a", True), True, operand(dec2, "b", True), True, dq, d, B * D, dqw, accumulate=True)
-        dqb = z(dq)
-        colsum_into(dq_, dqb)
+        gemm(operand(dq_a, "a", True), True, dec_mn, True, dq, d, B * D, Gqw, accumulate=True)
+        colsum_into(dq_, Gqb)
         docr = torch.empty(B * R, d, dtype=torch.float32, device=dev)
         gemm(operand(dk_a, "a", False), False, weight_operand([kw], True), True, B * R, d, dq, docr)
-        dkw = z(dq, d)
-        gemm(operand(dk_a, "a", True), True, operand(ocr2, "b", True), True, dq, d, B * R, dkw, accumulate=True)
-        dkb = z(dq)
-        colsum_into(dk_, dkb)
-        return ddec2.view(B, D, d), docr.view(B, R, d), None, dcw, dcb, dqw, dqb, dkw, dkb
+        gemm(operand(dk_a, "a", True), True, ocr_mn, True, dq, d, B * R, Gkw, accumulate=True)
+        colsum_into(dk_, Gkb)
+        return (ddec2.view(B, D, d), docr.view(B, R, d), None) + tuple(_ret(x) for x in G)
 
 
 class BceLossFn(torch.autograd.Function):
