@@ -228,12 +228,38 @@ def run_samk(args):
     ms = timed(lambda: step(resident, resident_adj), args.steps)
     launches = ops.launch_count - l0
 
-    def e2e_step():
-        up, a = upload()
-        return step(up, a).item()
+    # ---- end to end: every step's inputs come from pinned host memory; the copy of step i+1 runs on a
+    # side stream while step i computes (double-buffered device staging), and each step ends with a
+    # device->host read of its loss.  All K uploads and K loss reads are inside the timed region.
+    copy_stream = torch.cuda.Stream()
+    staged = [None, None]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
 
-    e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    def stage(slot):
+        with torch.cuda.stream(copy_stream):
+            staged[slot] = upload()
+            ready[slot].record(copy_stream)
+
+    def e2e_run(steps):
+        stage(0)
+        for i in range(steps):
+            torch.cuda.current_stream().wait_event(ready[i % 2])
+            if i + 1 < steps:
+                stage((i + 1) % 2)
+            up, a = staged[i % 2]
+            step(up, a).item()
+
+    e2e_run(2)
+    barrier()
+    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_ev.record()
+    e2e_run(args.steps)
+    e_ev.record()
+    barrier()
+    ms_t = torch.tensor([s_ev.elapsed_time(e_ev)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_e2e = ms_t.item() / args.steps
     clocks = sampler.stop() if sampler else None
 
     # ---- roofline of the dominant kernel family (tcgen05 GEMM), instrumented extra steps ----

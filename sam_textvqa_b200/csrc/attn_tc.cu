@@ -168,6 +168,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       ptx::tma_load_2d(sK, &tmKV, tma_bar, (H + h) * TDH, b * L + k0);
       ptx::tma_load_2d(sV, &tmKV, tma_bar, (2 * H + h) * TDH, b * L + k0);
     }
+    // allow-bit words of this row for the whole key tile: issued before the waits so the global-load
+    // latency hides behind TMA + MMA
+    uint32_t aw_t[KVT / 32];
+#pragma unroll
+    for (int c = 0; c < KVT / 32; ++c) aw_t[c] = allow_word(a, b, h, row, k0 + c * 32);
     ptx::mbar_wait(tma_bar, t & 1);
     if (tid == 0) {
       ptx::tc_fence_after();
@@ -182,12 +187,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
     // ---- pass 1: masked row maximum of this key tile
     float tmax = -INFINITY;
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < KVT / 32; ++c) {
       uint32_t r[32];
       ptx::tmem_ld_32x32(t_lane + c * 32, r);
       ptx::tmem_ld_wait();
-      const uint32_t aw = allow_word(a, b, h, row, k0 + c * 32);
+      const uint32_t aw = aw_t[c];
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         if ((aw >> i) & 1u) tmax = fmaxf(tmax, __uint_as_float(r[i]));
@@ -212,12 +217,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     m_run = m_new;
     // ---- pass 2: probabilities -> bf16 P tile (dropout applied), running sum from undropped p
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < KVT / 32; ++c) {
       uint32_t r[32];
       ptx::tmem_ld_32x32(t_lane + c * 32, r);
       ptx::tmem_ld_wait();
-      const uint32_t aw = allow_word(a, b, h, row, k0 + c * 32);
+      const uint32_t aw = aw_t[c];
       const uint32_t kw = aw ? keep_word(a, b, h, row, k0 + c * 32) : 0u;
       float p[32];
 #pragma unroll
@@ -364,21 +369,24 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       }
       ptx::umma_commit(s_bar);
     }
-    ptx::mbar_wait(s_bar, t & 1);
-    ptx::tc_fence_after();
-
-    // ---- P and dS for query row i = i0 + r, this thread's two 32-key chunks
+    // per-row scalars and allow words first: their global-load latency hides behind TMA + MMA
     const int i = i0 + r;
     const float lse2 = i < L ? a.lse[((size_t)b * H + h) * L + i] * kLog2e : INFINITY;
     const float dlt = i < L ? a.delta[((size_t)b * H + h) * L + i] : 0.f;
-#pragma unroll 1
+    uint32_t aw_t[2];
+    aw_t[0] = allow_word(a, b, h, i, j0 + (half * 2) * 32);
+    aw_t[1] = allow_word(a, b, h, i, j0 + (half * 2 + 1) * 32);
+    ptx::mbar_wait(s_bar, t & 1);
+    ptx::tc_fence_after();
+
+#pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
       const int c = half * 2 + cc;
       uint32_t s[32], d[32];
       ptx::tmem_ld_32x32(t_lane + kScol + c * 32, s);
       ptx::tmem_ld_32x32(t_lane + kDPcol + c * 32, d);
       ptx::tmem_ld_wait();
-      const uint32_t aw = allow_word(a, b, h, i, j0 + c * 32);
+      const uint32_t aw = aw_t[cc];
       const uint32_t kw = aw ? keep_word(a, b, h, i, j0 + c * 32) : 0u;
       float pv[32], dsv[32];
 #pragma unroll
