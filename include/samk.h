@@ -171,6 +171,8 @@ typedef struct samk_attn_params {
   unsigned long long drop_seed, drop_offset;
   const uint32_t* allow_bits; /* tensor-core path: [B, spatial?H:1, L, ceil(L/32)] from samk_attn_build_mask */
   float* dq_accum;            /* tensor-core backward: fp32 [B*L, H*64] scratch for the dQ reduction */
+  int q_begin;                /* forward only: compute query rows >= q_begin (rounded down to the kernel's
+                                 row tile); 0 = all rows.  Used by the cached greedy decoder (decoder rows only). */
 } samk_attn_params;
 int samk_attn_fwd(const samk_attn_params* p, int impl, void* stream);
 int samk_attn_bwd(const samk_attn_params* p, int impl, void* stream);

@@ -31,7 +31,7 @@ class AttnParams(ctypes.Structure):
         ("delta", c_void_p), ("dtype", c_int), ("B", c_int), ("H", c_int), ("head_dim", c_int), ("T", c_int),
         ("A", c_int), ("D", c_int), ("key_valid", c_void_p), ("rel_bits", c_void_p), ("quadrant_mask", ctypes.c_uint),
         ("spatial", c_int), ("scale", c_float), ("drop_p", c_float), ("drop_seed", c_ull), ("drop_offset", c_ull),
-        ("allow_bits", c_void_p), ("dq_accum", c_void_p),
+        ("allow_bits", c_void_p), ("dq_accum", c_void_p), ("q_begin", c_int),
     ]
 
 

@@ -30,6 +30,7 @@ struct AttnArgs {
   float scale;
   uint32_t drop_thresh; float drop_scale; unsigned long long seed, off;
   AttnMask m;
+  int q_blk0;   // forward: first 32-row block to compute
 };
 
 __device__ __forceinline__ float ld_elem(const void* p, int bf16, size_t i) {
@@ -88,7 +89,7 @@ attn_rows_kernel(const AttnArgs a) {
   const int L = m.L;
   const int b = blockIdx.z, h = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * OWN + warp * 4;
+  const int row0 = (blockIdx.x + (kBwd ? 0 : a.q_blk0)) * OWN + warp * 4;
   const long long ld = 3LL * a.H * DH;
   const size_t qbase = (size_t)b * L * ld + (size_t)h * DH;
   const size_t kbase = qbase + (size_t)a.H * DH, vbase = kbase + (size_t)a.H * DH;
@@ -365,6 +366,7 @@ static int fill_args(AttnArgs& a, const samk_attn_params* p) {
   a.m.valid = p->key_valid; a.m.rel = p->spatial ? p->rel_bits : nullptr;
   a.m.T = p->T; a.m.A = p->A; a.m.D = p->D; a.m.L = p->T + p->A + p->D;
   a.m.quad_mask = p->spatial ? p->quadrant_mask : 0u; a.m.spatial = p->spatial ? 1 : 0;
+  a.q_blk0 = p->q_begin > 0 ? p->q_begin / OWN : 0;
   return SAMK_OK;
 }
 
@@ -374,7 +376,7 @@ int attn_simt_fwd(const samk_attn_params* p, cudaStream_t stream) {
   if (rc) return rc;
   if (!p->ctx || !p->lse) { set_error("samk_attn_fwd: ctx/lse null"); return SAMK_ERR_ARG; }
   if (!a.B || !a.m.L) return SAMK_OK;
-  dim3 grid((a.m.L + OWN - 1) / OWN, a.H, a.B);
+  dim3 grid((a.m.L + OWN - 1) / OWN - a.q_blk0, a.H, a.B);
   if ((rc = ensure_smem(attn_rows_kernel<false>, kRowsSmem))) return rc;
   attn_rows_kernel<false><<<grid, kAttnThreads, kRowsSmem, stream>>>(a);
   return check_launch("samk_attn_fwd(simt)");

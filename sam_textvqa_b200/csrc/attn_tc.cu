@@ -76,6 +76,7 @@ struct TcArgs {
   void* dqkv; float* dq_accum;      // bwd outputs
   const uint32_t* allow; int Hm, W;
   int B, H, L;
+  int q_tile0;                      // forward: first 128-row query tile to compute
   float scale_log2;                 // scale * log2(e)
   float scale;
   uint32_t drop_thresh; float drop_scale; unsigned long long seed, off;
@@ -139,7 +140,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   constexpr uint32_t kOcol = 192;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = (blockIdx.x + a.q_tile0) * 128, h = blockIdx.y, b = blockIdx.z;
   const int L = a.L, H = a.H;
   const int n_kv = (L + KVT - 1) / KVT;
 
@@ -495,6 +496,7 @@ static int fill_tc(TcArgs& a, const samk_attn_params* p) {
   a.drop_thresh = p->drop_p > 0.f ? drop_threshold(p->drop_p) : 0u;
   a.drop_scale = p->drop_p > 0.f ? 1.0f / (1.0f - p->drop_p) : 1.0f;
   a.seed = p->drop_seed; a.off = p->drop_offset;
+  a.q_tile0 = p->q_begin > 0 ? p->q_begin / 128 : 0;
   return SAMK_OK;
 }
 
@@ -517,7 +519,7 @@ static int launch_fwd(const samk_attn_params* p, const TcArgs& a, cudaStream_t s
   if ((rc = make_tmap_bf16_2d(&tkv, p->qkv, rows, hd3, hd3, 64, KVT))) return rc;
   constexpr int smem = 16384 + 2 * KVT * 128 + (KVT / 64) * 16384 + 64;
   if ((rc = set_smem(attn_fwd_tc_kernel<KVT>, smem))) return rc;
-  dim3 grid((a.L + 127) / 128, a.H, a.B);
+  dim3 grid((a.L + 127) / 128 - a.q_tile0, a.H, a.B);
   attn_fwd_tc_kernel<KVT><<<grid, 128, smem, stream>>>(tq, tkv, a);
   return check_launch("samk_attn_fwd(tc)");
 }

@@ -472,13 +472,14 @@ def build_attn_mask(valid, rel, dims, spatial, quad_mask):
     return allow
 
 
-def attention_fwd(qkv, valid, rel, dims, spatial, quad_mask, p, drop, allow=None):
+def attention_fwd(qkv, valid, rel, dims, spatial, quad_mask, p, drop, allow=None, q_begin=0):
     B, L, H, T, A, D = dims
     if uses_tensor_core_attention(qkv.dtype) and allow is None:
         allow = build_attn_mask(valid, rel, dims, spatial, quad_mask)
     ctx_t = torch.empty(B * L, H * 64, dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty(B, H, L, dtype=torch.float32, device=qkv.device)
     ap = _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, allow=allow)
+    ap.q_begin = int(q_begin)
     check(lib().samk_attn_fwd(ctypes.byref(ap), _ATTN_IMPL, stream_ptr()), "attn_fwd")
     _count()
     return ctx_t, lse
@@ -604,6 +605,51 @@ class BertLayerFn(torch.autograd.Function):
             colsum_into(sl, Gb)
             gemm(operand(sl, "a", True), True, x_mn, True, d, d, M, Gw, accumulate=True)
         return (dx.view(B, L, d), None, None, None) + tuple(_ret(x) for x in G)
+
+
+def bert_layer_infer(x2, valid, rel, dims, spatial, quad_mask, eps, P, allow, cache=None):
+    """Inference-only (no autograd, no dropout) forward of one post-LN block, same kernels as BertLayerFn.
+
+    cache is None : x2 = all rows [B*L, d]; returns (out [B*L, d], {"qkv": fused q|k|v of every row}).
+    cache given   : x2 = the D decoder rows of every sample [B*D, d]; only those rows are recomputed: their
+                    q|k|v replace the decoder rows of cache["qkv"] (encoder rows never depend on the decoder,
+                    sa_m4c.py:793-795), attention runs for the query tiles that hold decoder rows, and the
+                    dense layers see B*D rows instead of B*L.  Returns (out [B*D, d], cache)."""
+    B, L, H, T, A, D = dims
+    qw, qb, kw, kb, vw, vb, ow, ob, g1, b1, iw, ib, o2w, o2b, g2, b2 = P
+    dev, adt = x2.device, act_dtype()
+    d, F = x2.shape[1], iw.shape[0]
+    rows = x2.shape[0]
+    wqkv = weight_operand([qw, kw, vw], False)
+    bqkv = torch.cat([qb, kb, vb]).detach()
+    qkv_rows = torch.empty(rows, 3 * d, dtype=adt, device=dev)
+    gemm(operand(x2, "a", False), False, wqkv, False, rows, 3 * d, d, qkv_rows, bias=bqkv)
+    if cache is None:
+        qkv = qkv_rows
+        ctx_t, _ = attention_fwd(qkv, valid, rel, dims, spatial, quad_mask, 0.0, (0, 0), allow)
+        ctx_rows = ctx_t
+        cache = {"qkv": qkv}
+    else:
+        qkv = cache["qkv"]
+        qkv.view(B, L, 3 * d)[:, L - D:, :] = qkv_rows.view(B, D, 3 * d)
+        ctx_t, _ = attention_fwd(qkv, valid, rel, dims, spatial, quad_mask, 0.0, (0, 0), allow, q_begin=L - D)
+        ctx_rows = ctx_t.view(B, L, d)[:, L - D:, :].reshape(rows, d)
+    y1 = torch.empty(rows, d, dtype=torch.float32, device=dev)
+    gemm(operand(ctx_rows, "a", False), False, weight_operand([ow], False), False, rows, d, d, y1, bias=ob, residual=x2)
+    a = torch.empty(rows, d, dtype=torch.float32, device=dev)
+    a_act = torch.empty(rows, d, dtype=adt, device=dev) if adt != torch.float32 else None
+    check(lib().samk_layernorm_fwd(ptr(y1), ptr(g1), ptr(b1), eps, ptr(a), ptr(a_act), DT_BF16, rows, d,
+                                   stream_ptr()), "ln1")
+    _count()
+    g = torch.empty(rows, F, dtype=adt, device=dev)
+    gemm(operand(a_act if a_act is not None else a, "a", False), False, weight_operand([iw], False), False, rows, F, d,
+         g, bias=ib, act=1)
+    y2 = torch.empty(rows, d, dtype=torch.float32, device=dev)
+    gemm(operand(g, "a", False), False, weight_operand([o2w], False), False, rows, d, F, y2, bias=o2b, residual=a)
+    out = torch.empty(rows, d, dtype=torch.float32, device=dev)
+    check(lib().samk_layernorm_fwd(ptr(y2), ptr(g2), ptr(b2), eps, ptr(out), None, 0, rows, d, stream_ptr()), "ln2")
+    _count()
+    return out, cache
 
 
 # ---- output heads + loss -------------------------------------------------------------------------------------

@@ -162,3 +162,31 @@ def test_direct_accumulation_into_flat_grad_buffer_matches_autograd_grads(golden
         ops.set_precision("bf16")
         for p in model.parameters():
             p.grad = None
+
+
+def test_cached_greedy_decoder_equals_reference_style_loop(monkeypatch):
+    """Encode-once / decoder-rows-only decoding vs the D full passes the reference performs, on the shipped
+    (n,n,s,s,s,s) schedule: identical tokens, logits equal to rounding (same kernels per row)."""
+    from sam_textvqa_b200 import ops, spatial_utils
+    mmt, tb = c3_config()
+    state = synth.seeded_state(sam4c_state_shapes(mmt, tb, V), 2)
+    model = _model(mmt, tb, state).eval()
+    graph_fn = lambda boxes: spatial_utils.build_graph_batch(boxes, 0.5)[0]
+    batch = synth.make_batch(3, V=V, seed=9, contexts=(1, 3), graph_fn=graph_fn)
+    for prec, tol in (("bf16x3", 1e-5), ("bf16", 1e-5)):
+        ops.set_precision(prec)
+        ops.clear_weight_cache()
+        outs = {}
+        try:
+            for mode in ("reference", "cached"):
+                monkeypatch.setenv("SAMK_GREEDY", mode)
+                bd = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+                with torch.no_grad():
+                    scores = model(bd)["textvqa_scores"]
+                outs[mode] = (scores.cpu(), bd["train_prev_inds"].cpu(), bd["mmt_seq_output"].cpu())
+        finally:
+            ops.set_precision("bf16")
+        live = outs["reference"][0] > -5000
+        assert torch.equal(outs["cached"][1], outs["reference"][1])
+        assert rel_err(outs["cached"][0], outs["reference"][0], live) < tol
+        assert rel_err(outs["cached"][2], outs["reference"][2]) < tol
