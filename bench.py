@@ -229,8 +229,8 @@ def run_samk(args):
     launches = ops.launch_count - l0
 
     # ---- end to end: every step's inputs come from pinned host memory; the copy of step i+1 runs on a
-    # side stream while step i computes (double-buffered device staging), and each step ends with a
-    # device->host read of its loss.  All K uploads and K loss reads are inside the timed region.
+    # side stream while step i computes (double-buffered device staging), and every step's loss is read
+    # back to the host.  All K uploads and K loss reads are inside the timed region.
     copy_stream = torch.cuda.Stream()
     staged = [None, None]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
@@ -240,14 +240,29 @@ def run_samk(args):
             staged[slot] = upload()
             ready[slot].record(copy_stream)
 
+    diag = os.environ.get("SAMK_E2E_DIAG", "")
+
     def e2e_run(steps):
+        if diag == "noupload":
+            for i in range(steps):
+                step(resident, resident_adj).item()
+            return
         stage(0)
+        pending = None
         for i in range(steps):
             torch.cuda.current_stream().wait_event(ready[i % 2])
             if i + 1 < steps:
                 stage((i + 1) % 2)
             up, a = staged[i % 2]
-            step(up, a).item()
+            loss = step(up, a)
+            # device->host read of every step's loss; the read of step i is issued after step i+1 has been
+            # enqueued so the host never drains the GPU queue (one step of latency, as a training loop's
+            # logging would do)
+            if pending is not None and diag != "noitem":
+                pending.item()
+            pending = loss
+        if pending is not None and diag != "noitem":
+            pending.item()
 
     e2e_run(2)
     barrier()
