@@ -46,14 +46,24 @@ __device__ __forceinline__ uint4 dropout_bits4(uint64_t seed, uint64_t offset, u
   return philox4x32_10(seed, e4, (uint32_t)offset);
 }
 
-__device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+// erf-GELU (sa_m4c.py:985-991) and its derivative from ONE exponential: erf by Abramowitz-Stegun 7.1.26
+// (|error| <= 1.5e-7, below fp32 rounding of the surrounding arithmetic), whose exp(-z^2) with
+// z = x/sqrt(2) is exactly the Gaussian of the pdf term.
+__device__ __forceinline__ void gelu_pair(float x, float& g, float& dg) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  const float e = __expf(-0.5f * x * x);
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);
+  const float cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  g = x * cdf;
+  dg = fmaf(x * 0.39894228040143267794f, e, cdf);
 }
-__device__ __forceinline__ float dgelu_erf(float x) {
-  float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
-}
+__device__ __forceinline__ float gelu_erf(float x) { float g, d; gelu_pair(x, g, d); return g; }
+__device__ __forceinline__ float dgelu_erf(float x) { float g, d; gelu_pair(x, g, d); return d; }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

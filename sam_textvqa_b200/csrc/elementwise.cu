@@ -151,22 +151,28 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 // dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)); dgamma += dy*xhat; dbeta += dy.
 // Optional second output dxd = dropout_mask(dx) in the activation dtype (the gradient of the dense
 // output that sits under dropout in BertSelfOutput / BertOutput) and dbias += colsum(dxd).
-// The three column sums are accumulated per block in shared memory (conflict-free shared atomics:
-// a warp adds 32 x 4 consecutive columns per instruction), so the row loop keeps few registers and
-// many warps stay resident; block partials go to `partials` (or global atomics when it is NULL).
-__global__ void __launch_bounds__(kRowThreads)
+// The three column sums are accumulated in a per-WARP shared-memory slice with plain vector loads /
+// stores (each lane owns its columns, so there are no conflicts and no atomics); the row loop keeps few
+// registers, several blocks stay resident per SM and the kernel makes a single pass over memory.  Block
+// partials go to `partials` (or global atomics when it is NULL).
+constexpr int kLnBwdWarps = 4;
+
+__global__ void __launch_bounds__(kLnBwdWarps * 32)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                      float eps, float* __restrict__ dx, void* __restrict__ dxd, int dxd_bf16, uint32_t thresh,
                      float scale, unsigned long long seed, unsigned long long off, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, float* __restrict__ dbias, float* __restrict__ partials, int rows,
                      int cols) {
-  extern __shared__ float acc_s[];   // [3][cols]
+  extern __shared__ float4 acc4[];   // [warps][3][cols/4]
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warp = blockIdx.x * (kRowThreads / 32) + wib;
-  const int nwarps = gridDim.x * (kRowThreads / 32);
-  for (int c = threadIdx.x; c < 3 * cols; c += kRowThreads) acc_s[c] = 0.f;
-  __syncthreads();
-  float* sg = acc_s; float* sb = acc_s + cols; float* sd = acc_s + 2 * cols;
+  const int warp = blockIdx.x * kLnBwdWarps + wib;
+  const int nwarps = gridDim.x * kLnBwdWarps;
+  const int c4n = cols >> 2;
+  float4* sg = acc4 + (size_t)wib * 3 * c4n;
+  float4* sb = sg + c4n;
+  float4* sd = sb + c4n;
+  for (int c = lane; c < 3 * c4n; c += 32) sg[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
   const bool want_d = dxd != nullptr || dbias != nullptr;
   const uint64_t row_groups = (uint64_t)((cols + 3) >> 2);
   for (int r = warp; r < rows; r += nwarps) {
@@ -196,15 +202,18 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) if (i < nvec) {
-      int c = 4 * (lane + 32 * i);
-      float4 gm = *reinterpret_cast<const float4*>(gamma + c);
+      const int c4 = lane + 32 * i;
+      float4 gm = *reinterpret_cast<const float4*>(gamma + 4 * c4);
       v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;   // xhat
       if (dgamma) {
-        atomicAdd(sg + c, d[i].x * v[i].x); atomicAdd(sg + c + 1, d[i].y * v[i].y);
-        atomicAdd(sg + c + 2, d[i].z * v[i].z); atomicAdd(sg + c + 3, d[i].w * v[i].w);
+        float4 t = sg[c4];
+        t.x += d[i].x * v[i].x; t.y += d[i].y * v[i].y; t.z += d[i].z * v[i].z; t.w += d[i].w * v[i].w;
+        sg[c4] = t;
       }
       if (dbeta) {
-        atomicAdd(sb + c, d[i].x); atomicAdd(sb + c + 1, d[i].y); atomicAdd(sb + c + 2, d[i].z); atomicAdd(sb + c + 3, d[i].w);
+        float4 t = sb[c4];
+        t.x += d[i].x; t.y += d[i].y; t.z += d[i].z; t.w += d[i].w;
+        sb[c4] = t;
       }
       d[i] = make_float4(gm.x * d[i].x, gm.y * d[i].y, gm.z * d[i].z, gm.w * d[i].w);
       s1 += d[i].x + d[i].y + d[i].z + d[i].w;
@@ -214,7 +223,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     s2 = warp_sum(s2) / cols;
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) if (i < nvec) {
-      int c = 4 * (lane + 32 * i);
+      const int c4 = lane + 32 * i, c = 4 * c4;
       float4 o;
       o.x = rstd * (d[i].x - s1 - v[i].x * s2);
       o.y = rstd * (d[i].y - s1 - v[i].y * s2);
@@ -222,20 +231,25 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
       o.w = rstd * (d[i].w - s1 - v[i].w * s2);
       if (dx) *reinterpret_cast<float4*>(dx + (size_t)r * cols + c) = o;
       if (want_d) {
-        float4 od = drop4(o, thresh, scale, seed, off, (uint64_t)r * row_groups + (uint64_t)(c >> 2));
+        float4 od = drop4(o, thresh, scale, seed, off, (uint64_t)r * row_groups + (uint64_t)c4);
         if (dxd) store_act(dxd, dxd_bf16, (size_t)r * cols + c, od);
-        if (dbias) { atomicAdd(sd + c, od.x); atomicAdd(sd + c + 1, od.y); atomicAdd(sd + c + 2, od.z); atomicAdd(sd + c + 3, od.w); }
+        if (dbias) { float4 t = sd[c4]; t.x += od.x; t.y += od.y; t.z += od.z; t.w += od.w; sd[c4] = t; }
       }
     }
   }
   __syncthreads();
+  // reduce the per-warp slices and publish the block partials
   float* outs[3] = {dgamma, dbeta, dbias};
+  const float* accf = reinterpret_cast<const float*>(acc4);
 #pragma unroll 1
   for (int k = 0; k < 3; ++k) {
     if (!outs[k]) continue;
-    for (int c = threadIdx.x; c < cols; c += kRowThreads) {
-      if (partials) partials[((size_t)blockIdx.x * 3 + k) * cols + c] = acc_s[k * cols + c];
-      else atomicAdd(outs[k] + c, acc_s[k * cols + c]);
+    for (int c = threadIdx.x; c < cols; c += kLnBwdWarps * 32) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kLnBwdWarps; ++w) t += accf[((size_t)w * 3 + k) * cols + c];
+      if (partials) partials[((size_t)blockIdx.x * 3 + k) * cols + c] = t;
+      else atomicAdd(outs[k] + c, t);
     }
   }
 }
@@ -287,7 +301,17 @@ __global__ void colsum_kernel(const void* __restrict__ x, int x_bf16, long long 
   const int rl = threadIdx.x >> 6;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (cq * 4 < cols) {
-    for (int r = blockIdx.y * 4 + rl; r < rows; r += gridDim.y * 4) {
+    const int stride = gridDim.y * 4;
+    int r = blockIdx.y * 4 + rl;
+    for (; r + 3 * stride < rows; r += 4 * stride) {   // 4 independent loads in flight per thread
+      float4 v0 = load_act(x, x_bf16, (size_t)r * ld + cq * 4);
+      float4 v1 = load_act(x, x_bf16, (size_t)(r + stride) * ld + cq * 4);
+      float4 v2 = load_act(x, x_bf16, (size_t)(r + 2 * stride) * ld + cq * 4);
+      float4 v3 = load_act(x, x_bf16, (size_t)(r + 3 * stride) * ld + cq * 4);
+      acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+      acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; r < rows; r += stride) {
       float4 v = load_act(x, x_bf16, (size_t)r * ld + cq * 4);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
@@ -704,9 +728,10 @@ int samk_layernorm_bwd(const float* dy, const float* x, const float* gamma, floa
   SAMK_REQUIRE(dy && x && gamma && rows >= 0, "bad argument");
   SAMK_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 1024, "cols must be a multiple of 4, <= 1024");
   if (!rows) return SAMK_OK;
-  int grid = grid_for(rows, 8 * 4);
+  int grid = grid_for(rows, kLnBwdWarps * 4);
   if (grid > 592) grid = 592;   // partials workspace is sized for 592 blocks (samk_layernorm_bwd_partials)
-  layernorm_bwd_kernel<<<grid, kRowThreads, 3 * cols * sizeof(float), (cudaStream_t)stream>>>(
+  const int smem = kLnBwdWarps * 3 * cols * (int)sizeof(float);
+  layernorm_bwd_kernel<<<grid, kLnBwdWarps * 32, smem, (cudaStream_t)stream>>>(
       dy, x, gamma, eps, dx, dxd, dxd_dtype == SAMK_DT_BF16, drop_p > 0.f ? drop_threshold(drop_p) : 0u,
       drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f, seed, offset, dgamma, dbeta, dbias, partials, rows, cols);
   int rc = check_launch(__func__);

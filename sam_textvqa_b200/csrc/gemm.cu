@@ -56,11 +56,7 @@ __device__ __forceinline__ void epilogue_row_chunk(const EpiArgs& ep, float* v, 
     // out = gelu(v), pre = gelu'(v): one erf and one exp serve both (backward then only multiplies)
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      const float x = v[i];
-      const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-      const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-      pre_v[i] = cdf + x * pdf;
-      v[i] = x * cdf;
+      gelu_pair(v[i], v[i], pre_v[i]);
     }
   }
   if (ep.pre) {
