@@ -44,10 +44,8 @@ __device__ __forceinline__ void st_elem(void* p, int bf16, size_t i, float v) {
 // keep-multiplier of attention-probability element (b,h,i,j): 0 or 1/(1-p)
 __device__ __forceinline__ float attn_keep(const AttnArgs& a, int b, int h, int i, int j) {
   if (!a.drop_thresh) return 1.0f;
-  const uint64_t row = ((uint64_t)(b * a.H + h) * a.m.L + i) * (uint64_t)((a.m.L + 3) >> 2);
-  uint4 r = dropout_bits4(a.seed, a.off, row + (uint64_t)(j >> 2));
-  uint32_t w = (j & 3) == 0 ? r.x : ((j & 3) == 1 ? r.y : ((j & 3) == 2 ? r.z : r.w));
-  return w >= a.drop_thresh ? a.drop_scale : 0.0f;
+  const uint64_t row = ((uint64_t)(b * a.H + h) * a.m.L + i) * (uint64_t)((a.m.L + 7) >> 3);   // groups of 8 keys
+  return dropout_keep1(a.seed, a.off, row * 8 + (uint64_t)j, a.drop_thresh) ? a.drop_scale : 0.0f;
 }
 
 // load rows [r0, r0+nrows) x 64 of one head slice into smem[nrows][65] (zero rows past L)
@@ -361,7 +359,7 @@ static int fill_args(AttnArgs& a, const samk_attn_params* p) {
   a.in_bf16 = p->dtype == SAMK_DT_BF16; a.out_bf16 = a.in_bf16;
   a.B = p->B; a.H = p->H; a.scale = p->scale;
   a.drop_thresh = p->drop_p > 0.f ? drop_threshold(p->drop_p) : 0u;
-  a.drop_scale = p->drop_p > 0.f ? 1.0f / (1.0f - p->drop_p) : 1.0f;
+  a.drop_scale = drop_keep_scale(p->drop_p);
   a.seed = p->drop_seed; a.off = p->drop_offset;
   a.m.valid = p->key_valid; a.m.rel = p->spatial ? p->rel_bits : nullptr;
   a.m.T = p->T; a.m.A = p->A; a.m.D = p->D; a.m.L = p->T + p->A + p->D;

@@ -92,16 +92,10 @@ __device__ __forceinline__ uint32_t allow_word(const TcArgs& a, int b, int h, in
 // dropout keep flags for 32 consecutive keys j0..j0+31 of probability row (b,h,i): bit k = keep
 __device__ __forceinline__ uint32_t keep_word(const TcArgs& a, int b, int h, int i, int j0) {
   if (!a.drop_thresh) return 0xffffffffu;
-  const uint64_t row = ((uint64_t)(b * a.H + h) * a.L + i) * (uint64_t)((a.L + 3) >> 2);
+  const uint64_t row = ((uint64_t)(b * a.H + h) * a.L + i) * (uint64_t)((a.L + 7) >> 3);   // groups of 8 keys
   uint32_t kw = 0;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    uint4 r = dropout_bits4(a.seed, a.off, row + (uint64_t)((j0 >> 2) + q));
-    kw |= (r.x >= a.drop_thresh ? 1u : 0u) << (4 * q);
-    kw |= (r.y >= a.drop_thresh ? 1u : 0u) << (4 * q + 1);
-    kw |= (r.z >= a.drop_thresh ? 1u : 0u) << (4 * q + 2);
-    kw |= (r.w >= a.drop_thresh ? 1u : 0u) << (4 * q + 3);
-  }
+  for (int q = 0; q < 4; ++q) kw |= dropout_keep8(a.seed, a.off, row + (uint64_t)((j0 >> 3) + q), a.drop_thresh) << (8 * q);
   return kw;
 }
 
@@ -494,7 +488,7 @@ static int fill_tc(TcArgs& a, const samk_attn_params* p) {
   a.B = p->B; a.H = p->H; a.L = p->T + p->A + p->D; a.W = (a.L + 31) / 32;
   a.scale = p->scale; a.scale_log2 = p->scale * kLog2e;
   a.drop_thresh = p->drop_p > 0.f ? drop_threshold(p->drop_p) : 0u;
-  a.drop_scale = p->drop_p > 0.f ? 1.0f / (1.0f - p->drop_p) : 1.0f;
+  a.drop_scale = drop_keep_scale(p->drop_p);
   a.seed = p->drop_seed; a.off = p->drop_offset;
   a.q_tile0 = p->q_begin > 0 ? p->q_begin / 128 : 0;
   return SAMK_OK;

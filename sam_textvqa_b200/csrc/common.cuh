@@ -16,14 +16,18 @@ void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 
 // ---------------------------------------------------------------------------------------------
-// Philox4x32-10 counter RNG: the dropout keep-mask of element e is a pure function of
-// (seed, offset, e), so forward and backward kernels regenerate identical masks.
+// Philox4x32-7 counter RNG (7 rounds: the fewest that pass BigCrush, Salmon et al. SC'11): the
+// dropout keep-mask of element e is a pure function of (seed, offset, e), so forward and backward
+// kernels regenerate identical masks.  One call yields 128 bits = 16 bits for each of 8 consecutive
+// elements (group g = e >> 3); element kept iff its 16 bits >= thresh16 = round(p * 65536), i.e. the
+// drop probability is p quantised to 2^-16 and the keep-scale is computed from the quantised value.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint64_t ctr_lo, uint32_t ctr_hi) {
+constexpr int kPhiloxRounds = 7;
+__device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr_lo, uint32_t ctr_hi) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = ctr_hi, c3 = 0x5a17c0deu;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < kPhiloxRounds; ++r) {
     uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
@@ -33,17 +37,62 @@ __device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint64_t ctr_lo, u
   return make_uint4(c0, c1, c2, c3);
 }
 
-// keep-threshold: element kept iff its 32 random bits >= thresh (thresh = p * 2^32)
+// thresh16 = round(p * 2^16) in [0, 65535]; 0 = no dropout
 __host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
-  double t = (double)p * 4294967296.0;
+  double t = (double)p * 65536.0 + 0.5;
   if (t < 0) t = 0;
-  if (t > 4294967295.0) t = 4294967295.0;
+  if (t > 65535.0) t = 65535.0;
   return (uint32_t)t;
 }
+// 1 / P(keep) for the quantised probability
+__host__ __device__ __forceinline__ float drop_keep_scale(float p) {
+  const uint32_t t = drop_threshold(p);
+  return t ? (float)(65536.0 / (65536.0 - (double)t)) : 1.0f;
+}
 
-// Random words for 4 consecutive elements starting at element index e4*4 of stream `offset`.
-__device__ __forceinline__ uint4 dropout_bits4(uint64_t seed, uint64_t offset, uint64_t e4) {
-  return philox4x32_10(seed, e4, (uint32_t)offset);
+// keep bits of the 8 elements of group g (bit k = element 8g+k kept)
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t offset, uint64_t g, uint32_t thresh16) {
+  const uint4 r = philox4x32(seed, g, (uint32_t)offset);
+  const uint32_t th = thresh16 << 16;     // hi16(x) >= t  <=>  x >= t << 16
+  uint32_t m = 0;
+  m |= ((r.x << 16) >= th ? 1u : 0u);
+  m |= (r.x >= th ? 2u : 0u);
+  m |= ((r.y << 16) >= th ? 4u : 0u);
+  m |= (r.y >= th ? 8u : 0u);
+  m |= ((r.z << 16) >= th ? 16u : 0u);
+  m |= (r.z >= th ? 32u : 0u);
+  m |= ((r.w << 16) >= th ? 64u : 0u);
+  m |= (r.w >= th ? 128u : 0u);
+  return m;
+}
+// v[k] = kept ? v[k] * scale : 0 for the 8 elements of group g
+__device__ __forceinline__ void dropout_apply8(float* v, uint64_t seed, uint64_t offset, uint64_t g, uint32_t thresh16,
+                                               float scale) {
+  const uint4 r = philox4x32(seed, g, (uint32_t)offset);
+  const uint32_t th = thresh16 << 16;
+  v[0] = (r.x << 16) >= th ? v[0] * scale : 0.f;
+  v[1] = r.x >= th ? v[1] * scale : 0.f;
+  v[2] = (r.y << 16) >= th ? v[2] * scale : 0.f;
+  v[3] = r.y >= th ? v[3] * scale : 0.f;
+  v[4] = (r.z << 16) >= th ? v[4] * scale : 0.f;
+  v[5] = r.z >= th ? v[5] * scale : 0.f;
+  v[6] = (r.w << 16) >= th ? v[6] * scale : 0.f;
+  v[7] = r.w >= th ? v[7] * scale : 0.f;
+}
+// the 4 elements 4*e4 .. 4*e4+3 (half of group e4 >> 1)
+__device__ __forceinline__ void dropout_apply4(float* v, uint64_t seed, uint64_t offset, uint64_t e4, uint32_t thresh16,
+                                               float scale) {
+  const uint4 r = philox4x32(seed, e4 >> 1, (uint32_t)offset);
+  const uint32_t a = (e4 & 1) ? r.z : r.x, b = (e4 & 1) ? r.w : r.y;
+  const uint32_t th = thresh16 << 16;
+  v[0] = (a << 16) >= th ? v[0] * scale : 0.f;
+  v[1] = a >= th ? v[1] * scale : 0.f;
+  v[2] = (b << 16) >= th ? v[2] * scale : 0.f;
+  v[3] = b >= th ? v[3] * scale : 0.f;
+}
+// single element e
+__device__ __forceinline__ bool dropout_keep1(uint64_t seed, uint64_t offset, uint64_t e, uint32_t thresh16) {
+  return (dropout_keep8(seed, offset, e >> 3, thresh16) >> (uint32_t)(e & 7)) & 1u;
 }
 
 // erf-GELU (sa_m4c.py:985-991) and its derivative from ONE exponential: erf by Abramowitz-Stegun 7.1.26

@@ -31,12 +31,9 @@ __device__ __forceinline__ float4 load_act(const void* base, int bf16, size_t id
 __device__ __forceinline__ float4 drop4(float4 v, uint32_t thresh, float scale, uint64_t seed, uint64_t off,
                                         uint64_t ctr) {
   if (!thresh) return v;
-  uint4 r = dropout_bits4(seed, off, ctr);
-  v.x = r.x >= thresh ? v.x * scale : 0.f;
-  v.y = r.y >= thresh ? v.y * scale : 0.f;
-  v.z = r.z >= thresh ? v.z * scale : 0.f;
-  v.w = r.w >= thresh ? v.w * scale : 0.f;
-  return v;
+  float t[4] = {v.x, v.y, v.z, v.w};
+  dropout_apply4(t, seed, off, ctr, thresh, scale);   // ctr = index of this group of 4 elements
+  return make_float4(t[0], t[1], t[2], t[3]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -733,7 +730,7 @@ int samk_layernorm_bwd(const float* dy, const float* x, const float* gamma, floa
   const int smem = kLnBwdWarps * 3 * cols * (int)sizeof(float);
   layernorm_bwd_kernel<<<grid, kLnBwdWarps * 32, smem, (cudaStream_t)stream>>>(
       dy, x, gamma, eps, dx, dxd, dxd_dtype == SAMK_DT_BF16, drop_p > 0.f ? drop_threshold(drop_p) : 0u,
-      drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f, seed, offset, dgamma, dbeta, dbias, partials, rows, cols);
+      drop_keep_scale(drop_p), seed, offset, dgamma, dbeta, dbias, partials, rows, cols);
   int rc = check_launch(__func__);
   if (rc || !partials) return rc;
   ln_bwd_finalize_kernel<<<dim3((cols + 31) / 32, 3), 256, 0, (cudaStream_t)stream>>>(partials, grid, cols, dgamma, dbeta, dbias);
@@ -748,7 +745,7 @@ int samk_dropout_add(const float* a, const float* b, float* out, void* out2, int
   if (!rows || !cols) return SAMK_OK;
   dropout_add_kernel<<<grid_for((long long)rows * cols / 4, 256), 256, 0, (cudaStream_t)stream>>>(
       a, b, out, out2, out2_dtype == SAMK_DT_BF16, rows, cols, drop_p > 0.f ? drop_threshold(drop_p) : 0u,
-      drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f, seed, offset);
+      drop_keep_scale(drop_p), seed, offset);
   return check_launch(__func__);
 }
 
@@ -778,7 +775,7 @@ int samk_bert_embed_fwd(const long long* ids, const float* word, const float* po
   if (!rows) return SAMK_OK;
   bert_embed_fwd_kernel<<<grid_for(rows, 8), kRowThreads, 0, (cudaStream_t)stream>>>(
       ids, word, pos, type, gamma, beta, eps, out, out2, out2_dtype == SAMK_DT_BF16, rows, T, cols,
-      drop_p > 0.f ? drop_threshold(drop_p) : 0u, drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f, seed, offset);
+      drop_p > 0.f ? drop_threshold(drop_p) : 0u, drop_keep_scale(drop_p), seed, offset);
   return check_launch(__func__);
 }
 
@@ -791,7 +788,7 @@ int samk_bert_embed_bwd(const float* dout, const long long* ids, const float* wo
   if (!rows) return SAMK_OK;
   bert_embed_bwd_kernel<<<grid_for(rows, 8), kRowThreads, 0, (cudaStream_t)stream>>>(
       dout, ids, word, pos, type, gamma, eps, dword, dpos, dtype, dgamma, dbeta, rows, T, cols,
-      drop_p > 0.f ? drop_threshold(drop_p) : 0u, drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f, seed, offset);
+      drop_p > 0.f ? drop_threshold(drop_p) : 0u, drop_keep_scale(drop_p), seed, offset);
   return check_launch(__func__);
 }
 
@@ -802,7 +799,7 @@ static int fill_prevpred(PrevPredParams& p, const long long* prev, const float* 
   p.ans_g = ln[0]; p.ans_b = ln[1]; p.ocr_g = ln[2]; p.ocr_b = ln[3]; p.emb_g = ln[4]; p.emb_b = ln[5];
   p.eps = eps; p.B = B; p.D = D; p.V = V; p.R = R; p.cols = cols;
   p.thresh = drop_p > 0.f ? drop_threshold(drop_p) : 0u;
-  p.scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  p.scale = drop_keep_scale(drop_p);
   p.seed = seed; p.off = offset;
   return 0;
 }

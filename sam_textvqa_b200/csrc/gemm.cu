@@ -24,162 +24,308 @@ constexpr int BK = 64;
 constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter, each takes half the columns
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 
+// Epilogue feature bits.  A kernel instantiation carries either a compile-time mask (EPI >= 0: the hot
+// combinations of the SA-M4C layers, dead branches removed -- a fully dynamic epilogue is ~100 KB of
+// SASS and stalls on instruction fetch) or EPI_DYNAMIC (runtime mask, any combination / odd sizes).
+enum : int {
+  F_OUT_BF16 = 1 << 0,    // out is bf16 (else fp32)
+  F_BIAS = 1 << 1,
+  F_DROP = 1 << 2,
+  F_RES = 1 << 3,         // += residual (fp32)
+  F_GELU_PAIR = 1 << 4,   // act 3: out = gelu(v), pre = gelu'(v)
+  F_PRE = 1 << 5,         // pre-activation copy (act != 3)
+  F_PRE_BF16 = 1 << 6,
+  F_MULAUX = 1 << 7,      // act 4: v *= aux
+  F_DGELU = 1 << 8,       // act 2: v *= gelu'(aux)
+  F_AUX_BF16 = 1 << 9,
+  F_GELU = 1 << 10,       // act 1
+  F_ATOMIC = 1 << 11,     // red.global.add into fp32 out
+  F_ALPHA = 1 << 12,      // alpha != 1
+  F_VEC = 1 << 13,        // all pointers / pitches vector friendly and N % 8 == 0: no scalar tails
+};
+constexpr int EPI_DYNAMIC = -1;
+
 struct EpiArgs {
-  void* out; long long ldo; int out_bf16; int atomic_add; float alpha;
+  void* out; long long ldo; float alpha;
   const float* bias;
-  void* pre; long long ldpre; int pre_bf16;
-  int act; const void* aux; long long ldaux; int aux_bf16;
+  void* pre; long long ldpre;
+  const void* aux; long long ldaux;
   uint32_t drop_thresh; float drop_scale; unsigned long long seed, offset;
   const float* residual; long long ldres;
-  int vec_ok;  // all pitches / pointers 16B friendly and N % 4 == 0
+  int flags;
 };
 
-// Apply the epilogue to `cnt` (<=32, multiple handled generally) consecutive columns of one row.
-__device__ __forceinline__ void epilogue_row_chunk(const EpiArgs& ep, float* v, int row, int col0, int cnt, int N) {
-  const bool full = (cnt == 32) && ep.vec_ok;
-  float pre_v[32];
-  float* const v_in = v;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] *= ep.alpha;
-  if (ep.bias) {
+template <int EPI> __device__ __forceinline__ int epi_flags(const EpiArgs& ep) {
+  if constexpr (EPI >= 0) return EPI; else return ep.flags;
+}
+
+// The epilogue of 8 consecutive columns [col, col+cnt) (cnt <= 8, col % 8 == 0) of one output row, split into
+// load / compute / store phases so that a caller handling several rows can issue all global loads
+// first (memory-level parallelism), then the math, then the stores.
+struct EpiRow {
+  float v[8];      // accumulator values -> final values
+};
+struct EpiIn {       // operands fetched from global memory ahead of the accumulator (kept raw: no use before compute)
+  float res[8];    // residual
+  float aux[8];    // aux operand (act 2 / 4), fp32 form
+  uint4 auxp;      // aux operand, packed bf16 form (vector path)
+};
+
+template <int EPI>
+__device__ __forceinline__ void epi_load(const EpiArgs& ep, EpiIn& e, int row, int col, int cnt) {
+  const int F = epi_flags<EPI>(ep);
+  const bool full = (F & F_VEC) && cnt == 8;
+  if (F & F_RES) {
+    const float* p = ep.residual + (size_t)row * ep.ldres + col;
     if (full) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        float4 b = *reinterpret_cast<const float4*>(ep.bias + col0 + i);
-        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-      }
+      const float4 b0 = *reinterpret_cast<const float4*>(p), b1 = *reinterpret_cast<const float4*>(p + 4);
+      e.res[0] = b0.x; e.res[1] = b0.y; e.res[2] = b0.z; e.res[3] = b0.w;
+      e.res[4] = b1.x; e.res[5] = b1.y; e.res[6] = b1.z; e.res[7] = b1.w;
     } else {
-      _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) v[i] += ep.bias[col0 + i];
+      _Pragma("unroll") for (int i = 0; i < 8; ++i) e.res[i] = i < cnt ? p[i] : 0.f;
     }
   }
-  if (ep.act == 3) {
+  if (F & (F_MULAUX | F_DGELU)) {
+    if (F & F_AUX_BF16) {
+      const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (size_t)row * ep.ldaux + col;
+      if (full) {
+        e.auxp = *reinterpret_cast<const uint4*>(p);
+      } else {
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) e.aux[i] = i < cnt ? __bfloat162float(p[i]) : 0.f;
+      }
+    } else {
+      const float* p = reinterpret_cast<const float*>(ep.aux) + (size_t)row * ep.ldaux + col;
+      _Pragma("unroll") for (int i = 0; i < 8; ++i) e.aux[i] = i < cnt ? p[i] : 0.f;
+    }
+  }
+}
+
+// w: second output (pre-activation copy, or gelu' when act == 3)
+template <int EPI>
+__device__ __forceinline__ void epi_compute(const EpiArgs& ep, EpiRow& e, const EpiIn& in, float* w, const float* bias8,
+                                            int row, int col, int cnt, int N) {
+  const int F = epi_flags<EPI>(ep);
+  const bool full = (F & F_VEC) && cnt == 8;
+  float* v = e.v;
+  if (F & F_ALPHA) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= ep.alpha;
+  }
+  if (F & F_BIAS) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += bias8[i];
+  }
+  if (F & F_GELU_PAIR) {
     // out = gelu(v), pre = gelu'(v): one erf and one exp serve both (backward then only multiplies)
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      gelu_pair(v[i], v[i], pre_v[i]);
-    }
-  }
-  if (ep.pre) {
-    const float* v = (ep.act == 3) ? pre_v : v_in;
-    if (ep.pre_bf16) {
-      __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.pre) + (size_t)row * ep.ldpre + col0;
-      if (full) {
+    for (int i = 0; i < 8; ++i) gelu_pair(v[i], v[i], w[i]);
+  } else if (F & F_PRE) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8)
-          *reinterpret_cast<uint4*>(p + i) = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]),
-                                                        pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
-      } else {
-        _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) p[i] = __float2bfloat16_rn(v[i]);
+    for (int i = 0; i < 8; ++i) w[i] = v[i];
+  }
+  if (F & F_GELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+  } else if (F & (F_MULAUX | F_DGELU)) {
+    float x[8];
+    if ((F & F_AUX_BF16) && full) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&in.auxp);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h[j]);
+        x[2 * j] = f.x; x[2 * j + 1] = f.y;
       }
     } else {
-      float* p = reinterpret_cast<float*>(ep.pre) + (size_t)row * ep.ldpre + col0;
-      if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-      } else {
-        _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) p[i] = v[i];
-      }
+      for (int i = 0; i < 8; ++i) x[i] = in.aux[i];
+    }
+    if (F & F_MULAUX) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] *= x[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] *= dgelu_erf(x[i]);
     }
   }
-  if (ep.act == 1) {
+  if (F & F_DROP) {
+    // element (row, c) belongs to the 4-group e4 = row * ceil(N/4) + c/4 of this dropout stream (the same
+    // index the LayerNorm-backward kernel regenerates the mask from); 8-groups are pairs of 4-groups
+    const uint64_t e4 = (uint64_t)row * (uint64_t)((N + 3) >> 2) + (uint64_t)(col >> 2);
+    if (full && ((F & F_VEC) || !(e4 & 1))) {        // F_VEC: N % 8 == 0, so e4 is even
+      dropout_apply8(v, ep.seed, ep.offset, e4 >> 1, ep.drop_thresh, ep.drop_scale);
+    } else {
+      dropout_apply4(v, ep.seed, ep.offset, e4, ep.drop_thresh, ep.drop_scale);
+      if (cnt > 4) dropout_apply4(v + 4, ep.seed, ep.offset, e4 + 1, ep.drop_thresh, ep.drop_scale);
+    }
+  }
+  if (F & F_RES) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-  } else if (ep.act == 4) {
-    if (ep.aux_bf16) {
-      const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (size_t)row * ep.ldaux + col0;
+    for (int i = 0; i < 8; ++i) v[i] += in.res[i];
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_store(const EpiArgs& ep, const EpiRow& e, const float* w, int row, int col, int cnt) {
+  const int F = epi_flags<EPI>(ep);
+  const bool full = (F & F_VEC) && cnt == 8;
+  const float* v = e.v;
+  if (F & (F_PRE | F_GELU_PAIR)) {
+    if (F & F_PRE_BF16) {
+      __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.pre) + (size_t)row * ep.ldpre + col;
       if (full) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 u = *reinterpret_cast<const uint4*>(p + i);
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float2 f = __bfloat1622float2(h[j]);
-            v[i + 2 * j] *= f.x;
-            v[i + 2 * j + 1] *= f.y;
-          }
-        }
+        *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]),
+                                                  pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
       } else {
-        _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) v[i] *= __bfloat162float(p[i]);
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) if (i < cnt) p[i] = __float2bfloat16_rn(w[i]);
       }
     } else {
-      const float* p = reinterpret_cast<const float*>(ep.aux) + (size_t)row * ep.ldaux + col0;
-      _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) v[i] *= p[i];
-    }
-  } else if (ep.act == 2) {
-    if (ep.aux_bf16) {
-      const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (size_t)row * ep.ldaux + col0;
+      float* p = reinterpret_cast<float*>(ep.pre) + (size_t)row * ep.ldpre + col;
       if (full) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 u = *reinterpret_cast<const uint4*>(p + i);
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float2 f = __bfloat1622float2(h[j]);
-            v[i + 2 * j] *= dgelu_erf(f.x);
-            v[i + 2 * j + 1] *= dgelu_erf(f.y);
-          }
-        }
+        *reinterpret_cast<float4*>(p) = make_float4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(w[4], w[5], w[6], w[7]);
       } else {
-        _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) v[i] *= dgelu_erf(__bfloat162float(p[i]));
-      }
-    } else {
-      const float* p = reinterpret_cast<const float*>(ep.aux) + (size_t)row * ep.ldaux + col0;
-      _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) v[i] *= dgelu_erf(p[i]);
-    }
-  }
-  if (ep.drop_thresh) {
-    const uint64_t row_ctr = (uint64_t)row * (uint64_t)((N + 3) >> 2);
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      if (i < cnt) {
-        uint4 r = dropout_bits4(ep.seed, ep.offset, row_ctr + (uint64_t)((col0 + i) >> 2));
-        v[i] = r.x >= ep.drop_thresh ? v[i] * ep.drop_scale : 0.f;
-        v[i + 1] = r.y >= ep.drop_thresh ? v[i + 1] * ep.drop_scale : 0.f;
-        v[i + 2] = r.z >= ep.drop_thresh ? v[i + 2] * ep.drop_scale : 0.f;
-        v[i + 3] = r.w >= ep.drop_thresh ? v[i + 3] * ep.drop_scale : 0.f;
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) if (i < cnt) p[i] = w[i];
       }
     }
   }
-  if (ep.residual) {
-    const float* p = ep.residual + (size_t)row * ep.ldres + col0;
+  if (F & F_ATOMIC) {
+    float* p = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col;
     if (full) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        float4 b = *reinterpret_cast<const float4*>(p + i);
-        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-      }
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
     } else {
-      _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) v[i] += p[i];
+      _Pragma("unroll") for (int i = 0; i < 8; ++i) if (i < cnt) atomicAdd(p + i, v[i]);
     }
-  }
-  if (ep.atomic_add) {
-    float* p = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col0;
+  } else if (F & F_OUT_BF16) {
+    __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldo + col;
     if (full) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 4)
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p + i), "f"(v[i]), "f"(v[i + 1]), "f"(v[i + 2]), "f"(v[i + 3]) : "memory");
+      *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                                                pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     } else {
-      _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) atomicAdd(p + i, v[i]);
-    }
-  } else if (ep.out_bf16) {
-    __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldo + col0;
-    if (full) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 8)
-        *reinterpret_cast<uint4*>(p + i) = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]),
-                                                      pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
-    } else {
-      _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) p[i] = __float2bfloat16_rn(v[i]);
+      _Pragma("unroll") for (int i = 0; i < 8; ++i) if (i < cnt) p[i] = __float2bfloat16_rn(v[i]);
     }
   } else {
-    float* p = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col0;
+    float* p = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col;
     if (full) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
     } else {
-      _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < cnt) p[i] = v[i];
+      _Pragma("unroll") for (int i = 0; i < 8; ++i) if (i < cnt) p[i] = v[i];
+    }
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_load_bias(const EpiArgs& ep, float* bias8, int col, int cnt) {
+  const int F = epi_flags<EPI>(ep);
+  if (!(F & F_BIAS)) return;
+  if ((F & F_VEC) && cnt == 8) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + 4));
+    bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w;
+    bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
+  } else {
+    _Pragma("unroll") for (int i = 0; i < 8; ++i) bias8[i] = i < cnt ? ep.bias[col + i] : 0.f;
+  }
+}
+
+// whole epilogue for one row x 8 columns (SIMT cross-check kernel)
+__device__ __forceinline__ void epilogue_8(const EpiArgs& ep, const float* acc, int row, int col, int cnt, int N) {
+  EpiRow e;
+  EpiIn in;
+  float bias8[8], w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) e.v[i] = acc[i];
+  epi_load_bias<EPI_DYNAMIC>(ep, bias8, col, cnt);
+  epi_load<EPI_DYNAMIC>(ep, in, row, col, cnt);
+  epi_compute<EPI_DYNAMIC>(ep, e, in, w, bias8, row, col, cnt, N);
+  epi_store<EPI_DYNAMIC>(ep, e, w, row, col, cnt);
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// One warp's 32 rows x 32 columns of accumulator, as delivered by tcgen05.ld (thread = row, 32 consecutive
+// columns in registers).
+//   STAGED = true : transposed through a warp-private 4 KB shared-memory tile (16-byte slots XOR-swizzled by
+//     row, conflict-free both ways) so that the epilogue math and every global access run in a coalesced
+//     layout: lane = (row sub-index lane/4, 8-column group lane%4); one warp-wide access covers 8 rows x
+//     128 contiguous bytes.  Costs shared-memory bandwidth, which the MMA operand reads also need.
+//   STAGED = false: each thread finishes its own row (4 groups of 8 columns): no shared-memory traffic,
+//     but a warp-wide access touches 32 different rows.
+constexpr int kStageBytesPerWarp = 32 * 32 * 4;
+
+// (row, first column) of the `it`-th 8-column group this lane finishes within a 32x32 warp chunk
+template <bool STAGED>
+__device__ __forceinline__ void chunk_coord(int lane, int it, int row0, int col0, int& row, int& col) {
+  if constexpr (STAGED) { row = row0 + it * 8 + (lane >> 2); col = col0 + (lane & 3) * 8; }
+  else { row = row0 + lane; col = col0 + it * 8; }
+}
+
+template <bool STAGED> struct ChunkIn {
+  EpiIn in[4];
+  float bias[STAGED ? 1 : 4][8];
+};
+
+// issue the global loads (bias, residual, aux) of one chunk; they are consumed one chunk later
+template <int EPI, bool STAGED>
+__device__ __forceinline__ void chunk_prefetch(const EpiArgs& ep, ChunkIn<STAGED>& c, int row0, int col0, int M, int N, int lane) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    int row, col;
+    chunk_coord<STAGED>(lane, it, row0, col0, row, col);
+    if (col < N) {
+      if (!STAGED || it == 0) epi_load_bias<EPI>(ep, c.bias[STAGED ? 0 : it], col, min(8, N - col));
+      if (row < M) epi_load<EPI>(ep, c.in[it], row, col, min(8, N - col));
+    }
+  }
+}
+
+template <int EPI, bool STAGED>
+__device__ __forceinline__ void chunk_finish(const EpiArgs& ep, const ChunkIn<STAGED>& c, uint32_t stage, const uint32_t (&r)[32],
+                                             bool zero, int row0, int col0, int M, int N, int lane) {
+  EpiRow e[4];
+  if constexpr (STAGED) {
+    const uint32_t srow = stage + lane * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      sts128(srow + ((j ^ (lane & 7)) << 4),
+             zero ? make_float4(0.f, 0.f, 0.f, 0.f)
+                  : make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                __uint_as_float(r[4 * j + 3])));
+    __syncwarp();
+    const int cg = lane & 3, sub = lane >> 2;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int rr = it * 8 + sub;
+      const uint32_t base = stage + rr * 128;
+      const float4 x0 = lds128(base + (((2 * cg) ^ (rr & 7)) << 4)), x1 = lds128(base + (((2 * cg + 1) ^ (rr & 7)) << 4));
+      e[it].v[0] = x0.x; e[it].v[1] = x0.y; e[it].v[2] = x0.z; e[it].v[3] = x0.w;
+      e[it].v[4] = x1.x; e[it].v[5] = x1.y; e[it].v[6] = x1.z; e[it].v[7] = x1.w;
+    }
+    __syncwarp();          // staging tile may be overwritten by the next chunk from here on
+  } else {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) e[it].v[i] = zero ? 0.f : __uint_as_float(r[8 * it + i]);
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    int row, col;
+    chunk_coord<STAGED>(lane, it, row0, col0, row, col);
+    if (row < M && col < N) {
+      float w[8];
+      const int cnt = min(8, N - col);
+      epi_compute<EPI>(ep, e[it], c.in[it], w, c.bias[STAGED ? 0 : it], row, col, cnt, N);
+      epi_store<EPI>(ep, e[it], w, row, col, cnt);
     }
   }
 }
@@ -189,7 +335,8 @@ template <int BN> struct GemmCfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingOff = kStages * kStageBytes + 256;       // after the barriers
+  static constexpr int kSmemBytes = kStagingOff + kEpiWarps * kStageBytesPerWarp /*epilogue transposes*/ + 1024 /*align slack*/;
   static constexpr int kTmemCols = 2 * BN;  // 256 or 512: power of two
 };
 
@@ -197,7 +344,7 @@ template <int BN> struct GemmCfg {
 // output tiles that need the same B tile: each CTA fetches half of it and TMA-multicasts it into both
 // shared memories, cutting the L2->SM operand traffic per flop by a third (the kernel is L2-bandwidth
 // bound at 128x256 tiles otherwise).  Slots are released to both producers with a multicast commit.
-template <int BN, int A_MN, int B_MN, int CL>
+template <int BN, int A_MN, int B_MN, int CL, int EPI, bool STAGED>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const EpiArgs ep, int M, int N, int K, int split_k) {
@@ -336,22 +483,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m0 = ((tile / n_tiles) * CL + cta_rank) * BM, n0 = (tile % n_tiles) * BN;
       const int kb0 = split * kb_per;
       const bool has_k = min(kb_total, kb0 + kb_per) > kb0;
+      const int row0 = m0 + lane_grp * 32;
+      const uint32_t stage = ptx::smem_u32(smem + Cfg::kStagingOff) + (warp - 2) * kStageBytesPerWarp;
+      constexpr int kChunks = BN / 64;               // 32-column chunks per warp
+      const int cbase = col_half * kChunks;
+      const bool live = (has_k || !(epi_flags<EPI>(ep) & F_ATOMIC)) && row0 < M;
+      // operands of chunk i+1 are fetched from global memory while chunk i is finished (the first one even
+      // before the accumulator is ready)
+      // (only pays off for the aux operand of the fused dgrad; measured slower for residual-only epilogues,
+      // and the runtime-flag epilogue has no registers to spare)
+      constexpr bool kPipe = EPI >= 0 && (EPI & (F_MULAUX | F_DGELU)) != 0;
+      ChunkIn<STAGED> cin[kPipe ? 2 : 1];
+      if (kPipe && live && n0 + cbase * 32 < N) chunk_prefetch<EPI, STAGED>(ep, cin[0], row0, n0 + cbase * 32, M, N, lane);
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const int row = m0 + lane_grp * 32 + lane;
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(lane_grp * 32) << 16);
-#pragma unroll 1
-      for (int c = col_half * (BN / 64); c < (col_half + 1) * (BN / 64); ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= N) break;  // warp-uniform
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(taddr + c * 32, r);
-        ptx::tmem_ld_wait();
-        if (row < M && (has_k || !ep.atomic_add)) {
-          float v[32];
+      if (live) {
+        if constexpr (kPipe) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = has_k ? __uint_as_float(r[i]) : 0.f;
-          epilogue_row_chunk(ep, v, row, col0, min(32, N - col0), N);
+          for (int i = 0; i < kChunks; ++i) {
+            const int col0 = n0 + (cbase + i) * 32;
+            if (col0 < N) {  // warp-uniform
+              if (i + 1 < kChunks && col0 + 32 < N) chunk_prefetch<EPI, STAGED>(ep, cin[(i + 1) & 1], row0, col0 + 32, M, N, lane);
+              uint32_t r[32];
+              ptx::tmem_ld_32x32(taddr + (cbase + i) * 32, r);
+              ptx::tmem_ld_wait();
+              chunk_finish<EPI, STAGED>(ep, cin[i & 1], stage, r, !has_k, row0, col0, M, N, lane);
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int i = 0; i < kChunks; ++i) {
+            const int col0 = n0 + (cbase + i) * 32;
+            if (col0 >= N) break;  // warp-uniform
+            chunk_prefetch<EPI, STAGED>(ep, cin[0], row0, col0, M, N, lane);
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(taddr + (cbase + i) * 32, r);
+            ptx::tmem_ld_wait();
+            chunk_finish<EPI, STAGED>(ep, cin[0], stage, r, !has_k, row0, col0, M, N, lane);
+          }
         }
       }
       ptx::tc_fence_before();
@@ -393,8 +563,8 @@ __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, int a_mn, 
     }
   }
   EpiArgs e2 = ep;
-  e2.vec_ok = 0;
-  epilogue_row_chunk(e2, v, row, col0, cnt, N);
+  e2.flags &= ~F_VEC;
+  for (int c = 0; c < cnt; c += 8) epilogue_8(e2, v + c, row, col0 + c, min(8, cnt - c), N);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -447,11 +617,11 @@ int sm_count() {
   return g_sm_count;
 }
 
-template <int BN, int A_MN, int B_MN, int CL>
+template <int BN, int A_MN, int B_MN, int CL, int EPI, bool STAGED>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiArgs& ep, int M, int N, int K, int split_k,
                      cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CL>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CL, EPI, STAGED>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) {
@@ -479,20 +649,24 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiArgs
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, M, N, K, split_k);
   if (e != cudaSuccess) {
     cudaGetLastError();
-    set_error("samk_gemm_bf16: cluster launch failed: %s", cudaGetErrorString(e));
+    set_error("samk_gemm_bf16: launch failed: %s", cudaGetErrorString(e));
     return SAMK_ERR_CUDA;
   }
   return check_launch("samk_gemm_bf16");
 }
 
-static int g_gemm_cluster = -1;
-static int gemm_cluster() {
-  if (g_gemm_cluster < 0) {
-    const char* s = getenv("SAMK_GEMM_CLUSTER");
-    g_gemm_cluster = (s && s[0] == '2') ? 2 : 1;
-  }
-  return g_gemm_cluster;
-}
+// the epilogue combinations of the SA-M4C layers that get a compile-time specialised kernel
+constexpr int M_QKV = F_OUT_BF16 | F_BIAS | F_VEC;                                        // fused q|k|v projection
+constexpr int M_OUTPROJ = F_BIAS | F_DROP | F_RES | F_VEC;                                // W_o / FFN2 forward (train)
+constexpr int M_FFN1 = F_OUT_BF16 | F_BIAS | F_GELU_PAIR | F_PRE_BF16 | F_VEC;           // FFN1 forward (train)
+constexpr int M_BF16 = F_OUT_BF16 | F_VEC;                                                // W_o dgrad
+constexpr int M_F32_BIAS = F_BIAS | F_VEC;                                                // input projections, heads
+constexpr int M_F32_BIAS_RES = F_BIAS | F_RES | F_VEC;                                    // inference W_o / FFN2
+constexpr int M_GELU = F_OUT_BF16 | F_BIAS | F_GELU | F_VEC;                              // inference FFN1
+constexpr int M_MULAUX = F_OUT_BF16 | F_MULAUX | F_AUX_BF16 | F_VEC;                      // FFN2 dgrad * gelu'
+constexpr int M_F32_RES = F_RES | F_VEC;                                                  // FFN1 / qkv dgrad + skip grad
+constexpr int M_F32 = F_VEC;
+constexpr int M_ATOMIC = F_ATOMIC | F_VEC;                                                // wgrad accumulation
 
 }  // namespace samk
 
@@ -510,22 +684,38 @@ extern "C" int samk_gemm_bf16(const void* A, int a_mn, long long lda, const void
     set_error("samk_gemm_bf16: operands need 16-byte aligned base and ld %% 8 == 0 (lda=%lld ldb=%lld)", lda, ldb);
     return SAMK_ERR_ARG;
   }
+  if ((e->act == 2 || e->act == 4) && !e->aux) { set_error("samk_gemm_bf16: act=2/4 needs aux"); return SAMK_ERR_ARG; }
+  if (e->act == 3 && !e->pre) { set_error("samk_gemm_bf16: act=3 needs pre"); return SAMK_ERR_ARG; }
+  if (e->act < 0 || e->act > 4) { set_error("samk_gemm_bf16: unknown act %d", e->act); return SAMK_ERR_ARG; }
   EpiArgs ep;
-  ep.out = e->out; ep.ldo = e->ldo; ep.out_bf16 = e->out_dtype == SAMK_DT_BF16; ep.atomic_add = e->atomic_add;
-  ep.alpha = e->alpha; ep.bias = e->bias;
-  ep.pre = e->pre; ep.ldpre = e->ldpre; ep.pre_bf16 = e->pre_dtype == SAMK_DT_BF16;
-  ep.act = e->act; ep.aux = e->aux; ep.ldaux = e->ldaux; ep.aux_bf16 = e->aux_dtype == SAMK_DT_BF16;
+  ep.out = e->out; ep.ldo = e->ldo; ep.alpha = e->alpha; ep.bias = e->bias;
+  ep.pre = e->pre; ep.ldpre = e->ldpre;
+  ep.aux = e->aux; ep.ldaux = e->ldaux;
   ep.drop_thresh = e->drop_p > 0.f ? drop_threshold(e->drop_p) : 0u;
-  ep.drop_scale = e->drop_p > 0.f ? 1.0f / (1.0f - e->drop_p) : 1.0f;
+  ep.drop_scale = drop_keep_scale(e->drop_p);
   ep.seed = e->drop_seed; ep.offset = e->drop_offset;
   ep.residual = e->residual; ep.ldres = e->ldres;
-  if ((ep.act == 2 || ep.act == 4) && !ep.aux) { set_error("samk_gemm_bf16: act=2/4 needs aux"); return SAMK_ERR_ARG; }
-  if (ep.act == 3 && !ep.pre) { set_error("samk_gemm_bf16: act=3 needs pre"); return SAMK_ERR_ARG; }
   auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
-  ep.vec_ok = (N % 4 == 0) && al16(ep.out) && (ep.ldo % 8 == 0) && (!ep.bias || al16(ep.bias)) &&
-              (!ep.pre || (al16(ep.pre) && ep.ldpre % 8 == 0)) && (!ep.aux || (al16(ep.aux) && ep.ldaux % 8 == 0)) &&
-              (!ep.residual || (al16(ep.residual) && ep.ldres % 4 == 0));
-  if (K == 0 && !ep.atomic_add) split_k = 1;
+  const bool vec_ok = (N % 8 == 0) && al16(ep.out) && (ep.ldo % 8 == 0) && (!ep.bias || al16(ep.bias)) &&
+                      (!ep.pre || (al16(ep.pre) && ep.ldpre % 8 == 0)) && (!ep.aux || (al16(ep.aux) && ep.ldaux % 8 == 0)) &&
+                      (!ep.residual || (al16(ep.residual) && ep.ldres % 4 == 0));
+  int flags = 0;
+  if (e->out_dtype == SAMK_DT_BF16) flags |= F_OUT_BF16;
+  if (ep.bias) flags |= F_BIAS;
+  if (ep.drop_thresh) flags |= F_DROP;
+  if (ep.residual) flags |= F_RES;
+  if (e->act == 3) flags |= F_GELU_PAIR;
+  else if (ep.pre) flags |= F_PRE;
+  if (ep.pre && e->pre_dtype == SAMK_DT_BF16) flags |= F_PRE_BF16;
+  if (e->act == 4) flags |= F_MULAUX;
+  if (e->act == 2) flags |= F_DGELU;
+  if ((e->act == 2 || e->act == 4) && e->aux_dtype == SAMK_DT_BF16) flags |= F_AUX_BF16;
+  if (e->act == 1) flags |= F_GELU;
+  if (e->atomic_add) flags |= F_ATOMIC;
+  if (ep.alpha != 1.0f) flags |= F_ALPHA;
+  if (vec_ok) flags |= F_VEC;
+  ep.flags = flags;
+  if (K == 0 && !e->atomic_add) split_k = 1;
 
   if (impl == 1) {
     long long chunks = (long long)M * ((N + 31) / 32);
@@ -546,26 +736,44 @@ extern "C" int samk_gemm_bf16(const void* A, int a_mn, long long lda, const void
   if (a_mn) rc = make_tmap_bf16_2d(&ta, A, K, M, lda, 64, BK);
   else rc = make_tmap_bf16_2d(&ta, A, M, K, lda, BK, BM);
   if (rc) return rc;
-  const int cl = gemm_cluster();
   if (b_mn) rc = make_tmap_bf16_2d(&tb, B, K, N, ldb, 64, BK);
-  else rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, BK, bn / cl);     // each cluster CTA fetches bn/cl rows of B
+  else rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, BK, bn);
   if (rc) return rc;
 
-#define SAMK_LAUNCH(BN_, AM_, BM_)                                                        \
-  do {                                                                                    \
-    if (cl == 2) return launch_tc<BN_, AM_, BM_, 2>(ta, tb, ep, M, N, K, split_k, stream); \
-    return launch_tc<BN_, AM_, BM_, 1>(ta, tb, ep, M, N, K, split_k, stream);              \
-  } while (0)
-  if (bn == 256) {
-    if (!a_mn && !b_mn) SAMK_LAUNCH(256, 0, 0);
-    if (!a_mn && b_mn) SAMK_LAUNCH(256, 0, 1);
-    if (a_mn && !b_mn) SAMK_LAUNCH(256, 1, 0);
-    SAMK_LAUNCH(256, 1, 1);
-  } else {
-    if (!a_mn && !b_mn) SAMK_LAUNCH(128, 0, 0);
-    if (!a_mn && b_mn) SAMK_LAUNCH(128, 0, 1);
-    if (a_mn && !b_mn) SAMK_LAUNCH(128, 1, 0);
-    SAMK_LAUNCH(128, 1, 1);
+  // specialised epilogues run in the coalesced (shared-memory transposed) layout: measured faster than the
+  // row-per-thread layout for every combination below (tools/gemm_bench.py)
+#define SAMK_SPEC(AM_, BM_, MASK_)                                                                        \
+  if (a_mn == AM_ && b_mn == BM_ && flags == (MASK_)) {                                                    \
+    if (bn == 256) return launch_tc<256, AM_, BM_, 1, MASK_, true>(ta, tb, ep, M, N, K, split_k, stream); \
+    return launch_tc<128, AM_, BM_, 1, MASK_, true>(ta, tb, ep, M, N, K, split_k, stream);                \
   }
-#undef SAMK_LAUNCH
+  SAMK_SPEC(0, 0, M_QKV)
+  SAMK_SPEC(0, 0, M_OUTPROJ)
+  SAMK_SPEC(0, 0, M_FFN1)
+  SAMK_SPEC(0, 0, M_BF16)
+  SAMK_SPEC(0, 0, M_F32_BIAS)
+  SAMK_SPEC(0, 0, M_F32_BIAS_RES)
+  SAMK_SPEC(0, 0, M_GELU)
+  SAMK_SPEC(0, 0, M_F32)
+  SAMK_SPEC(0, 1, M_BF16)
+  SAMK_SPEC(0, 1, M_MULAUX)
+  SAMK_SPEC(0, 1, M_F32_RES)
+  SAMK_SPEC(0, 1, M_F32)
+  SAMK_SPEC(1, 1, M_ATOMIC)
+#undef SAMK_SPEC
+
+  // anything else: runtime-flag epilogue
+#define SAMK_DYN(BN_, AM_, BM_) return launch_tc<BN_, AM_, BM_, 1, EPI_DYNAMIC, false>(ta, tb, ep, M, N, K, split_k, stream)
+  if (bn == 256) {
+    if (!a_mn && !b_mn) SAMK_DYN(256, 0, 0);
+    if (!a_mn && b_mn) SAMK_DYN(256, 0, 1);
+    if (a_mn && !b_mn) SAMK_DYN(256, 1, 0);
+    SAMK_DYN(256, 1, 1);
+  } else {
+    if (!a_mn && !b_mn) SAMK_DYN(128, 0, 0);
+    if (!a_mn && b_mn) SAMK_DYN(128, 0, 1);
+    if (a_mn && !b_mn) SAMK_DYN(128, 1, 0);
+    SAMK_DYN(128, 1, 1);
+  }
+#undef SAMK_DYN
 }

@@ -33,6 +33,11 @@ run("plain_3072", lambda: g(O(x768), False, O(W_1), False, M, 3072, 768, o3072b)
 run("plain_768k3072", lambda: g(O(x3072), False, O(W_2), False, M, 768, 3072, o768b), 2 * M * 3072 * 768)
 run("qkv_fwd", lambda: g(O(x768), False, O(W_qkv), False, M, 2304, 768, o2304b, bias=b2304), 2 * M * 2304 * 768)
 run("o_fwd", lambda: g(O(x768), False, O(W_o), False, M, 768, 768, o768f, bias=b768, drop_p=0.1, drop=(1, 2), residual=res), 2 * M * 768 * 768)
+run("o_f32", lambda: g(O(x768), False, O(W_o), False, M, 768, 768, o768f), 2 * M * 768 * 768)
+run("o_f32_bias", lambda: g(O(x768), False, O(W_o), False, M, 768, 768, o768f, bias=b768), 2 * M * 768 * 768)
+run("o_f32_res", lambda: g(O(x768), False, O(W_o), False, M, 768, 768, o768f, residual=res), 2 * M * 768 * 768)
+run("o_f32_drop", lambda: g(O(x768), False, O(W_o), False, M, 768, 768, o768f, drop_p=0.1, drop=(1, 2)), 2 * M * 768 * 768)
+run("o_bf16_drop", lambda: g(O(x768), False, O(W_o), False, M, 768, 768, o768b, drop_p=0.1, drop=(1, 2)), 2 * M * 768 * 768)
 run("ffn1_fwd", lambda: g(O(x768), False, O(W_1), False, M, 3072, 768, o3072b, bias=b3072, act=3, pre=pre3072), 2 * M * 3072 * 768)
 run("ffn2_fwd", lambda: g(O(x3072), False, O(W_2), False, M, 768, 3072, o768f, bias=b768, drop_p=0.1, drop=(1, 2), residual=res), 2 * M * 3072 * 768)
 run("ffn2_dgrad", lambda: g(O(dy768), False, O(W_2), True, M, 3072, 768, o3072b, act=4, aux=pre3072), 2 * M * 3072 * 768)
