@@ -17,6 +17,8 @@
 // The mask is a precomputed bit matrix allow[b, h|0, i, j/32] built once per step by
 // attn_build_mask_kernel from key_valid + packed relation words (attn_mask.cuh), 6 words per row
 // at L=182 instead of the reference's fp32 [B,L,L,12] tensor.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "attn_mask.cuh"
@@ -271,6 +273,417 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
+// forward, persistent + warp-specialised (the product path)
+//
+//   warp 0      TMA producer: Q tile pair (2 stages) and K/V tiles (KS-stage ring)
+//   warps 1,2   MMA issuers (one lane each), one per query tile g of the pair: S_g = Q_g K^T into TMEM,
+//               O_g (+)= P_g V with P_g read from TMEM
+//   warps 3-18  softmax: 8 warps per query tile = 4 TMEM lane quarters (32 query rows each) x 2 halves of the
+//               key tile; a row's two threads exchange their partial maximum / sum through shared memory
+//   work item   (sample, head, query-tile pair); a CTA walks items blockIdx.x, +gridDim.x, ...
+//
+// Per key tile: each thread reads its score row from TMEM once for the masked maximum and once for
+// p = 2^(s*c - m); the probabilities go back into TMEM as packed bf16 over the columns of S (no
+// shared-memory round trip: the MMA's shared-memory read port is the scarce resource on this part) and
+// are the A operand of the P V product.  Dropout bits come straight from Philox comparisons as select
+// predicates; the 1/(1-p) scale and the softmax denominator are applied once to the 64 output columns.
+// TMEM: group g uses columns [256 g, 256 g + KVT) for S/P and [256 g + 192, 256 g + 256) for O.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+#ifdef SAMK_TIMELINE
+// developer instrumentation (tools/attn_timeline.py): clock stamps of CTA 0's first items
+__device__ long long g_timeline[4096];
+#define TL_STAMP(slot, idx) do { if (blockIdx.x == 0 && (idx) < 64) g_timeline[(slot) * 64 + (idx)] = clock64(); } while (0)
+#else
+#define TL_STAMP(slot, idx) do { } while (0)
+#endif
+
+template <int KVT> struct Fwd2Cfg {
+  static constexpr int KS = KVT == 192 ? 2 : 3;             // K/V ring depth
+  static constexpr int kQBytes = 2 * 16384;                 // one stage: two 128 x 64 query tiles
+  static constexpr int kKVBytes = 2 * KVT * 128;            // one stage: K tile + V tile
+  static constexpr int kBarOff = 2 * kQBytes + KS * kKVBytes;
+  static constexpr int kXchOff = kBarOff + 256;             // row max / row sum exchange between column halves
+  static constexpr int kXchBytes = 2 /*kind*/ * 2 /*slot*/ * 2 /*tile*/ * 2 /*half*/ * 128 * 4;
+  static constexpr int kOutOff = kXchOff + kXchBytes;       // per softmax warp: 32 rows x 32 bf16 output transpose
+  static constexpr int kSmem = kOutOff + 16 * 2048 + 1024;
+};
+constexpr int kFwd2Threads = 96 + 16 * 32;     // producer, one MMA issuer per query tile, 16 softmax warps
+
+// allow words are re-read by all 12 heads' CTAs (non-spatial) / once per head: keep them in L2, skip L1
+__device__ __forceinline__ uint32_t ld_allow(const uint32_t* p) { return __ldg(p); }
+
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  while (!ptx::mbar_try_wait(bar, parity)) __nanosleep(64);
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+// masked maximum of 16 scores (aw: allow bits of these 16 keys in the low half)
+__device__ __forceinline__ float masked_max16(const uint32_t (&r)[16], uint32_t aw, float m) {
+  float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    if ((aw >> i) & 1u) m0 = fmaxf(m0, __uint_as_float(r[i]));
+    if ((aw >> (i + 1)) & 1u) m1 = fmaxf(m1, __uint_as_float(r[i + 1]));
+    if ((aw >> (i + 2)) & 1u) m2 = fmaxf(m2, __uint_as_float(r[i + 2]));
+    if ((aw >> (i + 3)) & 1u) m3 = fmaxf(m3, __uint_as_float(r[i + 3]));
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// 16 scores -> probabilities (masked, dropout applied) as 8 packed bf16 pairs; returns the sum of the
+// undropped probabilities.  grp0 = Philox group index of the first of the two 8-key groups.
+__device__ __forceinline__ float softmax_chunk16(const uint32_t (&r)[16], uint32_t aw, float sl2, float m_use,
+                                                 bool drop, uint64_t seed, uint32_t off, uint64_t grp0, uint32_t th16,
+                                                 uint32_t (&pk)[8]) {
+  float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    float e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float x = fmaf(__uint_as_float(r[8 * q + i]), sl2, -m_use);
+      e[i] = ((aw >> (8 * q + i)) & 1u) ? fast_exp2(x) : 0.f;
+    }
+    l0 += e[0] + e[4]; l1 += e[1] + e[5]; l2 += e[2] + e[6]; l3 += e[3] + e[7];
+    if (drop) {
+      const uint4 rnd = philox4x32(seed, grp0 + (uint64_t)q, off);
+      e[0] = (rnd.x << 16) >= th16 ? e[0] : 0.f;
+      e[1] = rnd.x >= th16 ? e[1] : 0.f;
+      e[2] = (rnd.y << 16) >= th16 ? e[2] : 0.f;
+      e[3] = rnd.y >= th16 ? e[3] : 0.f;
+      e[4] = (rnd.z << 16) >= th16 ? e[4] : 0.f;
+      e[5] = rnd.z >= th16 ? e[5] : 0.f;
+      e[6] = (rnd.w << 16) >= th16 ? e[6] : 0.f;
+      e[7] = rnd.w >= th16 ? e[7] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pk[4 * q + i] = pack_bf16(e[2 * i], e[2 * i + 1]);
+  }
+  return (l0 + l1) + (l2 + l3);
+}
+
+template <int KVT>
+__global__ void __launch_bounds__(kFwd2Threads, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const TcArgs a,
+                 int n_qp, int qp0, int n_items, uint32_t magic_qp, uint32_t magic_h) {
+  using Cfg = Fwd2Cfg<KVT>;
+  constexpr int KS = Cfg::KS;
+  constexpr int NC = KVT / 32;                          // 16-key chunks per thread (its half of the key tile)
+  extern __shared__ uint8_t smem_raw2[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // [2][2][128 x 64]
+  uint8_t* sKV = smem + 2 * Cfg::kQBytes;               // [KS][K | V]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* q_full = bars;            // [2]
+  uint64_t* q_empty = bars + 2;       // [2]
+  uint64_t* kv_full = bars + 4;       // [KS]
+  uint64_t* kv_empty = bars + 4 + KS; // [KS]
+  uint64_t* s_full = bars + 4 + 2 * KS;   // [2]
+  uint64_t* p_ready = s_full + 2;         // [2]
+  uint64_t* o_done = s_full + 4;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
+  float* xch = reinterpret_cast<float*>(smem + Cfg::kXchOff);   // [kind][slot][tile][half][128]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = a.L, H = a.H;
+  const int n_kv = (L + KVT - 1) / KVT;
+  const int n_qt = (L + 127) / 128;
+
+  if (tid == 0) {
+    ptx::prefetch_tensormap(&tmQ); ptx::prefetch_tensormap(&tmKV);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&q_full[i], 1); ptx::mbar_init(&q_empty[i], 2); }
+    for (int i = 0; i < KS; ++i) { ptx::mbar_init(&kv_full[i], 1); ptx::mbar_init(&kv_empty[i], 2); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&s_full[i], 1); ptx::mbar_init(&p_ready[i], 8); ptx::mbar_init(&o_done[i], 1); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // item -> (b, h, first query tile); the last, partial query tile of a sample is loaded shifted up on odd
+  // iterations (its rows then sit in the upper TMEM lanes) so that both halves of the SM's warp
+  // schedulers get the short tile's work in turn
+  auto decode = [&](int item, int iter, int& b, int& h, int& qs0, int& qs1, int& ql0, int& ql1) {
+    // exact for item < 2^32 / divisor (magic = ceil(2^32 / divisor), host side)
+    const int bh = n_qp == 1 ? item : (int)__umulhi((uint32_t)item, magic_qp);
+    const int qp = qp0 + item - bh * n_qp;
+    b = (int)__umulhi((uint32_t)bh, magic_h);
+    h = bh - b * H;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int qt = 2 * qp + g;
+      int st = qt * 128, lo = qt * 128;
+      if (qt >= n_qt || qt < a.q_tile0) { st = -1; lo = 0; }
+      else if ((iter & 1) && qt == n_qt - 1 && L >= 128 && L - qt * 128 <= 64) st = L - 128;
+      if (g == 0) { qs0 = st; ql0 = lo; } else { qs1 = st; ql1 = lo; }
+    }
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int iter = 0; uint32_t kvc = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++iter) {
+        int b, h, qs0, qs1, ql0, ql1;
+        decode(item, iter, b, h, qs0, qs1, ql0, ql1);
+        const int qs = iter & 1;
+        mbar_wait_backoff(&q_empty[qs], ((iter >> 1) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&q_full[qs], ((qs0 >= 0) + (qs1 >= 0)) * 16384);
+        if (qs0 >= 0) ptx::tma_load_2d(sQ + qs * Cfg::kQBytes, &tmQ, &q_full[qs], h * TDH, b * L + qs0);
+        if (qs1 >= 0) ptx::tma_load_2d(sQ + qs * Cfg::kQBytes + 16384, &tmQ, &q_full[qs], h * TDH, b * L + qs1);
+        for (int t = 0; t < n_kv; ++t, ++kvc) {
+          const int ks = kvc % KS;
+          mbar_wait_backoff(&kv_empty[ks], ((kvc / KS) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&kv_full[ks], Cfg::kKVBytes);
+          uint8_t* sk = sKV + ks * Cfg::kKVBytes;
+          ptx::tma_load_2d(sk, &tmKV, &kv_full[ks], (H + h) * TDH, b * L + t * KVT);
+          ptx::tma_load_2d(sk + KVT * 128, &tmKV, &kv_full[ks], (2 * H + h) * TDH, b * L + t * KVT);
+        }
+      }
+    }
+  } else if (warp <= 2) {
+    // ===================== MMA issuers: warp 1 drives query tile 0, warp 2 query tile 1 =====================
+    // (independent pipelines: the short last tile of a sample runs ahead instead of waiting for the full one)
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, KVT, 0, 0);
+      constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, 64, 0, 1);
+      const int g = warp - 1;
+      int iter = 0; uint32_t kvc = 0; uint32_t pc = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++iter) {
+        int b, h, qs0, qs1, ql0, ql1;
+        decode(item, iter, b, h, qs0, qs1, ql0, ql1);
+        const bool exists = (g ? qs1 : qs0) >= 0;
+        const int qs = iter & 1;
+        if (g == 0) TL_STAMP(0, iter);
+        mbar_wait_backoff(&q_full[qs], (iter >> 1) & 1);
+        for (int t = 0; t < n_kv; ++t, ++kvc) {
+          const int ks = kvc % KS;
+          mbar_wait_backoff(&kv_full[ks], (kvc / KS) & 1);
+          ptx::tc_fence_after();
+          if (g == 0) TL_STAMP(1, iter);
+          const uint32_t sk = ptx::smem_u32(sKV + ks * Cfg::kKVBytes), sv = sk + KVT * 128;
+          if (exists) {
+            const uint32_t sq = ptx::smem_u32(sQ + qs * Cfg::kQBytes + g * 16384);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_f16(tmem + g * 256, ptx::make_smem_desc_sw128(sq + k * 32, 16, 1024),
+                            ptx::make_smem_desc_sw128(sk + k * 32, 16, 1024), idesc_s, k > 0);
+            ptx::umma_commit(&s_full[g]);
+          }
+          if (t == n_kv - 1) {                     // all S products of this item issued: Q stage may be refilled
+            if (exists) ptx::umma_commit(&q_empty[qs]); else ptx::mbar_arrive(&q_empty[qs]);
+          }
+          if (exists) {
+            if (g == 0) TL_STAMP(2, iter);
+            ptx::mbar_wait(&p_ready[g], pc & 1); ++pc;
+            ptx::tc_fence_after();
+            if (g == 0) TL_STAMP(3, iter);
+#pragma unroll
+            for (int k = 0; k < KVT / 16; ++k)   // P (packed bf16) sits at the start of each column half of S
+              ptx::umma_f16_ts(tmem + g * 256 + 192, tmem + g * 256 + (k < KVT / 32 ? k * 8 : KVT / 2 + (k - KVT / 32) * 8),
+                               ptx::make_smem_desc_sw128(sv + k * 2048, 16384, 1024), idesc_o, (t > 0 || k > 0) ? 1u : 0u);
+            ptx::umma_commit(&o_done[g]);
+            ptx::umma_commit(&kv_empty[ks]);
+          } else {
+            ptx::mbar_arrive(&kv_empty[ks]);
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== softmax warps =====================
+    // 16 warps: query tile g = (warp-3)/8, column half hf = ((warp-3)/4)&1 (keys [hf*KVT/2, +KVT/2) of the key
+    // tile and output columns [32 hf, +32)), TMEM lane quarter = warp % 4.  The two halves of a row meet
+    // twice per key tile through shared memory (row maximum) and once per item (row sum).
+    const int g = (warp - 3) >> 3, hf = ((warp - 3) >> 2) & 1, quarter = warp & 3;
+    const int lrow = quarter * 32 + lane;
+    const uint32_t t_s = tmem + g * 256 + ((uint32_t)(quarter * 32) << 16);   // S columns of this tile
+    const uint32_t t_o = t_s + 192 + hf * 32;                                    // this half's 32 output columns
+    const uint32_t th16 = a.drop_thresh << 16;
+    const bool drop = a.drop_thresh != 0;
+    const float sl2 = a.scale_log2;
+    const uint32_t ngrp = (uint32_t)((L + 7) >> 3);
+    uint32_t sc = 0, oc = 0, xc = 0;
+    int iter = 0;
+    // allow-bit words of this thread's (row, key half), fetched one (item, key tile) ahead of their use
+    uint32_t aw_nx[NC / 2];
+    auto fetch_allow = [&](int item_, int iter_, int t_) {
+#pragma unroll
+      for (int c = 0; c < NC / 2; ++c) aw_nx[c] = 0u;
+      if (item_ >= n_items) return;
+      int b_, h_, s0, s1, l0, l1;
+      decode(item_, iter_, b_, h_, s0, s1, l0, l1);
+      const int st = g ? s1 : s0, lo = g ? l1 : l0;
+      const int row_ = st + lrow;
+      if (st < 0 || row_ < lo || row_ >= L) return;
+      const uint32_t* ar = a.allow + (((size_t)b_ * a.Hm + (a.Hm == 1 ? 0 : h_)) * L + row_) * a.W;
+      const int w0 = (t_ * KVT + hf * (KVT / 2)) >> 5;
+#pragma unroll
+      for (int c = 0; c < NC / 2; ++c) if (w0 + c < a.W) aw_nx[c] = ld_allow(ar + w0 + c);
+    };
+    fetch_allow(blockIdx.x, 0, 0);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++iter) {
+      int b, h, qs0, qs1, ql0, ql1;
+      decode(item, iter, b, h, qs0, qs1, ql0, ql1);
+      const int my_start = g ? qs1 : qs0, my_lo = g ? ql1 : ql0;
+      if (my_start < 0) { fetch_allow(item + gridDim.x, iter + 1, 0); continue; }
+      const int row = my_start + lrow;
+      const bool active = row >= my_lo && row < L;
+      const bool warp_active = __any_sync(0xffffffffu, active);
+      const uint64_t drow = ((uint64_t)(b * H + h) * L + (uint64_t)row) * ngrp;
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int t = 0; t < n_kv; ++t) {
+        const int k0 = t * KVT + hf * (KVT / 2);        // first key of this thread's half
+        uint32_t aw_t[NC / 2];
+#pragma unroll
+        for (int c = 0; c < NC / 2; ++c) aw_t[c] = aw_nx[c];
+        if (t + 1 < n_kv) fetch_allow(item, iter, t + 1); else fetch_allow(item + gridDim.x, iter + 1, 0);
+        if (warp == 3 && lane == 0) TL_STAMP(8, iter);
+        ptx::mbar_wait(&s_full[g], sc & 1); ++sc;
+        ptx::tc_fence_after();
+        if (warp == 3 && lane == 0) TL_STAMP(9, iter);
+        const uint32_t t_sh = t_s + hf * (KVT / 2);
+        uint32_t rA[16], rB[16];
+        // ---- pass 1: masked maximum of this half of the row (TMEM loads one chunk ahead of the math)
+        float tmax = -INFINITY;
+        if (warp_active) {
+          ptx::tmem_ld_32x16(t_sh, rA);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            if (c + 1 < NC) ptx::tmem_ld_32x16(t_sh + (c + 1) * 16, (c & 1) ? rA : rB);
+            tmax = masked_max16((c & 1) ? rB : rA, aw_t[c >> 1] >> (16 * (c & 1)), tmax);
+            if (c + 1 < NC) ptx::tmem_ld_wait();
+          }
+          // first chunk of pass 2 is fetched while the halves exchange their maxima
+          ptx::tmem_ld_32x16(t_sh, rA);
+        }
+        float* xm = xch + (((0 * 2 + (xc & 1)) * 2 + g) * 2) * 128;
+        xm[hf * 128 + lrow] = tmax;
+        if (warp == 3 && lane == 0) TL_STAMP(10, iter);
+        named_bar_sync(1 + g, 256);
+        if (warp == 3 && lane == 0) TL_STAMP(11, iter);
+        tmax = fmaxf(tmax, xm[(hf ^ 1) * 128 + lrow]);
+        ++xc;
+        if (warp_active) {
+          tmax *= sl2;                               // scale > 0: max commutes with the scaling
+          const float m_new = fmaxf(m_run, tmax);
+          const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+          if (t > 0) {
+            ptx::tmem_ld_wait();
+            ptx::mbar_wait(&o_done[g], oc & 1); ++oc;     // P V of the previous key tile has landed in O
+            ptx::tc_fence_after();
+            const float corr = (m_run == -INFINITY) ? 1.f : fast_exp2(m_run - m_use);
+            l_run *= corr;
+            if (__any_sync(0xffffffffu, corr != 1.f)) {
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                ptx::tmem_ld_32x16(t_o + c * 16, rB);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) rB[i] = __float_as_uint(__uint_as_float(rB[i]) * corr);
+                tmem_st_32x16(t_o + c * 16, rB);
+              }
+            }
+          }
+          m_run = m_new;
+          // ---- pass 2: p = 2^(s c - m) on allowed keys; kept (dropout) values -> packed bf16 P in TMEM
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            if (c + 1 < NC) ptx::tmem_ld_32x16(t_sh + (c + 1) * 16, (c & 1) ? rA : rB);
+            uint32_t pk[8];
+            l_run += softmax_chunk16((c & 1) ? rB : rA, aw_t[c >> 1] >> (16 * (c & 1)), sl2, m_use, drop, a.seed,
+                                     (uint32_t)a.off, drow + (uint64_t)((k0 >> 3) + c * 2), th16, pk);
+            if (c + 1 < NC) ptx::tmem_ld_wait();      // also orders the P store below after the S load of the same columns
+            tmem_st_32x8(t_sh + c * 8, pk);   // P of this half overlays the first columns of its own S half
+          }
+          tmem_st_wait();
+        } else if (t > 0) {
+          ++oc;                                   // keep the O-phase count in step without touching TMEM
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&p_ready[g]);
+        if (warp == 3 && lane == 0) TL_STAMP(12, iter);
+      }
+      // ---- epilogue: ctx = O * keep_scale / l, lse = ln(sum exp); the halves add their partial sums
+      float* xl = xch + (((1 * 2 + (iter & 1)) * 2 + g) * 2) * 128;
+      xl[hf * 128 + lrow] = l_run;
+      named_bar_sync(1 + g, 256);
+      l_run += xl[(hf ^ 1) * 128 + lrow];
+      if (warp == 3 && lane == 0) TL_STAMP(13, iter);
+      if (warp_active) {
+        ptx::mbar_wait(&o_done[g], oc & 1); ++oc;
+        ptx::tc_fence_after();
+        if (warp == 3 && lane == 0) TL_STAMP(14, iter);
+        const float inv = l_run > 0.f ? a.drop_scale / l_run : 0.f;
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(t_o, r);
+        ptx::tmem_ld_wait();
+        // transpose through shared memory: a row-per-thread store would touch 32 cache lines per instruction
+        const uint32_t st = ptx::smem_u32(smem + Cfg::kOutOff) + (warp - 3) * 2048;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = 8 * j;
+          sts128u(st + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4),
+                  make_uint4(pack_bf16(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
+                             pack_bf16(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
+                             pack_bf16(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
+                             pack_bf16(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv)));
+        }
+        __syncwarp();
+        const int row_w = my_start + quarter * 32;      // first row of this warp
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + (lane >> 2), cj = lane & 3, orow = row_w + rr;
+          const uint4 v = lds128u(st + rr * 64 + ((cj ^ ((rr >> 1) & 3)) << 4));
+          if (orow >= my_lo && orow < L)
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.ctx) + ((size_t)b * L + orow) * (size_t)(H * TDH) + h * TDH +
+                                      hf * 32 + cj * 8) = v;
+        }
+        __syncwarp();
+        if (active && hf == 0) a.lse[((size_t)b * H + h) * L + row] = l_run > 0.f ? (m_run + log2f(l_run)) * kLn2 : INFINITY;
+        if (warp == 3 && lane == 0) TL_STAMP(15, iter);
+      } else {
+        ++oc;
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc<512>(tmem); }
+}
+
+// ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
 // delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]
@@ -518,12 +931,51 @@ static int launch_fwd(const samk_attn_params* p, const TcArgs& a, cudaStream_t s
   return check_launch("samk_attn_fwd(tc)");
 }
 
+int sm_count();
+
+template <int KVT>
+static int launch_fwd2(const samk_attn_params* p, const TcArgs& a, cudaStream_t stream) {
+  const long long rows = (long long)a.B * a.L;
+  const int hd3 = 3 * a.H * TDH;
+  CUtensorMap tq, tkv;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&tq, p->qkv, rows, hd3, hd3, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tkv, p->qkv, rows, hd3, hd3, 64, KVT))) return rc;
+  if ((rc = set_smem(attn_fwd2_kernel<KVT>, Fwd2Cfg<KVT>::kSmem))) return rc;
+  const int n_qt = (a.L + 127) / 128;
+  const int qp0 = a.q_tile0 / 2;
+  const int n_qp = (n_qt + 1) / 2 - qp0;
+  if (n_qp <= 0) return SAMK_OK;
+  const long long n_items = (long long)a.B * a.H * n_qp;
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  const int grid = (int)(n_items < sms ? n_items : sms);
+  if (n_items >= (1ll << 24)) { set_error("samk_attn_fwd: too many work items"); return SAMK_ERR_UNSUPPORTED; }
+  const uint32_t magic_qp = (uint32_t)(((1ull << 32) + n_qp - 1) / n_qp), magic_h = (uint32_t)(((1ull << 32) + a.H - 1) / a.H);
+  attn_fwd2_kernel<KVT><<<grid, kFwd2Threads, Fwd2Cfg<KVT>::kSmem, stream>>>(tq, tkv, a, n_qp, qp0, (int)n_items, magic_qp,
+                                                                            magic_h);
+  return check_launch("samk_attn_fwd(tc v2)");
+}
+
+static int attn_fwd_version() {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("SAMK_ATTN_FWD_V");
+    v = (s && s[0] == '1') ? 1 : 2;
+  }
+  return v;
+}
+
 int attn_tc_fwd(const samk_attn_params* p, cudaStream_t stream) {
   TcArgs a;
   int rc = fill_tc(a, p);
   if (rc) return rc;
   if (!p->qkv || !p->ctx || !p->lse) { set_error("samk_attn_fwd: null pointer"); return SAMK_ERR_ARG; }
   if (!a.B || !a.L) return SAMK_OK;
+  if (attn_fwd_version() == 2) {
+    if (a.L > 128 && a.L <= 192) return launch_fwd2<192>(p, a, stream);
+    return launch_fwd2<128>(p, a, stream);
+  }
   // one 192-key tile covers the shipped L=182; otherwise stream 128-key tiles
   if (a.L > 128 && a.L <= 192) return launch_fwd<192>(p, a, stream);
   return launch_fwd<128>(p, a, stream);
@@ -562,6 +1014,12 @@ int attn_tc_bwd(const samk_attn_params* p, cudaStream_t stream) {
 }  // namespace samk
 
 extern "C" {
+
+#ifdef SAMK_TIMELINE
+int samk_debug_timeline(long long* dst, int n) {
+  return cudaMemcpyFromSymbol(dst, samk::g_timeline, sizeof(long long) * (size_t)(n < 4096 ? n : 4096)) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 long long samk_attn_mask_words(int B, int H, int T, int A, int D, int spatial) {
   const long long L = (long long)T + A + D;

@@ -1,0 +1,29 @@
+#!/usr/bin/env python
+"""Developer tool: per-item clock stamps of CTA 0 of the forward attention kernel (needs a build with
+SAMK_NVCC_EXTRA=-DSAMK_TIMELINE).  Prints, per item, cycles relative to the first stamp."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from sam_textvqa_b200 import ops, synth, _lib
+from sam_textvqa_b200.sa_m4c import pack_relation_bits
+dev = torch.device("cuda:0")
+B, T, O, R, D = 128, 20, 100, 50, 12
+A, L, H, d = O + R, T + O + R + D, 12, 768
+qkv = torch.randn(B * L, 3 * d, device=dev).bfloat16()
+valid = torch.ones(B, L, dtype=torch.uint8, device=dev); valid[:, -D:] = 0
+dims = (B, L, H, T, A, D)
+allow = ops.build_attn_mask(valid, None, dims, False, 0)
+p = float(os.environ.get("P", "0.1"))
+for _ in range(3):
+    ops.attention_fwd(qkv, valid, None, dims, False, 0, p, (1, 1), allow)
+torch.cuda.synchronize()
+buf = (ctypes.c_longlong * 4096)()
+lib = _lib.lib()
+lib.samk_debug_timeline.argtypes = [ctypes.c_void_p, ctypes.c_int]
+assert lib.samk_debug_timeline(buf, 4096) == 0
+tl = np.array(buf[:]).reshape(64, 64)
+names = {0: "mma:top", 1: "mma:kv_full", 2: "mma:S issued", 3: "mma:p_ready", 8: "sm:top", 9: "sm:s_full", 10: "sm:pass1 done",
+         11: "sm:max xchg", 12: "sm:P arrived", 13: "sm:l xchg", 14: "sm:o_done", 15: "sm:epilogue end"}
+t0 = tl[8, 0]
+for it in range(10):
+    print("item %d: " % it + "  ".join("%s=%d" % (names[s], tl[s, it] - t0) for s in sorted(names)))
