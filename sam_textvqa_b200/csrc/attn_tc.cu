@@ -30,6 +30,7 @@ int make_tmap_bf16_2d(CUtensorMap* m, const void* base, long long rows, long lon
                       int box_cols, int box_rows);
 int attn_simt_fwd(const samk_attn_params* p, cudaStream_t stream);
 int attn_simt_bwd(const samk_attn_params* p, cudaStream_t stream);
+int sm_count();
 
 constexpr int TDH = 64;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -301,9 +302,12 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
 #ifdef SAMK_TIMELINE
 // developer instrumentation (tools/attn_timeline.py): clock stamps of CTA 0's first items
 __device__ long long g_timeline[4096];
-#define TL_STAMP(slot, idx) do { if (blockIdx.x == 0 && (idx) < 64) g_timeline[(slot) * 64 + (idx)] = clock64(); } while (0)
+#define TL_STAMP(slot, idx) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (idx) < 64) g_timeline[(slot) * 64 + (idx)] = clock64(); } while (0)
+// converged-warp variant (MMA issuer warps: elect.sync needs the warp reconverged afterwards)
+#define TL_STAMP_W(slot, idx) do { TL_STAMP(slot, idx); __syncwarp(); } while (0)
 #else
 #define TL_STAMP(slot, idx) do { } while (0)
+#define TL_STAMP_W(slot, idx) do { } while (0)
 #endif
 
 template <int KVT> struct Fwd2Cfg {
@@ -470,10 +474,13 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else if (warp <= 2) {
     // ===================== MMA issuers: warp 1 drives query tile 0, warp 2 query tile 1 =====================
-    // (independent pipelines: the short last tile of a sample runs ahead instead of waiting for the full one)
-    if (lane == 0) {
+    // (independent pipelines: the short last tile of a sample runs ahead instead of waiting for the full one).
+    // The whole warp runs the loop converged and computes the warp-uniform descriptors; only the tcgen05
+    // instructions sit under the elected-lane predicate, so they issue back to back from uniform registers.
+    {
       constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, KVT, 0, 0);
       constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, 64, 0, 1);
+      constexpr uint64_t kStepK = 32 >> 4, kStepMN = 2048 >> 4;   // k-step increments of the descriptor address field
       const int g = warp - 1;
       int iter = 0; uint32_t kvc = 0; uint32_t pc = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++iter) {
@@ -481,39 +488,45 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         decode(item, iter, b, h, qs0, qs1, ql0, ql1);
         const bool exists = (g ? qs1 : qs0) >= 0;
         const int qs = iter & 1;
-        if (g == 0) TL_STAMP(0, iter);
+        if (g == 0) TL_STAMP_W(0, iter);
         mbar_wait_backoff(&q_full[qs], (iter >> 1) & 1);
         for (int t = 0; t < n_kv; ++t, ++kvc) {
           const int ks = kvc % KS;
           mbar_wait_backoff(&kv_full[ks], (kvc / KS) & 1);
           ptx::tc_fence_after();
-          if (g == 0) TL_STAMP(1, iter);
+          if (g == 0) TL_STAMP_W(1, iter);
           const uint32_t sk = ptx::smem_u32(sKV + ks * Cfg::kKVBytes), sv = sk + KVT * 128;
-          if (exists) {
-            const uint32_t sq = ptx::smem_u32(sQ + qs * Cfg::kQBytes + g * 16384);
+          const uint64_t dq = ptx::make_smem_desc_sw128(ptx::smem_u32(sQ + qs * Cfg::kQBytes + g * 16384), 16, 1024);
+          const uint64_t dk = ptx::make_smem_desc_sw128(sk, 16, 1024);
+          const uint64_t dv = ptx::make_smem_desc_sw128(sv, 16384, 1024);
+          if (ptx::elect_one()) {
+            if (exists) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ptx::umma_f16(tmem + g * 256, ptx::make_smem_desc_sw128(sq + k * 32, 16, 1024),
-                            ptx::make_smem_desc_sw128(sk + k * 32, 16, 1024), idesc_s, k > 0);
-            ptx::umma_commit(&s_full[g]);
+              for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem + g * 256, dq + k * kStepK, dk + k * kStepK, idesc_s, k > 0);
+              ptx::umma_commit(&s_full[g]);
+            }
+            if (t == n_kv - 1) {                     // all S products of this item issued: Q stage may be refilled
+              if (exists) ptx::umma_commit(&q_empty[qs]); else ptx::mbar_arrive(&q_empty[qs]);
+            }
           }
-          if (t == n_kv - 1) {                     // all S products of this item issued: Q stage may be refilled
-            if (exists) ptx::umma_commit(&q_empty[qs]); else ptx::mbar_arrive(&q_empty[qs]);
-          }
+          __syncwarp();
           if (exists) {
-            if (g == 0) TL_STAMP(2, iter);
+            if (g == 0) TL_STAMP_W(2, iter);
             ptx::mbar_wait(&p_ready[g], pc & 1); ++pc;
             ptx::tc_fence_after();
-            if (g == 0) TL_STAMP(3, iter);
+            if (g == 0) TL_STAMP_W(3, iter);
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < KVT / 16; ++k)   // P (packed bf16) sits at the start of each column half of S
-              ptx::umma_f16_ts(tmem + g * 256 + 192, tmem + g * 256 + (k < KVT / 32 ? k * 8 : KVT / 2 + (k - KVT / 32) * 8),
-                               ptx::make_smem_desc_sw128(sv + k * 2048, 16384, 1024), idesc_o, (t > 0 || k > 0) ? 1u : 0u);
-            ptx::umma_commit(&o_done[g]);
-            ptx::umma_commit(&kv_empty[ks]);
+              for (int k = 0; k < KVT / 16; ++k)   // P (packed bf16) sits at the start of each column half of S
+                ptx::umma_f16_ts(tmem + g * 256 + 192, tmem + g * 256 + (k < KVT / 32 ? k * 8 : KVT / 2 + (k - KVT / 32) * 8),
+                                 dv + k * kStepMN, idesc_o, (t > 0 || k > 0) ? 1u : 0u);
+              ptx::umma_commit(&o_done[g]);
+              ptx::umma_commit(&kv_empty[ks]);
+            }
           } else {
-            ptx::mbar_arrive(&kv_empty[ks]);
+            if (ptx::elect_one()) ptx::mbar_arrive(&kv_empty[ks]);
           }
+          __syncwarp();
         }
       }
     }
@@ -881,6 +894,367 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc<kTmemCols>(tmem); }
 }
 
+// ---------------------------------------------------------------------------------------------
+// backward, persistent + warp-specialised, for L <= 256 (every shipped geometry): one CTA owns a whole
+// (sample, head) at a time, so dQ, dK and dV are complete in TMEM and are written once as bf16 -- no
+// fp32 atomics, no accumulation buffer, no conversion pass.
+//
+//   warp 0      TMA producer: Q, dO (<= 2 tiles of 128 rows), K, V (64-row chunks) of the next item
+//   warp 1      MMA issuer
+//   warps 2-17  16 element-wise warps: TMEM lane quarter = warp % 4 (32 query rows), column slice = (warp-2)/4
+//   blocks      (key tile jt, query tile it), jt outer, processed as 64-key sub-blocks whose S / dP ping-pong
+//               between two TMEM buffers so the tensor cores run one sub-block ahead of the 16 warps.  Per block:
+//                 S = Q_it K_jt^T, dP = dO_it V_jt^T                     (tensor cores -> TMEM)
+//                 P = 2^(S c - lse), Pd = P keep/(1-p), dS = P (dP keep/(1-p) - delta)   (16 warps)
+//                   Pd, dS -> bf16, 128B-swizzled shared memory tiles [128 query rows][key columns]
+//                 dV_jt += Pd^T dO_it, dK_jt += dS^T Q_it, dQ_it += dS K_jt   (tensor cores; the staged tiles
+//                   serve as MN-major A for the first two and as K-major A for the third)
+//               after the last query tile of a key tile the element-wise warps drain dK_jt, dV_jt; after the last
+//               block they drain dQ.  The softmax scale is applied when dQ and dK are drained.
+//   TMEM        [S 64 | dP 64] x 2 buffers 0..255 | dV 256..319 | dK 320..383 | dQ_0 384..447 | dQ_1 448..511
+// ---------------------------------------------------------------------------------------------
+constexpr int kBwd2Threads = 64 + 16 * 32;
+struct Bwd2Smem {
+  static constexpr int kQ = 0;                    // [2][128 x 64]
+  static constexpr int kDO = 32768;               // [2][128 x 64]
+  static constexpr int kK = 65536;                // [4][64 x 64]
+  static constexpr int kV = 98304;                // [4][64 x 64]
+  static constexpr int kP = 131072;               // Pd : 2 blocks of [128 rows][64 keys]
+  static constexpr int kDS = 163840;              // dS
+  static constexpr int kOut = 196608;             // 16 warps x 2 KB drain transposes
+  static constexpr int kBar = 196608 + 32768;
+  static constexpr int kTotal = kBar + 128 + 1024;
+};
+
+// drain 32 TMEM columns of this warp's 32 lanes as bf16 (scaled) into out[row_base + lane][col0 .. col0+32),
+// rows limited to [row_lo, row_hi); the store is transposed through a warp-private 2 KB tile so that one warp
+// instruction covers 8 rows x 64 contiguous bytes
+__device__ __forceinline__ void drain32_bf16(uint32_t taddr, float mul, uint32_t st, __nv_bfloat16* out, long long ld,
+                                             long long row_base, int row_lo_rel, int row_hi_rel, int lane) {
+  uint32_t r[32];
+  ptx::tmem_ld_32x32(taddr, r);
+  ptx::tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = 8 * j;
+    sts128u(st + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4),
+            make_uint4(pack_bf16(__uint_as_float(r[i]) * mul, __uint_as_float(r[i + 1]) * mul),
+                       pack_bf16(__uint_as_float(r[i + 2]) * mul, __uint_as_float(r[i + 3]) * mul),
+                       pack_bf16(__uint_as_float(r[i + 4]) * mul, __uint_as_float(r[i + 5]) * mul),
+                       pack_bf16(__uint_as_float(r[i + 6]) * mul, __uint_as_float(r[i + 7]) * mul)));
+  }
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int rr = it * 8 + (lane >> 2), cj = lane & 3;
+    const uint4 v = lds128u(st + rr * 64 + ((cj ^ ((rr >> 1) & 3)) << 4));
+    if (rr >= row_lo_rel && rr < row_hi_rel) *reinterpret_cast<uint4*>(out + (row_base + rr) * ld + cj * 8) = v;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kBwd2Threads, 1)
+attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
+                 const __grid_constant__ CUtensorMap tmDO, const TcArgs a, int n_items, uint32_t magic_h) {
+  using SM = Bwd2Smem;
+  extern __shared__ uint8_t smem_raw3[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw3) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kBar);
+  uint64_t* in_full = bars; uint64_t* in_empty = bars + 1; uint64_t* s_full = bars + 2;   // s_full[2]
+  // sub_done[2], alternating per sub-block: S / dP of a sub-block are ready long before the slower warps finish the
+  // previous one, so with a single barrier a fast warp's arrival for sub-block u+1 would complete the phase of u
+  // early; with two, running two ahead is impossible (S / dP of u+2 are only produced after sub_done(u))
+  uint64_t* sub_done = bars + 4; uint64_t* stage_free = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = a.L, H = a.H;
+  const int n_t = (L + 127) / 128;                       // query tiles = key tiles (1 or 2)
+  const int n_last = (L - (n_t - 1) * 128 <= 64) ? 1 : 2;      // 64-key sub-blocks of the last key tile
+  const int kv_chunks = (n_t - 1) * 2 + n_last;          // 64-row chunks of K / V to fetch
+  // sub-block u of an item = (key tile jt, query tile it, 64-key half jh), jt outermost, jh innermost
+  const int subs_full = 2 * n_t;                         // sub-blocks in a full key tile
+  const int n_sub = (n_t - 1) * subs_full + n_last * n_t;
+  auto decode_sub = [&](int u, int& jt, int& it, int& jh, int& nh) {
+    if (u < (n_t - 1) * subs_full) { jt = 0; nh = 2; it = u >> 1; jh = u & 1; }     // (n_t <= 2: a full tile can only be jt 0)
+    else { const int v = u - (n_t - 1) * subs_full; jt = n_t - 1; nh = n_last; it = v / n_last; jh = v - it * n_last; }
+  };
+
+  if (tid == 0) {
+    ptx::prefetch_tensormap(&tmQKV128); ptx::prefetch_tensormap(&tmQKV64); ptx::prefetch_tensormap(&tmDO);
+    ptx::mbar_init(in_full, 1); ptx::mbar_init(in_empty, 1); ptx::mbar_init(&s_full[0], 1); ptx::mbar_init(&s_full[1], 1);
+    ptx::mbar_init(&sub_done[0], 16); ptx::mbar_init(&sub_done[1], 16); ptx::mbar_init(stage_free, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // S / dP of sub-block u live in buffer u & 1: S at 128 (u&1), dP at 128 (u&1) + 64
+  constexpr uint32_t kDVcol = 256, kDKcol = 320, kDQcol = 384;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int iter = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++iter) {
+        const int b = (int)__umulhi((uint32_t)item, magic_h), h = item - b * H;
+        mbar_wait_backoff(in_empty, (iter & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(in_full, n_t * 2 * 16384 + kv_chunks * 2 * 8192);
+        // in the order the first products need them
+        ptx::tma_load_2d(smem + SM::kQ, &tmQKV128, in_full, h * TDH, b * L);
+        for (int c = 0; c < kv_chunks; ++c) ptx::tma_load_2d(smem + SM::kK + c * 8192, &tmQKV64, in_full, (H + h) * TDH, b * L + c * 64);
+        ptx::tma_load_2d(smem + SM::kDO, &tmDO, in_full, h * TDH, b * L);
+        for (int c = 0; c < kv_chunks; ++c) ptx::tma_load_2d(smem + SM::kV + c * 8192, &tmQKV64, in_full, (2 * H + h) * TDH, b * L + c * 64);
+        if (n_t > 1) {
+          ptx::tma_load_2d(smem + SM::kQ + 16384, &tmQKV128, in_full, h * TDH, b * L + 128);
+          ptx::tma_load_2d(smem + SM::kDO + 16384, &tmDO, in_full, h * TDH, b * L + 128);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // The whole warp runs this loop converged and computes the (warp-uniform) descriptors; only the tcgen05
+    // instructions sit under the elected-lane predicate.  (With the arithmetic inside an `if (lane == 0)` ptxas
+    // wraps every UTCHMMA in an elect / R2UR.BROADCAST / branch loop: ~100 cycles per instruction.)
+    {
+      const uint32_t sQ = ptx::smem_u32(smem + SM::kQ), sDO = ptx::smem_u32(smem + SM::kDO);
+      const uint32_t sK = ptx::smem_u32(smem + SM::kK), sV = ptx::smem_u32(smem + SM::kV);
+      const uint32_t sP = ptx::smem_u32(smem + SM::kP), sDS = ptx::smem_u32(smem + SM::kDS);
+      constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, 64, 0, 0);    // S, dP of a 64-key sub-block
+      constexpr uint32_t idesc_kv = ptx::make_idesc_bf16(128, 64, 1, 1);   // dV, dK: A = Pd^T / dS^T (MN-major), B MN-major
+      constexpr uint32_t idesc_q = ptx::make_idesc_bf16(128, 64, 0, 1);    // dQ: A = dS (K-major), B = K (MN-major)
+      // k-step increments of the descriptor start-address field (bytes >> 4)
+      constexpr uint64_t kStepK = 32 >> 4, kStepMN = 2048 >> 4;
+      auto issue_sdp = [&](int u) {
+        int jt, it, jh, nh;
+        decode_sub(u, jt, it, jh, nh);
+        const uint32_t col = (uint32_t)(u & 1) * 128u;
+        const uint32_t kb = (uint32_t)(jt * 2 + jh) * 8192u;               // 64-row chunk of K / V
+        const uint64_t dq = ptx::make_smem_desc_sw128(sQ + it * 16384, 16, 1024), dk = ptx::make_smem_desc_sw128(sK + kb, 16, 1024);
+        const uint64_t dg = ptx::make_smem_desc_sw128(sDO + it * 16384, 16, 1024), dv = ptx::make_smem_desc_sw128(sV + kb, 16, 1024);
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) ptx::umma_f16(tmem + col, dq + kk * kStepK, dk + kk * kStepK, idesc_s, kk > 0);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) ptx::umma_f16(tmem + col + 64, dg + kk * kStepK, dv + kk * kStepK, idesc_s, kk > 0);
+          ptx::umma_commit(&s_full[u & 1]);
+        }
+        __syncwarp();
+      };
+      int iter = 0; uint32_t cu = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++iter) {
+        mbar_wait_backoff(in_full, iter & 1);
+        ptx::tc_fence_after();
+        issue_sdp(0);
+        if (n_sub > 1) issue_sdp(1);
+        for (int u = 0; u < n_sub; ++u, ++cu) {
+          int jt, it, jh, nh;
+          decode_sub(u, jt, it, jh, nh);
+          TL_STAMP_W(26, (int)cu);
+          ptx::mbar_wait(&sub_done[cu & 1], (cu >> 1) & 1);   // Pd, dS of sub-block u staged; its S / dP buffer is free again
+          ptx::tc_fence_after();
+          TL_STAMP_W(27, (int)cu);
+          // dQ_it[i,d] += sum_j dS[i,j] K[j,d]   (contraction over the 64 keys of this sub-block)
+          const uint64_t a_ds = ptx::make_smem_desc_sw128(sDS + jh * 16384, 16, 1024);
+          const uint64_t b_k = ptx::make_smem_desc_sw128(sK + (jt * 2 + jh) * 8192, 16384, 1024);
+          const uint64_t a_p = ptx::make_smem_desc_sw128(sP, 16384, 1024), b_do = ptx::make_smem_desc_sw128(sDO + it * 16384, 16384, 1024);
+          const uint64_t a_dst = ptx::make_smem_desc_sw128(sDS, 16384, 1024), b_q = ptx::make_smem_desc_sw128(sQ + it * 16384, 16384, 1024);
+          const uint32_t first_q = (jt > 0 || jh > 0) ? 1u : 0u, first_kv = it > 0 ? 1u : 0u;
+          const bool block_end = jh == nh - 1;
+          // the products that release the staging tiles go first, the S / dP two sub-blocks ahead last
+          if (ptx::elect_one()) {
+            if (block_end) {
+              // block (jt, it) complete: dV_jt[j,d] += sum_i Pd[i,j] dO[i,d] ; dK_jt[j,d] += sum_i dS[i,j] Q[i,d]
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk)
+                ptx::umma_f16(tmem + kDVcol, a_p + kk * kStepMN, b_do + kk * kStepMN, idesc_kv, kk > 0 ? 1u : first_kv);
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk)
+                ptx::umma_f16(tmem + kDKcol, a_dst + kk * kStepMN, b_q + kk * kStepMN, idesc_kv, kk > 0 ? 1u : first_kv);
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              ptx::umma_f16(tmem + kDQcol + it * 64, a_ds + kk * kStepK, b_k + kk * kStepMN, idesc_q, kk > 0 ? 1u : first_q);
+            if (block_end) ptx::umma_commit(stage_free);
+          }
+          __syncwarp();
+          if (u + 2 < n_sub) issue_sdp(u + 2);
+          TL_STAMP_W(28, (int)cu);
+        }
+        if (ptx::elect_one()) ptx::umma_commit(in_empty);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== element-wise warps =====================
+    const int quarter = warp & 3, slice = (warp - 2) >> 2;
+    const int lrow = quarter * 32 + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t sP = ptx::smem_u32(smem + SM::kP), sDS = ptx::smem_u32(smem + SM::kDS);
+    const uint32_t st_out = ptx::smem_u32(smem + SM::kOut) + (warp - 2) * 2048;
+    const uint32_t th16 = a.drop_thresh << 16;
+    const bool drop = a.drop_thresh != 0;
+    const float sl2 = a.scale_log2, ds = a.drop_scale;
+    const uint32_t ngrp = (uint32_t)((L + 7) >> 3);
+    __nv_bfloat16* dqkv = reinterpret_cast<__nv_bfloat16*>(a.dqkv);
+    const long long ld3 = 3ll * H * TDH;
+
+    // per-row scalars and allow bits of the next item are fetched one item ahead.  This thread's 16 key columns
+    // of sub-block (jt, jh) are keys jt*128 + jh*64 + slice*16 .. +15: bits (jh*64 + slice*16) & 31 .. of word
+    // 4 jt + 2 jh + slice/2 of its allow row; aw_nx[t][jt] holds them for jh = 0 (low half) and jh = 1 (high half)
+    float lse2_nx[2], dlt_nx[2];
+    uint32_t aw_nx[2][2];
+    auto fetch_rows = [&](int item_) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) { lse2_nx[t] = INFINITY; dlt_nx[t] = 0.f; aw_nx[t][0] = aw_nx[t][1] = 0u; }
+      if (item_ >= n_items) return;
+      const int b_ = (int)__umulhi((uint32_t)item_, magic_h), h_ = item_ - b_ * H;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int i = t * 128 + lrow;
+        if (t < n_t && i < L) {
+          lse2_nx[t] = __ldg(a.lse + ((size_t)b_ * H + h_) * L + i) * kLog2e;
+          dlt_nx[t] = __ldg(a.delta + ((size_t)b_ * H + h_) * L + i);
+          const uint32_t* ar = a.allow + (((size_t)b_ * a.Hm + (a.Hm == 1 ? 0 : h_)) * L + i) * a.W;
+#pragma unroll
+          for (int jt = 0; jt < 2; ++jt) {
+            if (jt >= n_t) continue;
+            uint32_t lo = 0u, hi = 0u;
+            const int w0 = 4 * jt + (slice >> 1), w1 = w0 + 2, sh = (slice & 1) * 16;
+            if (w0 < a.W) lo = (__ldg(ar + w0) >> sh) & 0xffffu;
+            if (w1 < a.W) hi = (__ldg(ar + w1) >> sh) & 0xffffu;
+            aw_nx[t][jt] = lo | (hi << 16);
+          }
+        }
+      }
+    };
+    fetch_rows(blockIdx.x);
+    uint32_t cs0 = 0, cs1 = 0, cf = 0, cg = 0;     // s_full[0/1], stage_free completion counters; sub-blocks done
+    int iter = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++iter) {
+      const int b = (int)__umulhi((uint32_t)item, magic_h), h = item - b * H;
+      float lse2[2], dlt[2];
+      uint32_t aw[2][2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) { lse2[t] = lse2_nx[t]; dlt[t] = dlt_nx[t]; aw[t][0] = aw_nx[t][0]; aw[t][1] = aw_nx[t][1]; }
+      fetch_rows(item + gridDim.x);
+      const uint64_t drow_b = (uint64_t)(b * H + h) * L;
+      for (int u = 0; u < n_sub; ++u) {
+        int jt, it, jh, nh;
+        decode_sub(u, jt, it, jh, nh);
+        const int i = it * 128 + lrow;
+        const bool active = i < L;
+        const bool warp_active = it * 128 + quarter * 32 < L;
+        const float my_lse2 = it ? lse2[1] : lse2[0], my_dlt = it ? dlt[1] : dlt[0];
+        const uint32_t my_aw = it ? (jt ? aw[1][1] : aw[1][0]) : (jt ? aw[0][1] : aw[0][0]);
+        const uint32_t awc = active ? ((my_aw >> (16 * jh)) & 0xffffu) : 0u;
+        const int col0 = jt * 128 + jh * 64 + slice * 16;      // first key of this thread's 16 columns
+        const uint64_t grp_base = (drow_b + (uint64_t)i) * ngrp + (uint64_t)(col0 >> 3);
+        if (warp == 2 && lane == 0) TL_STAMP(20, (int)(cs0 + cs1));
+        if (u & 1) { ptx::mbar_wait(&s_full[1], cs1 & 1); ++cs1; } else { ptx::mbar_wait(&s_full[0], cs0 & 1); ++cs0; }
+        ptx::tc_fence_after();
+        if (warp == 2 && lane == 0) TL_STAMP(21, (int)(cs0 + cs1) - 1);
+        uint32_t pk[8], dk_[8];                               // packed Pd / dS of the 16 columns
+        if (warp_active) {
+          uint32_t rs[16], rd[16];
+          const uint32_t tcol = t_lane + (uint32_t)(u & 1) * 128u + slice * 16;
+          ptx::tmem_ld_32x16(tcol, rs);
+          ptx::tmem_ld_32x16(tcol + 64, rd);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            float e[8], uu[8], kf[8];
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {
+              const float arg = fmaf(__uint_as_float(rs[8 * q + x]), sl2, -my_lse2);
+              e[x] = ((awc >> (8 * q + x)) & 1u) ? fast_exp2(arg) : 0.f;
+            }
+            if (drop) {
+              const uint4 rnd = philox4x32(a.seed, grp_base + (uint64_t)q, (uint32_t)a.off);
+              kf[0] = (rnd.x << 16) >= th16 ? ds : 0.f;
+              kf[1] = rnd.x >= th16 ? ds : 0.f;
+              kf[2] = (rnd.y << 16) >= th16 ? ds : 0.f;
+              kf[3] = rnd.y >= th16 ? ds : 0.f;
+              kf[4] = (rnd.z << 16) >= th16 ? ds : 0.f;
+              kf[5] = rnd.z >= th16 ? ds : 0.f;
+              kf[6] = (rnd.w << 16) >= th16 ? ds : 0.f;
+              kf[7] = rnd.w >= th16 ? ds : 0.f;
+            } else {
+#pragma unroll
+              for (int x = 0; x < 8; ++x) kf[x] = 1.f;
+            }
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {
+              uu[x] = e[x] * fmaf(__uint_as_float(rd[8 * q + x]), kf[x], -my_dlt);   // dS / scale
+              e[x] *= kf[x];                                                            // Pd
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+              pk[4 * q + x] = pack_bf16(e[2 * x], e[2 * x + 1]);
+              dk_[4 * q + x] = pack_bf16(uu[2 * x], uu[2 * x + 1]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int x = 0; x < 8; ++x) { pk[x] = 0u; dk_[x] = 0u; }
+        }
+        // the staging tiles of the previous block are free once its gradient MMAs have retired
+        if (warp == 2 && lane == 0) TL_STAMP(22, (int)(cs0 + cs1) - 1);
+        if (jh == 0 && cf > 0) ptx::mbar_wait(stage_free, (cf - 1) & 1);
+        if (warp == 2 && lane == 0) TL_STAMP(23, (int)(cs0 + cs1) - 1);
+        {
+          // row lrow, key columns jh*64 + slice*16 .. +15 of the [128 rows][2 x 64 keys] 128B-swizzled tile pair
+          const uint32_t base = (uint32_t)jh * 16384u + (uint32_t)lrow * 128u;
+          const int ch = slice * 2;                           // 16-byte chunk index within the 128-byte row
+          sts128u(sP + base + (((ch) ^ (lrow & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+          sts128u(sP + base + (((ch + 1) ^ (lrow & 7)) << 4), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+          sts128u(sDS + base + (((ch) ^ (lrow & 7)) << 4), make_uint4(dk_[0], dk_[1], dk_[2], dk_[3]));
+          sts128u(sDS + base + (((ch + 1) ^ (lrow & 7)) << 4), make_uint4(dk_[4], dk_[5], dk_[6], dk_[7]));
+        }
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&sub_done[cg & 1]);
+        ++cg;
+        if (warp == 2 && lane == 0) TL_STAMP(24, (int)(cs0 + cs1) - 1);
+        if (jh == nh - 1) {
+          ++cf;                                               // one stage_free completion per block
+          if (it == n_t - 1) {
+            // ---- key tile finished: drain dK_jt (scaled) and dV_jt.  slices 0,1 -> dK halves, slices 2,3 -> dV halves
+            ptx::mbar_wait(stage_free, (cf - 1) & 1);
+            ptx::tc_fence_after();
+            const int j0 = jt * 128 + quarter * 32;
+            if (j0 < L) {
+              const bool is_k = slice < 2;
+              const int hc = (slice & 1) * 32;
+              drain32_bf16(t_lane + (is_k ? kDKcol : kDVcol) + hc, is_k ? a.scale : 1.f, st_out,
+                           dqkv + (size_t)((is_k ? H : 2 * H) + h) * TDH + hc, ld3, (long long)b * L + j0, 0, min(32, L - j0), lane);
+            }
+            ptx::tc_fence_before();
+            if (warp == 2 && lane == 0) TL_STAMP(25, (int)(cs0 + cs1) - 1);
+          }
+        }
+      }
+      // ---- item finished: drain dQ (scaled).  slices 0,1 -> query tile 0 halves, slices 2,3 -> query tile 1
+      {
+        ptx::tc_fence_after();
+        const int t = slice >> 1, hc = (slice & 1) * 32;
+        const int i0 = t * 128 + quarter * 32;
+        if (t < n_t && i0 < L)
+          drain32_bf16(t_lane + kDQcol + t * 64 + hc, a.scale, st_out, dqkv + (size_t)h * TDH + hc, ld3, (long long)b * L + i0, 0,
+                       min(32, L - i0), lane);
+        ptx::tc_fence_before();
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc<512>(tmem); }
+}
+
 // dq_accum fp32 [rows, H*64] -> bf16 q-part of dqkv [rows, 3*H*64]
 __global__ void attn_dq_store_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, size_t rows, int hd) {
   const size_t n4 = rows * (size_t)(hd / 4);
@@ -981,12 +1355,21 @@ int attn_tc_fwd(const samk_attn_params* p, cudaStream_t stream) {
   return launch_fwd<128>(p, a, stream);
 }
 
+static int attn_bwd_version() {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("SAMK_ATTN_BWD_V");
+    v = (s && s[0] == '1') ? 1 : 2;
+  }
+  return v;
+}
+
 int attn_tc_bwd(const samk_attn_params* p, cudaStream_t stream) {
   TcArgs a;
   int rc = fill_tc(a, p);
   if (rc) return rc;
-  if (!p->qkv || !p->ctx || !p->lse || !p->dctx || !p->dqkv || !p->delta || !p->dq_accum) {
-    set_error("samk_attn_bwd: null pointer (tensor-core path also needs dq_accum)");
+  if (!p->qkv || !p->ctx || !p->lse || !p->dctx || !p->dqkv || !p->delta) {
+    set_error("samk_attn_bwd: null pointer");
     return SAMK_ERR_ARG;
   }
   if (!a.B || !a.L) return SAMK_OK;
@@ -995,13 +1378,31 @@ int attn_tc_bwd(const samk_attn_params* p, cudaStream_t stream) {
   attn_delta_kernel<<<(unsigned)((rows * a.H + 255) / 256), 256, 0, stream>>>(
       (const __nv_bfloat16*)p->dctx, (const __nv_bfloat16*)p->ctx, p->delta, a.B, a.H, a.L);
   if ((rc = check_launch("samk_attn_bwd(delta)"))) return rc;
+  CUtensorMap tqkv, tdo;
+  if ((rc = make_tmap_bf16_2d(&tqkv, p->qkv, rows, 3 * hd, 3 * hd, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tdo, p->dctx, rows, hd, hd, 64, 128))) return rc;
+
+  if (a.L <= 256 && attn_bwd_version() == 2) {
+    // whole (sample, head) per CTA: dQ, dK, dV complete in TMEM, written once
+    CUtensorMap tqkv64;
+    if ((rc = make_tmap_bf16_2d(&tqkv64, p->qkv, rows, 3 * hd, 3 * hd, 64, 64))) return rc;
+    if ((rc = set_smem(attn_bwd2_kernel, Bwd2Smem::kTotal))) return rc;
+    const long long n_items = (long long)a.B * a.H;
+    if (n_items >= (1ll << 24)) { set_error("samk_attn_bwd: too many work items"); return SAMK_ERR_UNSUPPORTED; }
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    const int grid = (int)(n_items < sms ? n_items : sms);
+    const uint32_t magic_h = (uint32_t)(((1ull << 32) + a.H - 1) / a.H);
+    attn_bwd2_kernel<<<grid, kBwd2Threads, Bwd2Smem::kTotal, stream>>>(tqkv, tqkv64, tdo, a, (int)n_items, magic_h);
+    return check_launch("samk_attn_bwd(tc v2)");
+  }
+
+  // long sequences: key-tile CTAs streaming query tiles, dQ reduced with fp32 atomics
+  if (!p->dq_accum) { set_error("samk_attn_bwd: L > 256 needs dq_accum"); return SAMK_ERR_ARG; }
   if (cudaMemsetAsync(p->dq_accum, 0, (size_t)rows * hd * sizeof(float), stream) != cudaSuccess) {
     set_error("samk_attn_bwd: memset failed");
     return SAMK_ERR_CUDA;
   }
-  CUtensorMap tqkv, tdo;
-  if ((rc = make_tmap_bf16_2d(&tqkv, p->qkv, rows, 3 * hd, 3 * hd, 64, 128))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tdo, p->dctx, rows, hd, hd, 64, 128))) return rc;
   constexpr int smem = 4 * 16384 + 2 * 32768 + 1024 + 64;
   if ((rc = set_smem(attn_bwd_tc_kernel, smem))) return rc;
   dim3 grid((a.L + 127) / 128, a.H, a.B);

@@ -450,20 +450,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        if (lane == 0) {
+        // descriptors are computed by the whole (converged) warp so that they live in uniform registers; only
+        // the tcgen05 instructions themselves sit under the elected-lane predicate (an `if (lane == 0)` around
+        // the arithmetic makes ptxas wrap every UTCHMMA in an elect / R2UR.BROADCAST / branch loop, ~150 cycles)
+        {
           const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t adesc0 = A_MN ? ptx::make_smem_desc_sw128(sa, BK * 128, 1024) : ptx::make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc0 = B_MN ? ptx::make_smem_desc_sw128(sb, BK * 128, 1024) : ptx::make_smem_desc_sw128(sb, 16, 1024);
+          const bool leader = ptx::elect_one();
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adesc = A_MN ? ptx::make_smem_desc_sw128(sa + k * 2048, BK * 128, 1024)
-                                        : ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t bdesc = B_MN ? ptx::make_smem_desc_sw128(sb + k * 2048, BK * 128, 1024)
-                                        : ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            ptx::umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            // advancing the start-address field (bytes >> 4) cannot carry out of its 14 bits for shared memory
+            const uint64_t adesc = adesc0 + (uint64_t)(A_MN ? k * (2048 >> 4) : k * (32 >> 4));
+            const uint64_t bdesc = bdesc0 + (uint64_t)(B_MN ? k * (2048 >> 4) : k * (32 >> 4));
+            if (leader) ptx::umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          if (CL == 1) ptx::umma_commit(&empty_bar[stage]);      // smem slot free once these MMAs retire
-          else ptx::umma_commit_mcast(&empty_bar[stage], kMcastMask);   // ... in every CTA that multicasts into it
-          if (kb == kb1 - 1) ptx::umma_commit(&tfull_bar[acc]);  // accumulator ready
+          if (leader) {
+            if (CL == 1) ptx::umma_commit(&empty_bar[stage]);      // smem slot free once these MMAs retire
+            else ptx::umma_commit_mcast(&empty_bar[stage], kMcastMask);   // ... in every CTA that multicasts into it
+            if (kb == kb1 - 1) ptx::umma_commit(&tfull_bar[acc]);  // accumulator ready
+          }
         }
         __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }

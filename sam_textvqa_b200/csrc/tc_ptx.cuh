@@ -11,7 +11,11 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of the (fully converged) warp.  The __syncwarp() matters: callers typically arrive here from a
+// per-lane mbarrier spin loop, and elect.sync executed by a partially converged warp elects one leader per
+// fragment, i.e. the guarded tcgen05 instructions would be issued more than once.
 __device__ __forceinline__ bool elect_one() {
+  __syncwarp();
   uint32_t pred = 0;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"

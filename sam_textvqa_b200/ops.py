@@ -491,13 +491,14 @@ def attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p
     if uses_tensor_core_attention(qkv.dtype):
         if allow is None:
             allow = build_attn_mask(valid, rel, dims, spatial, quad_mask)
-        dq_accum = torch.empty(B * L, H * 64, dtype=torch.float32, device=qkv.device)
+        if L > 256:      # long sequences: key-tile CTAs reduce dQ through an fp32 buffer
+            dq_accum = torch.empty(B * L, H * 64, dtype=torch.float32, device=qkv.device)
     dqkv = torch.empty_like(qkv)
     delta = torch.empty_like(lse)
     ap = _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, dctx, dqkv, delta,
                       allow=allow, dq_accum=dq_accum)
     check(lib().samk_attn_bwd(ctypes.byref(ap), _ATTN_IMPL, stream_ptr()), "attn_bwd")
-    _count(4 if dq_accum is not None else 2)
+    _count(4 if dq_accum is not None else 2)     # delta (+ memset) + main kernel (+ dq conversion)
     return dqkv
 
 

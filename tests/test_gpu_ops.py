@@ -257,7 +257,11 @@ def test_embeddings_prevpred_pointer_and_loss_vs_torch(ops):
 
 @pytest.mark.parametrize("case", [(2, 20, 150, 12, True, 0.0), (2, 20, 150, 12, False, 0.0), (3, 20, 0, 0, False, 0.0),
                                   (2, 20, 86, 12, True, 0.1), (2, 20, 200, 12, True, 0.0), (1, 20, 442, 12, False, 0.1),
-                                  (1, 20, 1004, 12, True, 0.0)])
+                                  (1, 20, 1004, 12, True, 0.0),
+                                  # more (sample, head) items than SMs: every persistent CTA walks several items
+                                  (40, 20, 150, 12, True, 0.1), (64, 20, 0, 0, False, 0.1), (30, 20, 86, 12, False, 0.0),
+                                  (28, 20, 200, 12, True, 0.1), (2, 20, 150, 12, True, 0.1), (40, 20, 150, 12, True, 0.0),
+                                  (40, 20, 150, 12, False, 0.0), (13, 20, 150, 12, False, 0.0)])
 def test_tcgen05_attention_matches_exact_fp32_kernel(ops, case):
     """bf16 tensor-core attention (fwd + bwd, masks, dead rows, dropout, multi-tile online softmax up to
     L=1036) against the exact-fp32 SIMT kernel on the same bf16-representable inputs and Philox masks."""

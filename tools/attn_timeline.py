@@ -14,8 +14,12 @@ valid = torch.ones(B, L, dtype=torch.uint8, device=dev); valid[:, -D:] = 0
 dims = (B, L, H, T, A, D)
 allow = ops.build_attn_mask(valid, None, dims, False, 0)
 p = float(os.environ.get("P", "0.1"))
+bwd = os.environ.get("BWD", "0") == "1"
+w = torch.randn(B * L, d, device=dev).bfloat16()
 for _ in range(3):
-    ops.attention_fwd(qkv, valid, None, dims, False, 0, p, (1, 1), allow)
+    ctx, lse = ops.attention_fwd(qkv, valid, None, dims, False, 0, p, (1, 1), allow)
+    if bwd:
+        ops.attention_bwd(w, qkv, ctx, lse, valid, None, dims, False, 0, p, (1, 1), allow)
 torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 4096)()
 lib = _lib.lib()
@@ -24,6 +28,13 @@ assert lib.samk_debug_timeline(buf, 4096) == 0
 tl = np.array(buf[:]).reshape(64, 64)
 names = {0: "mma:top", 1: "mma:kv_full", 2: "mma:S issued", 3: "mma:p_ready", 8: "sm:top", 9: "sm:s_full", 10: "sm:pass1 done",
          11: "sm:max xchg", 12: "sm:P arrived", 13: "sm:l xchg", 14: "sm:o_done", 15: "sm:epilogue end"}
-t0 = tl[8, 0]
-for it in range(10):
-    print("item %d: " % it + "  ".join("%s=%d" % (names[s], tl[s, it] - t0) for s in sorted(names)))
+if bwd:
+    names = {20: "ew:top", 21: "ew:s_full", 22: "ew:computed", 23: "ew:stage_free", 24: "ew:arrived", 25: "ew:drained",
+             26: "mma:top", 27: "mma:blk_done", 28: "mma:issued"}
+    t0 = tl[20, 0]
+    for it in range(12):
+        print("block %d: " % it + "  ".join("%s=%d" % (names[s], tl[s, it] - t0) for s in sorted(names)))
+else:
+    t0 = tl[8, 0]
+    for it in range(10):
+        print("item %d: " % it + "  ".join("%s=%d" % (names[s], tl[s, it] - t0) for s in sorted(names)))
