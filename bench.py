@@ -168,6 +168,12 @@ def run_samk(args):
     torch.manual_seed(0)
     model = SAM4C(BertConfig.from_dict(mmt), BertConfig.from_dict(tb)).to(dev).train()
     grads = dp.FlatGradBuffer(model.parameters())
+    # SAMK_DP_OVERLAP=1: bucketed NCCL all-reduce on a side stream under the backward pass.  Measured at N=2 it does
+    # not pay (13.97 vs 13.85 ms/step): NCCL's CTAs displace CTAs of the persistent 148-CTA GEMMs, which then run a
+    # second partial wave.  Default: one all-reduce of the flat buffer after backward (~0.9 ms exposed).
+    overlap = world > 1 and os.environ.get("SAMK_DP_OVERLAP", "0") == "1"
+    if overlap:
+        grads.enable_overlap()
     B = args.batch
 
     def graph_fn(boxes):
@@ -185,12 +191,16 @@ def run_samk(args):
 
     def step(inputs, adj_dev):
         grads.zero()
+        if overlap:
+            grads.begin_step()
         bd = dict(inputs)
         bd["spatial_adj_matrices"] = {"3": adj_dev}
         scores = model(bd)["textvqa_scores"]
         loss = ops.bce_with_mask_loss(scores, inputs["targets"], inputs["train_loss_mask"])
         loss.backward()
-        if world > 1:
+        if overlap:
+            grads.finish_step()
+        elif world > 1:
             grads.all_reduce()
         return loss
 
@@ -279,15 +289,31 @@ def run_samk(args):
 
     # ---- roofline of the dominant kernel family (tcgen05 GEMM), instrumented extra steps ----
     ops.gemm_profile = []
+    ops.attn_profile = []
     for _ in range(2):
         step(resident, resident_adj)
     torch.cuda.synchronize()
     prof, ops.gemm_profile = ops.gemm_profile, None
+    aprof, ops.attn_profile = ops.attn_profile, None
     g_ms = sum(s.elapsed_time(e) for s, e, _ in prof) / 2
     g_flop = sum(f for _, _, f in prof) / 2
     n_gemm = len(prof) // 2
     peak_tf, peak_gbs, peak_src = peaks()
     achieved = g_flop / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    # the north-star kernel: fused masked attention of the MMT layers (L = 182), HBM-bound at this length
+    Lm = CFG["T"] + CFG["O"] + CFG["R"] + CFG["D"]
+    attention = {}
+    for kind in ("fwd", "bwd"):
+        rows = [(s.elapsed_time(e), nb, fl) for k, L_, s, e, nb, fl in aprof if k == kind and L_ == Lm]
+        if rows:
+            ms_k = sum(r[0] for r in rows) / len(rows)
+            attention[kind] = {"us_per_launch": ms_k * 1e3, "launches_per_step": len(rows) // 2,
+                               "algorithmic_MB": rows[0][1] / 1e6, "achieved_GBs": rows[0][1] / (ms_k * 1e-3) / 1e9,
+                               "hbm_frac": rows[0][1] / (ms_k * 1e-3) / 1e9 / peak_gbs,
+                               "dense_equiv_TFLOPs": rows[0][2] / (ms_k * 1e-3) / 1e12}
+    attention["peak_GBs"] = peak_gbs
+    attention["ncu"] = ("profiles/r01g_ncu_summary.txt: fwd 91 us, DRAM 108+14 MB per launch, tensor pipe 10.9 %; "
+                        "bwd 176 us, DRAM 153+73 MB, tensor pipe 15.5 % (L=182 is HBM/ALU-bound, SURVEY 8d)")
 
     if rank != 0:
         if world > 1:
@@ -310,7 +336,10 @@ def run_samk(args):
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                      "traffic": None, "peak_source": peak_src + " (sustained bf16)",
                      "gemm_ms_per_step": g_ms, "gemm_share_of_step": g_ms / ms if ms > 0 else None,
-                     "step_flop_frac_of_peak": value / world * FLOP_PER_SAMPLE / (peak_tf * 1e12)},
+                     "step_flop_frac_of_peak": value / world * FLOP_PER_SAMPLE / (peak_tf * 1e12),
+                     "traffic_note": "per-shape DRAM bytes from ncu --set full are in profiles/r01g_ncu_summary.txt "
+                                     "(e.g. FFN2 wgrad 337+10 MB vs 322 MB algorithmic)"},
+        "attention": attention,
     }
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

@@ -40,6 +40,108 @@ class FlatGradBuffer(object):
                 p.grad = self.flat[off:off + n].view_as(p)
             off += n
 
+    # ---- overlapped exchange -------------------------------------------------------------------------
+    # The kernels accumulate straight into the flat buffer, so autograd never sees parameter gradients and
+    # parameter hooks do not fire; instead every backward op of `ops` reports the parameters it has just
+    # finished (`ops.grad_ready_hook`).  A parameter fed by several ops (classifier.weight: output head and
+    # PrevPredEmbeddings) is ready after its last report; the number of reports per parameter is learned in
+    # the first step.  Maximal runs of ready, not yet reduced parameters are all-reduced on a side stream as
+    # soon as they reach `bucket_bytes`, so the NVLink exchange runs under the rest of the backward pass.
+    def enable_overlap(self, group=None, average=True, bucket_bytes=48 << 20):
+        from . import ops
+        self._ov = {"group": group, "average": average, "bucket": int(bucket_bytes), "expected": None,
+                    "seen": {}, "stream": None, "works": []}
+        self._index = {id(p): i for i, p in enumerate(self.params)}
+        offs, off = [], 0
+        for p in self.params:
+            offs.append(off)
+            off += p.numel()
+        self._offs = offs + [off]
+        ops.grad_ready_hook = self._notify
+
+    def begin_step(self):
+        ov = self._ov
+        if ov["expected"] is None:
+            ov["seen"] = {}
+        else:
+            ov["left"] = list(ov["expected"])
+            ov["ready"] = [False] * len(self.params)
+            ov["sent"] = [False] * len(self.params)
+        ov["works"] = []
+
+    def _notify(self, params):
+        ov = getattr(self, "_ov", None)
+        if ov is None:
+            return
+        if ov["expected"] is None:                     # learning step
+            for p in params:
+                i = self._index.get(id(p))
+                if i is not None:
+                    ov["seen"][i] = ov["seen"].get(i, 0) + 1
+            return
+        changed = False
+        for p in params:
+            i = self._index.get(id(p))
+            if i is None or ov["ready"][i]:
+                continue
+            ov["left"][i] -= 1
+            if ov["left"][i] <= 0:
+                ov["ready"][i] = True
+                changed = True
+        if changed:
+            self._flush(final=False)
+
+    def _flush(self, final):
+        ov = self._ov
+        n = len(self.params)
+        i = 0
+        while i < n:
+            if ov["sent"][i] or not (ov["ready"][i] or final):
+                i += 1
+                continue
+            j = i
+            while j < n and not ov["sent"][j] and (ov["ready"][j] or final):
+                j += 1
+            lo, hi = self._offs[i], self._offs[j]
+            if final or (hi - lo) * 4 >= ov["bucket"]:
+                self._launch(lo, hi)
+                for k in range(i, j):
+                    ov["sent"][k] = True
+            i = j
+
+    def _launch(self, lo, hi):
+        ov = self._ov
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(ov["group"]) == 1:
+            return
+        view = self.flat[lo:hi]
+        if view.is_cuda:
+            if ov["stream"] is None:
+                ov["stream"] = torch.cuda.Stream()
+            ev = torch.cuda.Event()
+            ev.record()                                  # everything enqueued so far produced this slice
+            with torch.cuda.stream(ov["stream"]):
+                ov["stream"].wait_event(ev)
+                if ov["average"]:
+                    view.div_(dist.get_world_size(ov["group"]))
+                ov["works"].append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=ov["group"], async_op=True))
+        else:
+            if ov["average"]:
+                view.div_(dist.get_world_size(ov["group"]))
+            ov["works"].append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=ov["group"], async_op=True))
+
+    def finish_step(self):
+        """Call after backward(): exchanges whatever is left and makes the current stream wait for all of it."""
+        ov = self._ov
+        if ov["expected"] is None:                     # learning step: one plain all-reduce
+            ov["expected"] = [ov["seen"].get(i, 0) for i in range(len(self.params))]
+            self.all_reduce(group=ov["group"], average=ov["average"])
+            return
+        self._flush(final=True)
+        for w in ov["works"]:
+            w.wait()
+        if ov["stream"] is not None:
+            torch.cuda.current_stream().wait_stream(ov["stream"])
+
     def all_reduce(self, group=None, average=True, async_op=False):
         """Sum (or average) gradients over the data-parallel group with one collective."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:

@@ -25,6 +25,8 @@ _GEMM_IMPL = int(os.environ.get("SAMK_GEMM_IMPL", "0"))
 _ATTN_IMPL = int(os.environ.get("SAMK_ATTN_IMPL", "0"))
 launch_count = 0  # kernels launched through this module (bench.py reports it)
 gemm_profile = None  # bench.py: list collecting (start_event, end_event, algorithmic_flops) per GEMM launch
+grad_ready_hook = None  # dp.FlatGradBuffer.enable_overlap: called with the parameters a backward op has just finished
+attn_profile = None  # bench.py: list collecting (kind, L, start_event, end_event, algorithmic_bytes, dense_flops) per launch
 
 
 def set_precision(mode):
@@ -78,6 +80,11 @@ def _gbuf(p):
 
 def _ret(buf_direct):
     return None if buf_direct[1] else buf_direct[0]
+
+
+def _grads_done(*params):
+    if grad_ready_hook is not None:
+        grad_ready_hook([p for p in params if p is not None])
 
 
 _ln_ws = {}
@@ -283,6 +290,7 @@ class LinearFn(torch.autograd.Function):
         dW, db = _gbuf(weight), _gbuf(ctx_bias)
         gemm(dy_mn, True, x_mn, True, N, K, M, dW[0][:, :K], accumulate=True)
         colsum_into(dy, db[0])
+        _grads_done(weight, ctx_bias)
         return dx, _ret(dW), _ret(db), None
 
 
@@ -311,6 +319,7 @@ class LayerNormFn(torch.autograd.Function):
         dx = torch.empty_like(x2d)
         dg, db = _gbuf(gamma), _gbuf(ctx.beta_ref)
         _ln_bwd(dy, x2d, gamma, ctx.eps, dx, None, 0.0, (0, 0), dg[0], db[0], None, x2d.shape[0], x2d.shape[1])
+        _grads_done(gamma, ctx.beta_ref)
         return dx, _ret(dg), _ret(db), None
 
 
@@ -429,6 +438,7 @@ class PrevPredFn(torch.autograd.Function):
                                       ctx.eps, g10, B, D, V, R, d, ctx.p, ctx.drop[0], ctx.drop[1], stream_ptr()),
               "prevpred_bwd")
         _count()
+        _grads_done(*[t for t in (cls_w, ocr_in, pos, type_, ag, ab, og, ob, eg, eb) if t.is_leaf])
         return (None,) + tuple(_ret(g) for g in gs) + (None, None)
 
 
@@ -480,7 +490,15 @@ def attention_fwd(qkv, valid, rel, dims, spatial, quad_mask, p, drop, allow=None
     lse = torch.empty(B, H, L, dtype=torch.float32, device=qkv.device)
     ap = _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, allow=allow)
     ap.q_begin = int(q_begin)
+    if attn_profile is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     check(lib().samk_attn_fwd(ctypes.byref(ap), _ATTN_IMPL, stream_ptr()), "attn_fwd")
+    if attn_profile is not None:
+        ev1.record()
+        # Q+K+V+O bf16, allow bits, LSE; dense-equivalent 4 L^2 d FLOP
+        mask_b = B * (H if spatial else 1) * L * ((L + 31) // 32) * 4
+        attn_profile.append(("fwd", L, ev0, ev1, B * (4 * L * H * 64 * 2 + H * L * 4) + mask_b, 4.0 * B * L * L * H * 64))
     _count()
     return ctx_t, lse
 
@@ -497,7 +515,15 @@ def attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p
     delta = torch.empty_like(lse)
     ap = _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, dctx, dqkv, delta,
                       allow=allow, dq_accum=dq_accum)
+    if attn_profile is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     check(lib().samk_attn_bwd(ctypes.byref(ap), _ATTN_IMPL, stream_ptr()), "attn_bwd")
+    if attn_profile is not None:
+        ev1.record()
+        # Q,K,V,O,dO read + dQ,dK,dV written (bf16), allow bits, LSE + delta; 10 L^2 d FLOP
+        mask_b = B * (H if spatial else 1) * L * ((L + 31) // 32) * 4
+        attn_profile.append(("bwd", L, ev0, ev1, B * (8 * L * H * 64 * 2 + 2 * H * L * 4) + mask_b, 10.0 * B * L * L * H * 64))
     _count(4 if dq_accum is not None else 2)     # delta (+ memset) + main kernel (+ dq conversion)
     return dqkv
 
@@ -605,6 +631,7 @@ class BertLayerFn(torch.autograd.Function):
             sl = dqkv[:, part * d:(part + 1) * d]
             colsum_into(sl, Gb)
             gemm(operand(sl, "a", True), True, x_mn, True, d, d, M, Gw, accumulate=True)
+        _grads_done(*P)
         return (dx.view(B, L, d), None, None, None) + tuple(_ret(x) for x in G)
 
 
@@ -718,6 +745,7 @@ class OutputFn(torch.autograd.Function):
         gemm(operand(dk_a, "a", False), False, weight_operand([kw], True), True, B * R, d, dq, docr)
         gemm(operand(dk_a, "a", True), True, ocr_mn, True, dq, d, B * R, Gkw, accumulate=True)
         colsum_into(dk_, Gkb)
+        _grads_done(cw, cb, qw, qb, kw, kb)
         return (ddec2.view(B, D, d), docr.view(B, R, d), None) + tuple(_ret(x) for x in G)
 
 

@@ -126,7 +126,24 @@ def _dp_worker(rank, world, port, q):
     model.zero_grad(set_to_none=True)
     buf.zero()                                    # re-attaches the views
     ((model(batch["x"]) - batch["y"]) ** 2).mean().backward()
-    q.put((rank, float((got - buf.flat).abs().max()), dp.global_loss_scale(torch.tensor(float(rank + 1)))))
+    full = buf.flat.clone()
+    # overlapped, bucketed exchange: step 1 learns how often each parameter is reported (weight of layer 2 twice,
+    # like the classifier weight shared with PrevPredEmbeddings), later steps reduce ready runs early
+    from sam_textvqa_b200 import ops
+    buf.enable_overlap(average=True, bucket_bytes=256)
+    params = list(model.parameters())
+    errs = []
+    for _ in range(3):
+        buf.zero()
+        buf.begin_step()
+        ((model(shard["x"]) - shard["y"]) ** 2).mean().backward()
+        for p in reversed(params):                 # what the backward ops of `ops` report as they finish
+            ops.grad_ready_hook([p])
+        ops.grad_ready_hook([params[2]])
+        buf.finish_step()
+        errs.append(float((buf.flat - full).abs().max()))
+    ops.grad_ready_hook = None
+    q.put((rank, max(float((got - full).abs().max()), max(errs)), dp.global_loss_scale(torch.tensor(float(rank + 1)))))
     dist.destroy_process_group()
 
 

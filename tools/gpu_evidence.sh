@@ -27,13 +27,13 @@ launches)
   head -30 $OUT/${TAG}_launches_summary.txt; gzip -f $OUT/${TAG}_launches.csv ;;
 ncu)
   FULL="$NCU --set full --import-source on"
-  for shape in ffn1_fwd ffn2_fwd ffn2_wgrad ffn1_dgrad; do
+  for shape in ffn1_fwd ffn2_fwd ffn2_wgrad ffn2_dgrad qkv_fwd; do
     REPS=1 timeout 300 $FULL -k regex:gemm_tc_kernel -s 3 -c 1 -f -o $OUT/${TAG}_ncu_gemm_$shape \
         python tools/gemm_bench.py $shape > $OUT/${TAG}_ncu_gemm_$shape.out 2>&1
   done
-  timeout 400 $FULL -k regex:attn_fwd_tc_kernel -s 12 -c 3 -f -o $OUT/${TAG}_ncu_attn_fwd \
+  timeout 400 $FULL -k regex:attn_fwd2_kernel -s 12 -c 3 -f -o $OUT/${TAG}_ncu_attn_fwd \
       python bench.py --profile-only > $OUT/${TAG}_ncu_attn_fwd.out 2>&1
-  timeout 400 $FULL -k regex:attn_bwd_tc_kernel -s 9 -c 2 -f -o $OUT/${TAG}_ncu_attn_bwd \
+  timeout 400 $FULL -k regex:attn_bwd2_kernel -s 9 -c 2 -f -o $OUT/${TAG}_ncu_attn_bwd \
       python bench.py --profile-only > $OUT/${TAG}_ncu_attn_bwd.out 2>&1
   timeout 400 $FULL -k regex:"layernorm_bwd_kernel|colsum_kernel|layernorm_fwd_kernel" -s 90 -c 6 -f -o $OUT/${TAG}_ncu_ln \
       python bench.py --profile-only > $OUT/${TAG}_ncu_ln.out 2>&1
