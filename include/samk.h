@@ -115,6 +115,10 @@ int samk_dropout_add(const float* a, const float* b, float* out, void* out2, int
                      float drop_p, unsigned long long seed, unsigned long long offset, void* stream);
 /* out[c] += sum_r x[r,c] */
 int samk_colsum(const void* x, int x_dtype, long long ld, int rows, int cols, float* out, void* stream);
+/* x = [rows, 3*part_cols]: column sums of the three column groups added into out0 / out1 / out2 (bias gradients of
+ * the fused q|k|v projection, sa_m4c.py:554-560 backward: three separate nn.Linear biases) in one pass. */
+int samk_colsum3(const void* x, int x_dtype, long long ld, int rows, int part_cols, float* out0, float* out1, float* out2,
+                 void* stream);
 /* BertEmbeddings of TextBert (sa_m4c.py:383): dropout(LN(word[id] + pos[t] + type[0])); backward
  * accumulates into the five gradient buffers. */
 int samk_bert_embed_fwd(const long long* ids, const float* word, const float* pos, const float* type,

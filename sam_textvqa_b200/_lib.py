@@ -57,6 +57,7 @@ SIGNATURES = {
     "samk_layernorm_bwd_partials": (c_ll, [c_int]),
     "samk_dropout_add": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_ull, c_ull, c_void_p]),
     "samk_colsum": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p]),
+    "samk_colsum3": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "samk_bert_embed_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
                                     c_void_p, c_int, c_int, c_int, c_int, c_float, c_ull, c_ull, c_void_p]),
     "samk_bert_embed_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,

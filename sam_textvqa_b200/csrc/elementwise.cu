@@ -291,8 +291,10 @@ __global__ void dropout_add_kernel(const float* __restrict__ a, const float* __r
 }
 
 // out[c] += sum_r x[r, c]
+// part_cols > 0: the columns are n consecutive groups of part_cols with separate destinations out, out1, out2
+// (bias gradients of the fused q|k|v projection are three separate parameters)
 __global__ void colsum_kernel(const void* __restrict__ x, int x_bf16, long long ld, int rows, int cols,
-                              float* __restrict__ out) {
+                              float* __restrict__ out, float* __restrict__ out1, float* __restrict__ out2, int part_cols) {
   // block = 256 threads = 64 column-quads x 4 row lanes
   const int cq = blockIdx.x * 64 + (threadIdx.x & 63);
   const int rl = threadIdx.x >> 6;
@@ -320,8 +322,13 @@ __global__ void colsum_kernel(const void* __restrict__ x, int x_bf16, long long 
     float4 t = red[0][threadIdx.x];
 #pragma unroll
     for (int k = 1; k < 4; ++k) { float4 u = red[k][threadIdx.x]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
-    atomicAdd(out + cq * 4 + 0, t.x); atomicAdd(out + cq * 4 + 1, t.y);
-    atomicAdd(out + cq * 4 + 2, t.z); atomicAdd(out + cq * 4 + 3, t.w);
+    float* dst = out + cq * 4;
+    if (part_cols > 0) {
+      const int part = (cq * 4) / part_cols;
+      dst = (part == 0 ? out : (part == 1 ? out1 : out2)) + (cq * 4 - part * part_cols);
+    }
+    atomicAdd(dst + 0, t.x); atomicAdd(dst + 1, t.y);
+    atomicAdd(dst + 2, t.z); atomicAdd(dst + 3, t.w);
   }
 }
 
@@ -398,6 +405,78 @@ __device__ __forceinline__ void row_ln_backward(float4* d, const RowLN& st, cons
   }
 }
 
+// same, but dgamma / dbeta contributions are added to per-lane register accumulators (lane owns fixed columns), to be
+// reduced per block by block_flush_columns: thousands of rows hammering the same 768 addresses with global atomics
+// cost 260 us in the TextBert embedding backward
+__device__ __forceinline__ void row_ln_backward_acc(float4* d, const RowLN& st, const float* gamma, float4* ag, float4* ab,
+                                                    int cols, int lane) {
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) if (i < st.nvec) {
+    int c = 4 * (lane + 32 * i);
+    float4 gm = *reinterpret_cast<const float4*>(gamma + c);
+    ag[i].x += d[i].x * st.xh[i].x; ag[i].y += d[i].y * st.xh[i].y; ag[i].z += d[i].z * st.xh[i].z; ag[i].w += d[i].w * st.xh[i].w;
+    ab[i].x += d[i].x; ab[i].y += d[i].y; ab[i].z += d[i].z; ab[i].w += d[i].w;
+    d[i] = make_float4(gm.x * d[i].x, gm.y * d[i].y, gm.z * d[i].z, gm.w * d[i].w);
+    s1 += d[i].x + d[i].y + d[i].z + d[i].w;
+    s2 += d[i].x * st.xh[i].x + d[i].y * st.xh[i].y + d[i].z * st.xh[i].z + d[i].w * st.xh[i].w;
+  }
+  s1 = warp_sum(s1) / cols;
+  s2 = warp_sum(s2) / cols;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) if (i < st.nvec) {
+    d[i].x = st.rstd * (d[i].x - s1 - st.xh[i].x * s2);
+    d[i].y = st.rstd * (d[i].y - s1 - st.xh[i].y * s2);
+    d[i].z = st.rstd * (d[i].z - s1 - st.xh[i].z * s2);
+    d[i].w = st.rstd * (d[i].w - s1 - st.xh[i].w * s2);
+  }
+}
+
+// same again, accumulating dgamma / dbeta into shared-memory arrays of the block (kernels with too many hot arrays
+// for register accumulators)
+__device__ __forceinline__ void row_ln_backward_smem(float4* d, const RowLN& st, const float* gamma, float* sg, float* sb,
+                                                     int cols, int lane) {
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) if (i < st.nvec) {
+    int c = 4 * (lane + 32 * i);
+    float4 gm = *reinterpret_cast<const float4*>(gamma + c);
+    atomicAdd(sg + c + 0, d[i].x * st.xh[i].x); atomicAdd(sg + c + 1, d[i].y * st.xh[i].y);
+    atomicAdd(sg + c + 2, d[i].z * st.xh[i].z); atomicAdd(sg + c + 3, d[i].w * st.xh[i].w);
+    atomicAdd(sb + c + 0, d[i].x); atomicAdd(sb + c + 1, d[i].y);
+    atomicAdd(sb + c + 2, d[i].z); atomicAdd(sb + c + 3, d[i].w);
+    d[i] = make_float4(gm.x * d[i].x, gm.y * d[i].y, gm.z * d[i].z, gm.w * d[i].w);
+    s1 += d[i].x + d[i].y + d[i].z + d[i].w;
+    s2 += d[i].x * st.xh[i].x + d[i].y * st.xh[i].y + d[i].z * st.xh[i].z + d[i].w * st.xh[i].w;
+  }
+  s1 = warp_sum(s1) / cols;
+  s2 = warp_sum(s2) / cols;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) if (i < st.nvec) {
+    d[i].x = st.rstd * (d[i].x - s1 - st.xh[i].x * s2);
+    d[i].y = st.rstd * (d[i].y - s1 - st.xh[i].y * s2);
+    d[i].z = st.rstd * (d[i].z - s1 - st.xh[i].z * s2);
+    d[i].w = st.rstd * (d[i].w - s1 - st.xh[i].w * s2);
+  }
+}
+
+// block-wide: sum the per-lane column accumulators of all warps in shared memory, then one global atomic per column
+__device__ __forceinline__ void block_flush_columns(const float4* acc, float* sm /*[cols]*/, float* out, int cols, int lane) {
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    int c = 4 * (lane + 32 * i);
+    if (c < cols) {
+      atomicAdd(sm + c + 0, acc[i].x); atomicAdd(sm + c + 1, acc[i].y);
+      atomicAdd(sm + c + 2, acc[i].z); atomicAdd(sm + c + 3, acc[i].w);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) atomicAdd(out + c, sm[c]);
+  __syncthreads();
+}
+
 __device__ __forceinline__ void atomic_add4(float* p, float4 v) {
   atomicAdd(p + 0, v.x); atomicAdd(p + 1, v.y); atomicAdd(p + 2, v.z); atomicAdd(p + 3, v.w);
 }
@@ -446,6 +525,10 @@ bert_embed_bwd_kernel(const float* __restrict__ dout, const long long* __restric
                       float scale, unsigned long long seed, unsigned long long off) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  __shared__ float sm_cols[1024];
+  float4 ag[kMaxVec], ab[kMaxVec], at[kMaxVec];      // dgamma, dbeta, d(token_type row 0): identical addresses for every row
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) ag[i] = ab[i] = at[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int r = warp; r < rows; r += nwarps) {
     const long long id = ids[r];
     const int t = r % T;
@@ -464,15 +547,18 @@ bert_embed_bwd_kernel(const float* __restrict__ dout, const long long* __restric
     }
     RowLN st;
     row_ln_forward(v, cols, lane, eps, st);
-    row_ln_backward(d, st, gamma, dgamma, dbeta, cols, lane);
+    row_ln_backward_acc(d, st, gamma, ag, ab, cols, lane);
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) if (i < st.nvec) {
       int c = 4 * (lane + 32 * i);
       if (id != 0) atomic_add4(dword + (size_t)id * cols + c, d[i]);  // padding_idx = 0 gets no gradient
       atomic_add4(dpos + (size_t)t * cols + c, d[i]);
-      atomic_add4(dtype + c, d[i]);
+      at[i].x += d[i].x; at[i].y += d[i].y; at[i].z += d[i].z; at[i].w += d[i].w;
     }
   }
+  block_flush_columns(ag, sm_cols, dgamma, cols, lane);
+  block_flush_columns(ab, sm_cols, dbeta, cols, lane);
+  block_flush_columns(at, sm_cols, dtype, cols, lane);
 }
 
 // PrevPredEmbeddings (sa_m4c.py:919-948): row (b,t): idx = prev[b,t];
@@ -534,6 +620,11 @@ prevpred_bwd_kernel(PrevPredParams p, const float* __restrict__ dout, PrevPredGr
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int cols = p.cols;
+  // gradients that every row adds to the same few addresses (three LayerNorms, the two token-type rows) are summed
+  // per block in shared memory first: [ans_g, ans_b, ocr_g, ocr_b, emb_g, emb_b, type0, type1][cols]
+  extern __shared__ float sacc[];
+  for (int c = threadIdx.x; c < 8 * cols; c += blockDim.x) sacc[c] = 0.f;
+  __syncthreads();
   for (int r = warp; r < p.B * p.D; r += nwarps) {
     const int b = r / p.D, t = r % p.D;
     long long idx = p.prev[r];
@@ -557,17 +648,26 @@ prevpred_bwd_kernel(PrevPredParams p, const float* __restrict__ dout, PrevPredGr
     RowLN s1, s2;
     row_ln_forward(v, cols, lane, p.eps, s1);
     row_ln_forward(e, cols, lane, p.eps, s2);
-    row_ln_backward(d1, s1, is_ocr ? p.ocr_g : p.ans_g, is_ocr ? g.d_ocr_g : g.d_ans_g, is_ocr ? g.d_ocr_b : g.d_ans_b, cols, lane);
-    row_ln_backward(d2, s2, p.emb_g, g.d_emb_g, g.d_emb_b, cols, lane);
+    row_ln_backward_smem(d1, s1, is_ocr ? p.ocr_g : p.ans_g, sacc + (is_ocr ? 2 : 0) * cols, sacc + (is_ocr ? 3 : 1) * cols, cols, lane);
+    row_ln_backward_smem(d2, s2, p.emb_g, sacc + 4 * cols, sacc + 5 * cols, cols, lane);
     float* dsrc = (is_ocr ? g.d_ocr_in : g.d_cls_w) + src_off;
+    float* stype = sacc + (is_ocr ? 7 : 6) * cols;
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) if (i < s1.nvec) {
       int c = 4 * (lane + 32 * i);
       atomic_add4(dsrc + c, d1[i]);
       atomic_add4(g.d_pos + (size_t)t * cols + c, d2[i]);
-      atomic_add4(g.d_type + (size_t)(is_ocr ? 1 : 0) * cols + c, d2[i]);
+      atomic_add4(stype + c, d2[i]);
     }
   }
+  __syncthreads();
+  float* const dst[8] = {g.d_ans_g, g.d_ans_b, g.d_ocr_g, g.d_ocr_b, g.d_emb_g, g.d_emb_b, g.d_type, g.d_type + cols};
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+      const float x = sacc[a * cols + c];
+      if (x != 0.f) atomicAdd(dst[a] + c, x);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -762,7 +862,23 @@ int samk_colsum(const void* x, int x_dtype, long long ld, int rows, int cols, fl
   if (gy > (rows + 3) / 4) gy = (rows + 3) / 4;
   if (gy < 1) gy = 1;
   dim3 grid(gx, gy);
-  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_dtype == SAMK_DT_BF16, ld, rows, cols, out);
+  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_dtype == SAMK_DT_BF16, ld, rows, cols, out, nullptr, nullptr, 0);
+  return check_launch(__func__);
+}
+
+int samk_colsum3(const void* x, int x_dtype, long long ld, int rows, int part_cols, float* out0, float* out1, float* out2,
+                 void* stream) {
+  SAMK_REQUIRE(x && out0 && out1 && out2 && rows >= 0 && part_cols > 0, "bad argument");
+  const bool bf = x_dtype == SAMK_DT_BF16;
+  SAMK_REQUIRE(part_cols % 4 == 0 && ld % 4 == 0 && ((uintptr_t)x & (bf ? 7 : 15)) == 0, "needs 4-column aligned parts");
+  if (!rows) return SAMK_OK;
+  const int cols = 3 * part_cols;
+  const int gx = (cols / 4 + 63) / 64;
+  int gy = (148 * 4 + gx - 1) / gx;
+  if (gy > (rows + 3) / 4) gy = (rows + 3) / 4;
+  if (gy < 1) gy = 1;
+  dim3 grid(gx, gy);
+  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, bf, ld, rows, cols, out0, out1, out2, part_cols);
   return check_launch(__func__);
 }
 
@@ -786,7 +902,8 @@ int samk_bert_embed_bwd(const float* dout, const long long* ids, const float* wo
   SAMK_REQUIRE(dout && ids && word && pos && type && gamma && dword && dpos && dtype && dgamma && dbeta, "null pointer");
   SAMK_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 1024 && T > 0, "bad size");
   if (!rows) return SAMK_OK;
-  bert_embed_bwd_kernel<<<grid_for(rows, 8), kRowThreads, 0, (cudaStream_t)stream>>>(
+  // few blocks: each reduces its rows' hot-column gradients in shared memory before touching global memory
+  bert_embed_bwd_kernel<<<grid_for(rows, 32) < 148 ? grid_for(rows, 32) : 148, kRowThreads, 0, (cudaStream_t)stream>>>(
       dout, ids, word, pos, type, gamma, eps, dword, dpos, dtype, dgamma, dbeta, rows, T, cols,
       drop_p > 0.f ? drop_threshold(drop_p) : 0u, drop_keep_scale(drop_p), seed, offset);
   return check_launch(__func__);
@@ -829,7 +946,8 @@ int samk_prevpred_bwd(const float* dout, const long long* prev, const float* cls
   g.d_cls_w = grads10[0]; g.d_ocr_in = grads10[1]; g.d_pos = grads10[2]; g.d_type = grads10[3];
   g.d_ans_g = grads10[4]; g.d_ans_b = grads10[5]; g.d_ocr_g = grads10[6]; g.d_ocr_b = grads10[7];
   g.d_emb_g = grads10[8]; g.d_emb_b = grads10[9];
-  prevpred_bwd_kernel<<<grid_for((long long)B * D, 8), kRowThreads, 0, (cudaStream_t)stream>>>(p, dout, g);
+  const int grid = grid_for((long long)B * D, 16) < 148 ? grid_for((long long)B * D, 16) : 148;
+  prevpred_bwd_kernel<<<grid, kRowThreads, 8 * cols * sizeof(float), (cudaStream_t)stream>>>(p, dout, g);
   return check_launch(__func__);
 }
 

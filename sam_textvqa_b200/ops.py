@@ -160,6 +160,26 @@ class Operand(object):
         self.t, self.ld, self.kmul = t, ld, kmul
 
 
+# bf16 operand copies of fp32 activations made during the current forward pass, keyed on the fp32 tensor's
+# storage.  The entry keeps the fp32 tensor alive (so the address cannot be recycled under the key) and is
+# dropped at the next forward (`begin_forward`).  Serves the backward pass (wgrad re-reads the layer input) and the
+# next layer (LayerNorm writes the bf16 copy of its output in the same pass, no separate cast kernel).
+_act_cache = {}
+
+
+def begin_forward():
+    _act_cache.clear()
+
+
+def _act_key(x2d):
+    return (x2d.data_ptr(), tuple(x2d.shape), x2d.stride(0), x2d._version)
+
+
+def remember_bf16(x2d, y_bf16):
+    if _PRECISION == "bf16":
+        _act_cache[_act_key(x2d)] = (x2d, y_bf16)
+
+
 def operand(x2d, role, mn_major):
     """x2d: logical [rows(MN), K] if not mn_major else stored [K, MN].  role 'a' or 'b'."""
     _cuda(x2d)
@@ -169,7 +189,12 @@ def operand(x2d, role, mn_major):
         assert x2d.stride(1) == 1 and x2d.stride(0) % 8 == 0 and x2d.data_ptr() % 16 == 0
         return Operand(x2d, x2d.stride(0), 1)
     if _PRECISION == "bf16":
+        hit = _act_cache.get(_act_key(x2d))
+        if hit is not None:
+            return Operand(hit[1], hit[1].stride(0), 1)
         y = cast_bf16(x2d)
+        if x2d.shape[0] >= 1024 and x2d.shape[1] % 8 == 0:       # activations worth remembering (wgrad re-reads them)
+            _act_cache[_act_key(x2d)] = (x2d, y)
         return Operand(y, y.stride(0), 1)
     y = _split3(x2d, 0 if role == "a" else 1, 1 if mn_major else 0)
     return Operand(y, y.stride(0), 3)
@@ -579,8 +604,12 @@ class BertLayerFn(torch.autograd.Function):
         gemm(operand(g, "a", False), False, weight_operand([o2w], False), False, M, d, F, y2, bias=o2b, drop_p=p_hid,
              drop=drops[2], residual=a)
         out = torch.empty(M, d, dtype=torch.float32, device=dev)
-        check(lib().samk_layernorm_fwd(ptr(y2), ptr(g2), ptr(b2), eps, ptr(out), None, 0, M, d, stream_ptr()), "ln2")
+        out_act = torch.empty(M, d, dtype=adt, device=dev) if adt != torch.float32 else None
+        check(lib().samk_layernorm_fwd(ptr(y2), ptr(g2), ptr(b2), eps, ptr(out), ptr(out_act), DT_BF16, M, d, stream_ptr()),
+              "ln2")
         _count()
+        if out_act is not None:
+            remember_bf16(out, out_act)          # the next layer's q|k|v projection and its wgrad read this copy
 
         ctx.cfg, ctx.drops = cfg[:6], drops
         ctx.save_for_backward(x2, valid, rel, qkv, ctx_t, lse, y1, a_in, h, g, y2, allow, *P)
@@ -627,9 +656,11 @@ class BertLayerFn(torch.autograd.Function):
         dx = torch.empty(M, d, dtype=torch.float32, device=dev)
         gemm(operand(dqkv, "a", False), False, weight_operand([qw, kw, vw], True), True, M, d, 3 * d, dx, residual=dy1)
         x_mn = operand(x2, "b", True)
-        for part, (Gw, Gb) in enumerate(((Gqw, Gqb), (Gkw, Gkb), (Gvw, Gvb))):
+        check(lib().samk_colsum3(ptr(dqkv), _dt(dqkv), dqkv.stride(0), M, d, ptr(Gqb), ptr(Gkb), ptr(Gvb), stream_ptr()),
+              "colsum3")
+        _count()
+        for part, Gw in enumerate((Gqw, Gkw, Gvw)):
             sl = dqkv[:, part * d:(part + 1) * d]
-            colsum_into(sl, Gb)
             gemm(operand(sl, "a", True), True, x_mn, True, d, d, M, Gw, accumulate=True)
         _grads_done(*P)
         return (dx.view(B, L, d), None, None, None) + tuple(_ret(x) for x in G)

@@ -493,6 +493,7 @@ class SAM4C(nn.Module):
         if use_beam_search:
             raise NotImplementedError("beam search is disabled in the reference (train.py:222, README.md:68-69)")
         self._to_device(batch_dict)
+        ops.begin_forward()
         batch_dict.pop("_samk_rel_bits", None)
         self._forward_obj_encoding(batch_dict)
         self._forward_ocr_encoding(batch_dict)
