@@ -82,6 +82,12 @@ typedef struct samk_gemm_epilogue {
   unsigned long long drop_seed, drop_offset;
   const float* residual; /* [M,N] fp32 or NULL */
   long long ldres;
+  /* atomic_add only: if part_rows > 0 the M rows are consecutive groups of part_rows rows with separate fp32
+   * destinations out, out_part1, out_part2 (each [part_rows, N], pitch ldo): the weight gradients of the fused
+   * q|k|v projection are three separate parameters, one launch computes all three. part_rows % 32 == 0. */
+  int part_rows;
+  void* out_part1;
+  void* out_part2;
 } samk_gemm_epilogue;
 
 /* split_k >= 1 partitions K over CTAs (requires atomic_add and a pre-zeroed or accumulating out).

@@ -22,6 +22,7 @@ class GemmEpilogue(ctypes.Structure):
         ("bias", c_void_p), ("pre", c_void_p), ("ldpre", c_ll), ("pre_dtype", c_int), ("act", c_int),
         ("aux", c_void_p), ("ldaux", c_ll), ("aux_dtype", c_int), ("drop_p", c_float),
         ("drop_seed", c_ull), ("drop_offset", c_ull), ("residual", c_void_p), ("ldres", c_ll),
+        ("part_rows", c_int), ("out_part1", c_void_p), ("out_part2", c_void_p),
     ]
 
 

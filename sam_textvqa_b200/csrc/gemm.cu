@@ -53,6 +53,7 @@ struct EpiArgs {
   uint32_t drop_thresh; float drop_scale; unsigned long long seed, offset;
   const float* residual; long long ldres;
   int flags;
+  int part_rows; void* out1; void* out2;   // F_ATOMIC: row groups with separate destinations (0 = single output)
 };
 
 template <int EPI> __device__ __forceinline__ int epi_flags(const EpiArgs& ep) {
@@ -189,7 +190,14 @@ __device__ __forceinline__ void epi_store(const EpiArgs& ep, const EpiRow& e, co
     }
   }
   if (F & F_ATOMIC) {
-    float* p = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col;
+    void* base = ep.out;
+    int prow = row;
+    if (ep.part_rows > 0) {
+      const int part = row / ep.part_rows;
+      prow = row - part * ep.part_rows;
+      base = part == 0 ? ep.out : (part == 1 ? ep.out1 : ep.out2);
+    }
+    float* p = reinterpret_cast<float*>(base) + (size_t)prow * ep.ldo + col;
     if (full) {
       asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
       asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
@@ -702,8 +710,17 @@ extern "C" int samk_gemm_bf16(const void* A, int a_mn, long long lda, const void
   ep.drop_scale = drop_keep_scale(e->drop_p);
   ep.seed = e->drop_seed; ep.offset = e->drop_offset;
   ep.residual = e->residual; ep.ldres = e->ldres;
+  ep.part_rows = 0; ep.out1 = ep.out2 = nullptr;
+  if (e->part_rows > 0) {
+    if (!e->atomic_add || !e->out_part1 || !e->out_part2 || e->part_rows % 32 || M > 3 * e->part_rows) {
+      set_error("samk_gemm_bf16: part_rows needs atomic_add, two more outputs, part_rows %% 32 == 0 and M <= 3*part_rows");
+      return SAMK_ERR_ARG;
+    }
+    ep.part_rows = e->part_rows; ep.out1 = e->out_part1; ep.out2 = e->out_part2;
+  }
   auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
-  const bool vec_ok = (N % 8 == 0) && al16(ep.out) && (ep.ldo % 8 == 0) && (!ep.bias || al16(ep.bias)) &&
+  const bool vec_ok = (N % 8 == 0) && al16(ep.out) && (!ep.out1 || (al16(ep.out1) && al16(ep.out2))) && (ep.ldo % 8 == 0) &&
+                      (!ep.bias || al16(ep.bias)) &&
                       (!ep.pre || (al16(ep.pre) && ep.ldpre % 8 == 0)) && (!ep.aux || (al16(ep.aux) && ep.ldaux % 8 == 0)) &&
                       (!ep.residual || (al16(ep.residual) && ep.ldres % 4 == 0));
   int flags = 0;

@@ -235,7 +235,7 @@ def _pick_split_k(M, N, K, sms=148):
 
 
 def gemm(a, a_mn, b, b_mn, M, N, K, out, bias=None, act=0, pre=None, aux=None, drop_p=0.0, drop=None,
-         residual=None, alpha=1.0, accumulate=False, split_k=None):
+         residual=None, alpha=1.0, accumulate=False, split_k=None, out_parts=None):
     """out[M,N] = epilogue(alpha * A.B^T).  a, b: Operand.  out: fp32/bf16 2-D view (unit column stride)."""
     assert a.kmul == b.kmul
     ep = GemmEpilogue()
@@ -257,6 +257,8 @@ def gemm(a, a_mn, b, b_mn, M, N, K, out, bias=None, act=0, pre=None, aux=None, d
     if split_k is None:
         split_k = _pick_split_k(M, N, Kk) if accumulate else 1
     ep.atomic_add = 1 if (accumulate or split_k > 1) else 0
+    if out_parts is not None:       # (rows per part, out1, out2): M = 3 * rows, destinations out / out1 / out2
+        ep.part_rows, ep.out_part1, ep.out_part2 = out_parts[0], out_parts[1].data_ptr(), out_parts[2].data_ptr()
     if gemm_profile is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -659,9 +661,13 @@ class BertLayerFn(torch.autograd.Function):
         check(lib().samk_colsum3(ptr(dqkv), _dt(dqkv), dqkv.stride(0), M, d, ptr(Gqb), ptr(Gkb), ptr(Gvb), stream_ptr()),
               "colsum3")
         _count()
-        for part, Gw in enumerate((Gqw, Gkw, Gvw)):
-            sl = dqkv[:, part * d:(part + 1) * d]
-            gemm(operand(sl, "a", True), True, x_mn, True, d, d, M, Gw, accumulate=True)
+        if Gqw.stride(0) == Gkw.stride(0) == Gvw.stride(0) and d % 32 == 0:
+            # the three weight gradients in one launch: M = 3d output rows routed to three destinations
+            gemm(operand(dqkv, "a", True), True, x_mn, True, 3 * d, d, M, Gqw, accumulate=True, out_parts=(d, Gkw, Gvw))
+        else:
+            for part, Gw in enumerate((Gqw, Gkw, Gvw)):
+                sl = dqkv[:, part * d:(part + 1) * d]
+                gemm(operand(sl, "a", True), True, x_mn, True, d, d, M, Gw, accumulate=True)
         _grads_done(*P)
         return (dx.view(B, L, d), None, None, None) + tuple(_ret(x) for x in G)
 
