@@ -1,6 +1,6 @@
 // tcgen05 GEMM with fused epilogues: C[M,N] = epi(alpha * A[M,K] * B[N,K]^T), bf16 x bf16 -> fp32.
 //
-// Persistent, warp-specialised, one CTA per SM:
+// Persistent, warp-specialised, one CTA per SM (a CTA pair per 256 x 256 tile for the large shapes, see CL below):
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128B swizzle, kStages-deep mbarrier ring)
 //   warp 1      MMA issuer     (one elected lane issues tcgen05.mma, accumulators in TMEM,
 //                               two accumulator buffers so the epilogue overlaps the next tile)
@@ -338,25 +338,28 @@ __device__ __forceinline__ void chunk_finish(const EpiArgs& ep, const ChunkIn<ST
   }
 }
 
-template <int BN> struct GemmCfg {
-  static constexpr int kStages = BN == 256 ? 4 : 6;
+template <int BN, int CL = 1> struct GemmCfg {
+  static constexpr int kStages = (BN == 256 && CL == 1) ? 4 : 6;
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (BN / CL) * BK * 2;      // CTA pair: each CTA holds half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingOff = kStages * kStageBytes + 256;       // after the barriers
   static constexpr int kSmemBytes = kStagingOff + kEpiWarps * kStageBytesPerWarp /*epilogue transposes*/ + 1024 /*align slack*/;
   static constexpr int kTmemCols = 2 * BN;  // 256 or 512: power of two
 };
 
-// CL = cluster size along M (1 or 2).  With CL = 2 the two CTAs of a cluster work on vertically adjacent
-// output tiles that need the same B tile: each CTA fetches half of it and TMA-multicasts it into both
-// shared memories, cutting the L2->SM operand traffic per flop by a third (the kernel is L2-bandwidth
-// bound at 128x256 tiles otherwise).  Slots are released to both producers with a multicast commit.
+// CL = 1: one CTA per 128 x BN tile.
+// CL = 2: CTA pair (tcgen05 cta_group::2): a cluster of two CTAs owns a 256 x BN tile.  Each CTA loads its own 128
+//   rows of A and HALF of the B tile; the leader CTA issues one M=256 MMA that reads both shared memories and writes
+//   the accumulator rows of each CTA into that CTA's TMEM.  Per MMA cycle every SM then reads 32 KB instead of 48 KB
+//   of operands from shared memory (the port the staged epilogue also needs).  All TMA loads of a stage complete on
+//   the leader's full barrier; MMA completion is multicast to both CTAs' empty / accumulator-full barriers; both
+//   CTAs' epilogue warps release the accumulator on the leader's barrier.
 template <int BN, int A_MN, int B_MN, int CL, int EPI, bool STAGED>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const EpiArgs ep, int M, int N, int K, int split_k) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -377,7 +380,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_work = m_groups * n_tiles * split_k;
   const int cta_rank = CL > 1 ? (int)ptx::cluster_ctarank() : 0;
   const int work0 = blockIdx.x / CL, work_stride = gridDim.x / CL;
-  constexpr uint16_t kMcastMask = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
@@ -385,12 +387,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < Cfg::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], CL); }
-      for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], kEpiWarps); }
+      for (int s = 0; s < Cfg::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+      for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], CL * kEpiWarps); }
       ptx::fence_barrier_init();
     }
     __syncwarp();
-    ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    if (CL == 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    else ptx::tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot);
   }
   ptx::tc_fence_before();
   if (CL > 1) ptx::cluster_sync_all();   // peer barriers must be initialised before remote arrivals / multicasts
@@ -412,14 +415,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          if (A_MN) {
-#pragma unroll
-            for (int g = 0; g < BM / 64; ++g) ptx::tma_load_2d(sa + g * (BK * 128), &tmA, &full_bar[stage], m0 + g * 64, kb * BK);
-          } else {
-            ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
-          }
           if (CL == 1) {
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            if (A_MN) {
+#pragma unroll
+              for (int g = 0; g < BM / 64; ++g) ptx::tma_load_2d(sa + g * (BK * 128), &tmA, &full_bar[stage], m0 + g * 64, kb * BK);
+            } else {
+              ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+            }
             if (B_MN) {
 #pragma unroll
               for (int g = 0; g < BN / 64; ++g) ptx::tma_load_2d(sb + g * (BK * 128), &tmB, &full_bar[stage], n0 + g * 64, kb * BK);
@@ -427,16 +430,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
             }
           } else {
-            // this CTA fetches its 1/CL share of the B tile and multicasts it to the whole cluster
+            // the leader's barrier collects the bytes of both CTAs (its own expect_tx may come after the peer's
+            // first bytes: the transaction count is signed)
+            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            if (A_MN) {
+#pragma unroll
+              for (int g = 0; g < BM / 64; ++g) ptx::tma_load_2d_2sm(sa + g * (BK * 128), &tmA, &full_bar[stage], m0 + g * 64, kb * BK);
+            } else {
+              ptx::tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * BK, m0);
+            }
+            const int nh = n0 + cta_rank * (BN / 2);       // this CTA's half of the B tile
             if (B_MN) {
 #pragma unroll
-              for (int g = 0; g < BN / 64 / CL; ++g) {
-                const int gg = cta_rank * (BN / 64 / CL) + g;
-                ptx::tma_load_2d_mcast(sb + gg * (BK * 128), &tmB, &full_bar[stage], n0 + gg * 64, kb * BK, kMcastMask);
-              }
+              for (int g = 0; g < BN / 128; ++g) ptx::tma_load_2d_2sm(sb + g * (BK * 128), &tmB, &full_bar[stage], nh + g * 64, kb * BK);
             } else {
-              ptx::tma_load_2d_mcast(sb + cta_rank * (BN / CL) * 128, &tmB, &full_bar[stage], kb * BK,
-                                     n0 + cta_rank * (BN / CL), kMcastMask);
+              ptx::tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * BK, nh);
             }
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -444,48 +452,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN, B_MN);
+    // ===================== MMA issuer (CTA pair: the leader CTA only) =====================
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(BM * CL, BN, A_MN, B_MN);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int w = work0; w < num_work; w += work_stride) {
-      const int split = w % split_k;
-      const int kb0 = split * kb_per;
-      const int kb1 = min(kb_total, kb0 + kb_per);
-      ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-      ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        ptx::mbar_wait(&full_bar[stage], phase);
+    if (CL == 1 || cta_rank == 0) {
+      for (int w = work0; w < num_work; w += work_stride) {
+        const int split = w % split_k;
+        const int kb0 = split * kb_per;
+        const int kb1 = min(kb_total, kb0 + kb_per);
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
-        // descriptors are computed by the whole (converged) warp so that they live in uniform registers; only
-        // the tcgen05 instructions themselves sit under the elected-lane predicate (an `if (lane == 0)` around
-        // the arithmetic makes ptxas wrap every UTCHMMA in an elect / R2UR.BROADCAST / branch loop, ~150 cycles)
-        {
-          const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
-          const uint64_t adesc0 = A_MN ? ptx::make_smem_desc_sw128(sa, BK * 128, 1024) : ptx::make_smem_desc_sw128(sa, 16, 1024);
-          const uint64_t bdesc0 = B_MN ? ptx::make_smem_desc_sw128(sb, BK * 128, 1024) : ptx::make_smem_desc_sw128(sb, 16, 1024);
-          const bool leader = ptx::elect_one();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          // descriptors are computed by the whole (converged) warp so that they live in uniform registers; only
+          // the tcgen05 instructions themselves sit under the elected-lane predicate (an `if (lane == 0)` around
+          // the arithmetic makes ptxas wrap every UTCHMMA in an elect / R2UR.BROADCAST / branch loop, ~150 cycles)
+          {
+            const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t sb = sa + Cfg::kABytes;
+            const uint64_t adesc0 = A_MN ? ptx::make_smem_desc_sw128(sa, BK * 128, 1024) : ptx::make_smem_desc_sw128(sa, 16, 1024);
+            const uint64_t bdesc0 = B_MN ? ptx::make_smem_desc_sw128(sb, BK * 128, 1024) : ptx::make_smem_desc_sw128(sb, 16, 1024);
+            const bool leader = ptx::elect_one();
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advancing the start-address field (bytes >> 4) cannot carry out of its 14 bits for shared memory
-            const uint64_t adesc = adesc0 + (uint64_t)(A_MN ? k * (2048 >> 4) : k * (32 >> 4));
-            const uint64_t bdesc = bdesc0 + (uint64_t)(B_MN ? k * (2048 >> 4) : k * (32 >> 4));
-            if (leader) ptx::umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advancing the start-address field (bytes >> 4) cannot carry out of its 14 bits for shared memory
+              const uint64_t adesc = adesc0 + (uint64_t)(A_MN ? k * (2048 >> 4) : k * (32 >> 4));
+              const uint64_t bdesc = bdesc0 + (uint64_t)(B_MN ? k * (2048 >> 4) : k * (32 >> 4));
+              if (leader) {
+                if (CL == 1) ptx::umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                else ptx::umma_f16_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              }
+            }
+            if (leader) {
+              if (CL == 1) {
+                ptx::umma_commit(&empty_bar[stage]);                    // smem slot free once these MMAs retire
+                if (kb == kb1 - 1) ptx::umma_commit(&tfull_bar[acc]);   // accumulator ready
+              } else {
+                ptx::umma_commit_2sm(&empty_bar[stage], 0b11);          // ... in both CTAs of the pair
+                if (kb == kb1 - 1) ptx::umma_commit_2sm(&tfull_bar[acc], 0b11);
+              }
+            }
           }
-          if (leader) {
-            if (CL == 1) ptx::umma_commit(&empty_bar[stage]);      // smem slot free once these MMAs retire
-            else ptx::umma_commit_mcast(&empty_bar[stage], kMcastMask);   // ... in every CTA that multicasts into it
-            if (kb == kb1 - 1) ptx::umma_commit(&tfull_bar[acc]);  // accumulator ready
-          }
+          __syncwarp();
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        if (kb1 <= kb0 && ptx::elect_one()) {                           // empty K range: still hand over
+          if (CL == 1) ptx::umma_commit(&tfull_bar[acc]); else ptx::umma_commit_2sm(&tfull_bar[acc], 0b11);
         }
         __syncwarp();
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (kb1 <= kb0 && lane == 0) ptx::umma_commit(&tfull_bar[acc]);  // empty K range: still hand over
-      __syncwarp();
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================== epilogue =====================
@@ -541,7 +560,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (CL == 1) ptx::mbar_arrive(&tempty_bar[acc]);
+        else ptx::mbar_arrive_leader(&tempty_bar[acc]);       // the leader's MMA warp waits for both CTAs' epilogues
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -551,7 +573,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (CL == 1) ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    else ptx::tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -635,7 +658,7 @@ int sm_count() {
 template <int BN, int A_MN, int B_MN, int CL, int EPI, bool STAGED>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiArgs& ep, int M, int N, int K, int split_k,
                      cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CL, EPI, STAGED>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -668,6 +691,16 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiArgs
     return SAMK_ERR_CUDA;
   }
   return check_launch("samk_gemm_bf16");
+}
+
+// CTA-pair tiles (cta_group::2): SAMK_GEMM_2CTA=0/1 overrides the default
+static int g_gemm_2cta = -1;
+static int gemm_2cta() {
+  if (g_gemm_2cta < 0) {
+    const char* s = getenv("SAMK_GEMM_2CTA");
+    g_gemm_2cta = s ? (s[0] == '1' ? 1 : 0) : 1;     // measured faster on every layer shape (tools/gemm_bench.py)
+  }
+  return g_gemm_2cta;
 }
 
 // the epilogue combinations of the SA-M4C layers that get a compile-time specialised kernel
@@ -760,14 +793,23 @@ extern "C" int samk_gemm_bf16(const void* A, int a_mn, long long lda, const void
   if (a_mn) rc = make_tmap_bf16_2d(&ta, A, K, M, lda, 64, BK);
   else rc = make_tmap_bf16_2d(&ta, A, M, K, lda, BK, BM);
   if (rc) return rc;
+  // CTA pair: 256 x 256 tile per two SMs; needs at least a pair of row tiles per column tile to be worth it
+  struct Spec { int am, bm, mask; };
+  static const Spec kSpecs[] = {{0, 0, M_QKV}, {0, 0, M_OUTPROJ}, {0, 0, M_FFN1}, {0, 0, M_BF16}, {0, 0, M_F32_BIAS},
+                                {0, 0, M_F32_BIAS_RES}, {0, 0, M_GELU}, {0, 0, M_F32}, {0, 1, M_BF16}, {0, 1, M_MULAUX},
+                                {0, 1, M_F32_RES}, {0, 1, M_F32}, {1, 1, M_ATOMIC}};   // keep in step with SAMK_SPEC below
+  bool spec = false;
+  for (const Spec& sp : kSpecs) spec = spec || (sp.am == (a_mn ? 1 : 0) && sp.bm == (b_mn ? 1 : 0) && sp.mask == flags);
+  const bool pair = gemm_2cta() && spec && bn == 256 && M >= 2 * BM;
   if (b_mn) rc = make_tmap_bf16_2d(&tb, B, K, N, ldb, 64, BK);
-  else rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, BK, bn);
+  else rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, BK, pair ? bn / 2 : bn);
   if (rc) return rc;
 
   // specialised epilogues run in the coalesced (shared-memory transposed) layout: measured faster than the
   // row-per-thread layout for every combination below (tools/gemm_bench.py)
 #define SAMK_SPEC(AM_, BM_, MASK_)                                                                        \
   if (a_mn == AM_ && b_mn == BM_ && flags == (MASK_)) {                                                    \
+    if (pair) return launch_tc<256, AM_, BM_, 2, MASK_, true>(ta, tb, ep, M, N, K, split_k, stream);      \
     if (bn == 256) return launch_tc<256, AM_, BM_, 1, MASK_, true>(ta, tb, ep, M, N, K, split_k, stream); \
     return launch_tc<128, AM_, BM_, 1, MASK_, true>(ta, tb, ep, M, N, K, split_k, stream);                \
   }
