@@ -28,6 +28,10 @@ int samk_version(void);
 const char* samk_last_error(void);
 /* number of SMs of the current device (grid sizing); <0 on error */
 int samk_sm_count(void);
+/* XORed into the key of every dropout stream of every kernel launched afterwards on this device (default 0).  Kernels
+ * replayed from a CUDA graph keep the (seed, offset) they were captured with; setting a new salt before each replay
+ * (stream-ordered, not itself captured) gives every replay fresh masks, identical in its forward and backward. */
+int samk_set_dropout_salt(unsigned long long salt, void* stream);
 
 /* ---- spatial graph ------------------------------------------------------------------------
  * Replaces build_graph_using_normalized_boxes (sam/spatial_utils.py:92-218) for a batch of box

@@ -398,3 +398,4 @@ int attn_simt_bwd(const samk_attn_params* p, cudaStream_t stream) {
 
 }  // namespace samk
 
+namespace samk { int set_drop_salt_attn_simt(unsigned long long salt, cudaStream_t stream) { return set_drop_salt_tu(salt, stream); } }

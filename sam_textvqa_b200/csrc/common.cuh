@@ -23,7 +23,17 @@ int check_launch(const char* what);
 // drop probability is p quantised to 2^-16 and the keep-scale is computed from the quantised value.
 // ---------------------------------------------------------------------------------------------
 constexpr int kPhiloxRounds = 7;
+// Per-replay salt of every dropout stream, XORed into the Philox key.  A CUDA-graph replay re-issues the kernels with
+// the (seed, offset) arguments they were captured with; samk_set_dropout_salt() (one tiny copy before each replay)
+// is what makes every replay draw new masks.  Forward and backward of one step see the same salt.  One copy of the
+// variable per translation unit (no relocatable device code), all set together by the entry point in api.cu.
+static __constant__ unsigned long long g_drop_salt = 0ull;
+static inline int set_drop_salt_tu(unsigned long long salt, cudaStream_t stream) {
+  return cudaMemcpyToSymbolAsync(g_drop_salt, &salt, sizeof(salt), 0, cudaMemcpyHostToDevice, stream) == cudaSuccess ? 0 : -2;
+}
+
 __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr_lo, uint32_t ctr_hi) {
+  seed ^= g_drop_salt;
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = ctr_hi, c3 = 0x5a17c0deu;
 #pragma unroll

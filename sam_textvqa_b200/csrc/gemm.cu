@@ -843,3 +843,5 @@ extern "C" int samk_gemm_bf16(const void* A, int a_mn, long long lda, const void
   }
 #undef SAMK_DYN
 }
+
+namespace samk { int set_drop_salt_gemm(unsigned long long salt, cudaStream_t stream) { return set_drop_salt_tu(salt, stream); } }

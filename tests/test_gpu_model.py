@@ -190,3 +190,43 @@ def test_cached_greedy_decoder_equals_reference_style_loop(monkeypatch):
         assert torch.equal(outs["cached"][1], outs["reference"][1])
         assert rel_err(outs["cached"][0], outs["reference"][0], live) < tol
         assert rel_err(outs["cached"][2], outs["reference"][2]) < tol
+
+
+def test_cuda_graph_replay_matches_eager_step_and_redraws_dropout(golden):
+    """GraphedTrainStep: (1) without dropout a replay reproduces the eager loss and gradients, also after the
+    weights were changed in place (the weight operand casts are part of the graph); (2) with dropout every replay
+    draws new masks (salt) and the gradients stay finite."""
+    from sam_textvqa_b200 import dp, ops
+    from sam_textvqa_b200.graph_step import GraphedTrainStep
+    g, _, _, _, _ = golden
+    for p_drop in (0.0, 0.1):
+        mmt2, tb2 = c3_config(layer_type_list=["n", "s"], mix_list=["none", "share3"], hidden_dropout_prob=p_drop,
+                              attention_probs_dropout_prob=p_drop, obj_drop=p_drop, ocr_drop=p_drop)
+        tb2 = dict(tb2, hidden_dropout_prob=p_drop, attention_probs_dropout_prob=p_drop)
+        state2 = synth.seeded_state(sam4c_state_shapes(mmt2, tb2, V), 0)
+        model = _model(mmt2, tb2, state2).train()
+        grads = dp.FlatGradBuffer(model.parameters())
+        batch = {k: v for k, v in golden_batch(g).items() if torch.is_tensor(v) or isinstance(v, dict)}
+        step = GraphedTrainStep(model, grads, batch)
+        try:
+            if p_drop == 0.0:
+                for it in range(2):
+                    loss_g = step.run().item()
+                    flat_g = grads.flat.clone()
+                    grads.zero()
+                    bd = dict(batch)
+                    bd["spatial_adj_matrices"] = dict(batch["spatial_adj_matrices"])
+                    loss_e = ops.bce_with_mask_loss(model(bd)["textvqa_scores"], bd["targets"], bd["train_loss_mask"])
+                    loss_e.backward()
+                    assert abs(loss_g - loss_e.item()) < 1e-4 * abs(loss_e.item())
+                    assert rel_err(flat_g, grads.flat) < 2e-3          # fp32 atomics: summation order differs
+                    with torch.no_grad():                               # an "optimizer step": the next replay must see it
+                        model.classifier.weight.mul_(1.5)
+                        model.mmt.encoder.spatial_layers[0].intermediate.dense.weight.add_(0.01)
+            else:
+                losses = [step.run().item() for _ in range(3)]
+                assert len(set(round(x, 6) for x in losses)) == 3, losses
+                assert torch.isfinite(grads.flat).all()
+        finally:
+            from sam_textvqa_b200._lib import check, lib, stream_ptr
+            check(lib().samk_set_dropout_salt(0, stream_ptr()), "salt")     # default state for the other tests

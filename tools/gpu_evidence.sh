@@ -27,7 +27,7 @@ launches)
   head -30 $OUT/${TAG}_launches_summary.txt; gzip -f $OUT/${TAG}_launches.csv ;;
 ncu)
   FULL="$NCU --set full --import-source on"
-  for shape in ffn1_fwd ffn2_fwd ffn2_wgrad ffn2_dgrad qkv_fwd; do
+  for shape in ffn1_fwd ffn2_wgrad ffn2_dgrad qkv_fwd; do
     REPS=1 timeout 300 $FULL -k regex:gemm_tc_kernel -s 3 -c 1 -f -o $OUT/${TAG}_ncu_gemm_$shape \
         python tools/gemm_bench.py $shape > $OUT/${TAG}_ncu_gemm_$shape.out 2>&1
   done
