@@ -58,19 +58,40 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // ---------------------------------------------------------------------------------------------
 // allow-bit matrix: words[b][hm][i][w], bit (j&31) of word j>>5 = query i may attend key j
 // ---------------------------------------------------------------------------------------------
+// One thread builds the word (32 keys) of one query row for ALL heads: the packed relation word of a pair already
+// holds every head's bit, so the pair is classified once (attn_mask.cuh rules) instead of once per head.
 __global__ void attn_build_mask_kernel(AttnMask m, int H, int Hm, int W, uint32_t* __restrict__ out) {
   __shared__ int sflag;
-  const int b = blockIdx.z, hm = blockIdx.y;
+  const int b = blockIdx.y;
   const bool any_valid = sample_any_valid(m, b, &sflag);
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= m.L * W) return;
   const int i = e / W, w = e % W;
-  uint32_t bits = 0;
+  const int si = seg_of(m, i);
+  uint32_t words[16];
+#pragma unroll
+  for (int h = 0; h < 16; ++h) words[h] = 0u;
   for (int k = 0; k < 32; ++k) {
     const int j = w * 32 + k;
-    if (j < m.L && attn_allowed(m, b, hm, i, j, any_valid)) bits |= 1u << k;
+    if (j >= m.L) break;
+    const int sj = seg_of(m, j);
+    const bool ok = (sj == 2) ? (si == 2 && j <= i) : (m.valid[(size_t)b * m.L + j] != 0);
+    uint32_t hb;                                   // bit h = head h may attend (i -> j)
+    if (!m.spatial) {
+      hb = ((!any_valid && si != 2) || ok) ? 0xFFFFu : 0u;
+    } else if ((m.quad_mask >> (3 * si + sj)) & 1u) {
+      hb = 0u;
+    } else if (si == 1 && sj == 1) {
+      hb = ok ? (uint32_t)m.rel[((size_t)b * m.A + (i - m.T)) * m.A + (j - m.T)] : 0u;
+    } else {
+      hb = ok ? 0xFFFFu : 0u;
+    }
+#pragma unroll
+    for (int h = 0; h < 16; ++h) words[h] |= ((hb >> h) & 1u) << k;
   }
-  out[(((size_t)b * Hm + hm) * m.L + i) * W + w] = bits;
+#pragma unroll
+  for (int h = 0; h < 16; ++h)
+    if (h < Hm) out[(((size_t)b * Hm + h) * m.L + i) * W + w] = words[h];
 }
 
 struct TcArgs {
@@ -1437,7 +1458,8 @@ int samk_attn_build_mask(const samk_attn_params* p, uint32_t* allow_bits, void* 
   m.quad_mask = p->spatial ? p->quadrant_mask : 0u; m.spatial = p->spatial ? 1 : 0;
   if (!p->B || !m.L) return SAMK_OK;
   const int W = (m.L + 31) / 32, Hm = p->spatial ? p->H : 1;
-  dim3 grid((m.L * W + 127) / 128, Hm, p->B);
+  if (Hm > 16) { set_error("samk_attn_build_mask: at most 16 heads (relation words are 16 bits)"); return SAMK_ERR_UNSUPPORTED; }
+  dim3 grid((m.L * W + 127) / 128, p->B);
   attn_build_mask_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(m, p->H, Hm, W, allow_bits);
   return check_launch("samk_attn_build_mask");
 }

@@ -251,23 +251,30 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
   }
 }
 
-// out_k[c] += sum over blocks of partials[blk][k][c]; block = 32 columns x 8 block-lanes
-__global__ void ln_bwd_finalize_kernel(const float* __restrict__ partials, int nblk, int cols, float* dgamma,
-                                       float* dbeta, float* dbias) {
-  __shared__ float red[8][33];
+// out_k[c] += sum over blocks of partials[blk][k][c]; block = 32 columns x 32 block-lanes (latency-bound: the more
+// independent loads in flight the better)
+__global__ void __launch_bounds__(1024)
+ln_bwd_finalize_kernel(const float* __restrict__ partials, int nblk, int cols, float* dgamma, float* dbeta, float* dbias) {
+  __shared__ float red[32][33];
   const int k = blockIdx.y;
   float* out = k == 0 ? dgamma : (k == 1 ? dbeta : dbias);
   if (!out) return;
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
-  float t = 0.f;
-  if (c < cols)
-    for (int b = g; b < nblk; b += 8) t += partials[((size_t)b * 3 + k) * cols + c];
-  red[g][threadIdx.x & 31] = t;
+  float t0 = 0.f, t1 = 0.f;
+  if (c < cols) {
+    int b = g;
+    for (; b + 32 < nblk; b += 64) {
+      t0 += partials[((size_t)b * 3 + k) * cols + c];
+      t1 += partials[((size_t)(b + 32) * 3 + k) * cols + c];
+    }
+    if (b < nblk) t0 += partials[((size_t)b * 3 + k) * cols + c];
+  }
+  red[g][threadIdx.x & 31] = t0 + t1;
   __syncthreads();
   if (g == 0 && c < cols) {
     float u = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) u += red[w][threadIdx.x];
+    for (int w = 0; w < 32; ++w) u += red[w][threadIdx.x];
     out[c] += u;
   }
 }
@@ -703,28 +710,49 @@ __global__ void ptr_scores_bwd_kernel(const float* __restrict__ ds, long long ld
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nq = B * D, nk = B * R;
   if (warp >= nq + nk) return;
+  // all column chunks of the row are accumulated together: kMaxVec independent loads in flight per step of the
+  // (short, latency-bound) contraction loop
+  float4 acc[kMaxVec];
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (warp < nq) {
     const int b = warp / D;
     const float* dsr = ds + (size_t)warp * ldds + col_off;
-    for (int c = lane * 4; c < dq; c += 128) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = 0; r < R; ++r) {
-        float w = dsr[r] * inv_sqrt;
-        float4 kv = *reinterpret_cast<const float4*>(k + ((size_t)b * R + r) * dq + c);
-        acc.x += w * kv.x; acc.y += w * kv.y; acc.z += w * kv.z; acc.w += w * kv.w;
+    for (int r = 0; r < R; ++r) {
+      const float w = dsr[r] * inv_sqrt;
+      const float* kr = k + ((size_t)b * R + r) * dq;
+#pragma unroll
+      for (int i = 0; i < kMaxVec; ++i) {
+        const int c = 4 * (lane + 32 * i);
+        if (c < dq) {
+          const float4 kv = *reinterpret_cast<const float4*>(kr + c);
+          acc[i].x += w * kv.x; acc[i].y += w * kv.y; acc[i].z += w * kv.z; acc[i].w += w * kv.w;
+        }
       }
-      *reinterpret_cast<float4*>(dq_ + (size_t)warp * dq + c) = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int c = 4 * (lane + 32 * i);
+      if (c < dq) *reinterpret_cast<float4*>(dq_ + (size_t)warp * dq + c) = acc[i];
     }
   } else {
     const int row = warp - nq, b = row / R, r = row % R;
-    for (int c = lane * 4; c < dq; c += 128) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int t = 0; t < D; ++t) {
-        float w = ds[((size_t)b * D + t) * ldds + col_off + r] * inv_sqrt;
-        float4 qv = *reinterpret_cast<const float4*>(q + ((size_t)b * D + t) * dq + c);
-        acc.x += w * qv.x; acc.y += w * qv.y; acc.z += w * qv.z; acc.w += w * qv.w;
+    for (int t = 0; t < D; ++t) {
+      const float w = ds[((size_t)b * D + t) * ldds + col_off + r] * inv_sqrt;
+      const float* qr = q + ((size_t)b * D + t) * dq;
+#pragma unroll
+      for (int i = 0; i < kMaxVec; ++i) {
+        const int c = 4 * (lane + 32 * i);
+        if (c < dq) {
+          const float4 qv = *reinterpret_cast<const float4*>(qr + c);
+          acc[i].x += w * qv.x; acc[i].y += w * qv.y; acc[i].z += w * qv.z; acc[i].w += w * qv.w;
+        }
       }
-      *reinterpret_cast<float4*>(dk_ + (size_t)row * dq + c) = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int c = 4 * (lane + 32 * i);
+      if (c < dq) *reinterpret_cast<float4*>(dk_ + (size_t)row * dq + c) = acc[i];
     }
   }
 }
@@ -833,7 +861,7 @@ int samk_layernorm_bwd(const float* dy, const float* x, const float* gamma, floa
       drop_keep_scale(drop_p), seed, offset, dgamma, dbeta, dbias, partials, rows, cols);
   int rc = check_launch(__func__);
   if (rc || !partials) return rc;
-  ln_bwd_finalize_kernel<<<dim3((cols + 31) / 32, 3), 256, 0, (cudaStream_t)stream>>>(partials, grid, cols, dgamma, dbeta, dbias);
+  ln_bwd_finalize_kernel<<<dim3((cols + 31) / 32, 3), 1024, 0, (cudaStream_t)stream>>>(partials, grid, cols, dgamma, dbeta, dbias);
   return check_launch(__func__);
 }
 
@@ -962,7 +990,7 @@ int samk_ptr_scores_fwd(const float* q, const float* k, const long long* ocr_mas
 
 int samk_ptr_scores_bwd(const float* dscores, long long ldds, int col_off, const float* q, const float* k, float* dq_,
                         float* dk_, int B, int D, int R, int dq, void* stream) {
-  SAMK_REQUIRE(dscores && q && k && dq_ && dk_ && dq % 4 == 0, "bad argument");
+  SAMK_REQUIRE(dscores && q && k && dq_ && dk_ && dq % 4 == 0 && dq <= 1024, "bad argument (ptr_query_size <= 1024)");
   long long warps = (long long)B * (D + R);
   if (!warps) return SAMK_OK;
   ptr_scores_bwd_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(dscores, ldds, col_off, q, k, dq_, dk_, B, D, R, dq, 1.0f / sqrtf((float)dq));
