@@ -342,8 +342,8 @@ def run_samk(args):
                                "hbm_frac": rows[0][1] / (ms_k * 1e-3) / 1e9 / peak_gbs,
                                "dense_equiv_TFLOPs": rows[0][2] / (ms_k * 1e-3) / 1e12}
     attention["peak_GBs"] = peak_gbs
-    attention["ncu"] = ("profiles/r01g_ncu_summary.txt: fwd 91 us, DRAM 108+14 MB per launch, tensor pipe 10.9 %; "
-                        "bwd 176 us, DRAM 153+73 MB, tensor pipe 15.5 % (L=182 is HBM/ALU-bound, SURVEY 8d)")
+    attention["ncu"] = ("profiles/r01i_ncu_summary.txt: fwd 91 us, DRAM 108+15 MB per launch, tensor pipe 10.9 %; "
+                        "bwd 176 us, DRAM 153+72 MB, tensor pipe 15.5 % (L=182 is HBM/ALU-bound, SURVEY 8d)")
 
     if rank != 0:
         if world > 1:
@@ -368,8 +368,9 @@ def run_samk(args):
                      "traffic": None, "peak_source": peak_src + " (sustained bf16)",
                      "gemm_ms_per_step": g_ms, "gemm_share_of_step": g_ms / ms if ms > 0 else None,
                      "step_flop_frac_of_peak": value / world * FLOP_PER_SAMPLE / (peak_tf * 1e12),
-                     "traffic_note": "per-shape DRAM bytes from ncu --set full are in profiles/r01g_ncu_summary.txt "
-                                     "(e.g. FFN2 wgrad 337+10 MB vs 322 MB algorithmic)"},
+                     "traffic_note": "aggregate over all GEMM shapes of the step, so no single per-launch figure; per-shape "
+                                     "DRAM bytes from ncu --set full are in profiles/r01i_ncu_summary.txt "
+                                     "(e.g. FFN2 wgrad 342+9 MB vs 322 MB algorithmic)"},
         "attention": attention,
     }
     if world == 1 and not args.no_cpu_baseline:
