@@ -718,6 +718,279 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
+// forward v3: one query tile per CTA, TWO CTAs per SM.  Same arithmetic and TMEM use as v2 per tile (S/P 192 columns +
+// O 64 columns = 256 columns per CTA), but the two resident CTAs are in different phases of their items, so one
+// CTA's softmax fills the issue slots while the other waits for its TMA / MMA / barriers.  Work items are ordered
+// full tiles first, the short last tile of every sample afterwards (static round-robin then balances the CTAs).
+//   warp 0 TMA producer (Q double-buffered, K/V single stage), warp 1 MMA issuer, warps 2-9 softmax
+//   (TMEM lane quarter = warp % 4, key half = (warp-2)/4).
+// ---------------------------------------------------------------------------------------------
+template <int KVT> struct Fwd3Cfg {
+  static constexpr int kKVOff = 2 * 16384;                  // after the two Q stages
+  static constexpr int kKVBytes = 2 * KVT * 128;            // K tile + V tile
+  static constexpr int kBarOff = kKVOff + kKVBytes;
+  static constexpr int kXchOff = kBarOff + 256;             // [kind][slot][half][128] floats
+  static constexpr int kXchBytes = 2 * 2 * 2 * 128 * 4;
+  static constexpr int kOutOff = kXchOff + kXchBytes;       // per softmax warp: 32 rows x 32 bf16
+  static constexpr int kSmem = kOutOff + 8 * 2048 + 1024;
+};
+constexpr int kFwd3Threads = 64 + 8 * 32;
+
+template <int KVT>
+__global__ void __launch_bounds__(kFwd3Threads, 2)
+attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const TcArgs a,
+                 int n_bh, int n_items, uint32_t magic_bh, uint32_t magic_h) {
+  using Cfg = Fwd3Cfg<KVT>;
+  constexpr int NC = KVT / 32;                          // 16-key chunks per thread (its half of the key tile)
+  extern __shared__ uint8_t smem_raw4[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw4) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // [2][128 x 64]
+  uint8_t* sKV = smem + Cfg::kKVOff;                    // K | V
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* q_full = bars;            // [2]
+  uint64_t* q_empty = bars + 2;       // [2]
+  uint64_t* kv_full = bars + 4;
+  uint64_t* kv_empty = bars + 5;
+  uint64_t* s_full = bars + 6;
+  uint64_t* p_ready = bars + 7;
+  uint64_t* o_done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  float* xch = reinterpret_cast<float*>(smem + Cfg::kXchOff);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = a.L, H = a.H;
+  const int n_kv = (L + KVT - 1) / KVT;
+  const int n_qt = (L + 127) / 128;
+
+  if (tid == 0) {
+    ptx::prefetch_tensormap(&tmQ); ptx::prefetch_tensormap(&tmKV);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&q_full[i], 1); ptx::mbar_init(&q_empty[i], 1); }
+    ptx::mbar_init(kv_full, 1); ptx::mbar_init(kv_empty, 1);
+    ptx::mbar_init(s_full, 1); ptx::mbar_init(p_ready, 8); ptx::mbar_init(o_done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<256>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // item -> (query tile, b, h): tiles ascending (the short last tile of every sample comes last); that tile is loaded
+  // shifted up on odd iterations so its rows alternate between the lower and the upper TMEM lane quarters
+  auto decode = [&](int item, int iter, int& b, int& h, int& q_start, int& q_lo) {
+    const int qi = (int)__umulhi((uint32_t)item, magic_bh);       // exact for item < 2^32 / n_bh
+    const int bh = item - qi * n_bh;
+    const int qt = a.q_tile0 + qi;
+    b = (int)__umulhi((uint32_t)bh, magic_h);
+    h = bh - b * H;
+    q_lo = qt * 128;
+    q_start = qt * 128;
+    if ((iter & 1) && qt == n_qt - 1 && L >= 128 && L - qt * 128 <= 64) q_start = L - 128;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int iter = 0; uint32_t kvc = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++iter) {
+        int b, h, q_start, q_lo;
+        decode(item, iter, b, h, q_start, q_lo);
+        const int qs = iter & 1;
+        mbar_wait_backoff(&q_empty[qs], ((iter >> 1) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&q_full[qs], 16384);
+        ptx::tma_load_2d(sQ + qs * 16384, &tmQ, &q_full[qs], h * TDH, b * L + q_start);
+        for (int t = 0; t < n_kv; ++t, ++kvc) {
+          mbar_wait_backoff(kv_empty, (kvc & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(kv_full, Cfg::kKVBytes);
+          ptx::tma_load_2d(sKV, &tmKV, kv_full, (H + h) * TDH, b * L + t * KVT);
+          ptx::tma_load_2d(sKV + KVT * 128, &tmKV, kv_full, (2 * H + h) * TDH, b * L + t * KVT);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp converged, tcgen05 under the elected lane) =====================
+    constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, KVT, 0, 0);
+    constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, 64, 0, 1);
+    constexpr uint64_t kStepK = 32 >> 4, kStepMN = 2048 >> 4;
+    int iter = 0; uint32_t kvc = 0, pc = 0;
+    const uint32_t sk = ptx::smem_u32(sKV), sv = sk + KVT * 128;
+    const uint64_t dk = ptx::make_smem_desc_sw128(sk, 16, 1024);
+    const uint64_t dv = ptx::make_smem_desc_sw128(sv, 16384, 1024);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++iter) {
+      const int qs = iter & 1;
+      mbar_wait_backoff(&q_full[qs], (iter >> 1) & 1);
+      const uint64_t dq = ptx::make_smem_desc_sw128(ptx::smem_u32(sQ + qs * 16384), 16, 1024);
+      for (int t = 0; t < n_kv; ++t, ++kvc) {
+        mbar_wait_backoff(kv_full, kvc & 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem, dq + k * kStepK, dk + k * kStepK, idesc_s, k > 0);
+          ptx::umma_commit(s_full);
+          if (t == n_kv - 1) ptx::umma_commit(&q_empty[qs]);     // all S products of this item issued
+        }
+        __syncwarp();
+        ptx::mbar_wait(p_ready, pc & 1); ++pc;
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < KVT / 16; ++k)   // P (packed bf16) sits at the start of each column half of S
+            ptx::umma_f16_ts(tmem + 192, tmem + (k < KVT / 32 ? k * 8 : KVT / 2 + (k - KVT / 32) * 8), dv + k * kStepMN, idesc_o,
+                             (t > 0 || k > 0) ? 1u : 0u);
+          ptx::umma_commit(o_done);
+          ptx::umma_commit(kv_empty);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== softmax warps =====================
+    const int hf = (warp - 2) >> 2, quarter = warp & 3;
+    const int lrow = quarter * 32 + lane;
+    const uint32_t t_s = tmem + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t t_o = t_s + 192 + hf * 32;
+    const uint32_t th16 = a.drop_thresh << 16;
+    const bool drop = a.drop_thresh != 0;
+    const float sl2 = a.scale_log2;
+    const uint32_t ngrp = (uint32_t)((L + 7) >> 3);
+    uint32_t sc = 0, oc = 0, xc = 0;
+    int iter = 0;
+    uint32_t aw_nx[NC / 2];
+    auto fetch_allow = [&](int item_, int iter_, int t_) {
+#pragma unroll
+      for (int c = 0; c < NC / 2; ++c) aw_nx[c] = 0u;
+      if (item_ >= n_items) return;
+      int b_, h_, st, lo;
+      decode(item_, iter_, b_, h_, st, lo);
+      const int row_ = st + lrow;
+      if (row_ < lo || row_ >= L) return;
+      const uint32_t* ar = a.allow + (((size_t)b_ * a.Hm + (a.Hm == 1 ? 0 : h_)) * L + row_) * a.W;
+      const int w0 = (t_ * KVT + hf * (KVT / 2)) >> 5;
+#pragma unroll
+      for (int c = 0; c < NC / 2; ++c) if (w0 + c < a.W) aw_nx[c] = ld_allow(ar + w0 + c);
+    };
+    fetch_allow(blockIdx.x, 0, 0);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++iter) {
+      int b, h, my_start, my_lo;
+      decode(item, iter, b, h, my_start, my_lo);
+      const int row = my_start + lrow;
+      const bool active = row >= my_lo && row < L;
+      const bool warp_active = __any_sync(0xffffffffu, active);
+      const uint64_t drow = ((uint64_t)(b * H + h) * L + (uint64_t)row) * ngrp;
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int t = 0; t < n_kv; ++t) {
+        const int k0 = t * KVT + hf * (KVT / 2);
+        uint32_t aw_t[NC / 2];
+#pragma unroll
+        for (int c = 0; c < NC / 2; ++c) aw_t[c] = aw_nx[c];
+        if (t + 1 < n_kv) fetch_allow(item, iter, t + 1); else fetch_allow(item + gridDim.x, iter + 1, 0);
+        ptx::mbar_wait(s_full, sc & 1); ++sc;
+        ptx::tc_fence_after();
+        const uint32_t t_sh = t_s + hf * (KVT / 2);
+        uint32_t rA[16], rB[16];
+        float tmax = -INFINITY;
+        if (warp_active) {
+          ptx::tmem_ld_32x16(t_sh, rA);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            if (c + 1 < NC) ptx::tmem_ld_32x16(t_sh + (c + 1) * 16, (c & 1) ? rA : rB);
+            tmax = masked_max16((c & 1) ? rB : rA, aw_t[c >> 1] >> (16 * (c & 1)), tmax);
+            if (c + 1 < NC) ptx::tmem_ld_wait();
+          }
+          ptx::tmem_ld_32x16(t_sh, rA);            // first chunk of pass 2, in flight during the exchange
+        }
+        float* xm = xch + ((0 * 2 + (xc & 1)) * 2) * 128;
+        xm[hf * 128 + lrow] = tmax;
+        named_bar_sync(1, 256);
+        tmax = fmaxf(tmax, xm[(hf ^ 1) * 128 + lrow]);
+        ++xc;
+        if (warp_active) {
+          tmax *= sl2;
+          const float m_new = fmaxf(m_run, tmax);
+          const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+          if (t > 0) {
+            ptx::tmem_ld_wait();
+            ptx::mbar_wait(o_done, oc & 1); ++oc;
+            ptx::tc_fence_after();
+            const float corr = (m_run == -INFINITY) ? 1.f : fast_exp2(m_run - m_use);
+            l_run *= corr;
+            if (__any_sync(0xffffffffu, corr != 1.f)) {
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                ptx::tmem_ld_32x16(t_o + c * 16, rB);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) rB[i] = __float_as_uint(__uint_as_float(rB[i]) * corr);
+                tmem_st_32x16(t_o + c * 16, rB);
+              }
+            }
+          }
+          m_run = m_new;
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            if (c + 1 < NC) ptx::tmem_ld_32x16(t_sh + (c + 1) * 16, (c & 1) ? rA : rB);
+            uint32_t pk[8];
+            l_run += softmax_chunk16((c & 1) ? rB : rA, aw_t[c >> 1] >> (16 * (c & 1)), sl2, m_use, drop, a.seed,
+                                     (uint32_t)a.off, drow + (uint64_t)((k0 >> 3) + c * 2), th16, pk);
+            if (c + 1 < NC) ptx::tmem_ld_wait();
+            tmem_st_32x8(t_sh + c * 8, pk);
+          }
+          tmem_st_wait();
+        } else if (t > 0) {
+          ++oc;
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(p_ready);
+      }
+      // ---- epilogue
+      float* xl = xch + ((1 * 2 + (iter & 1)) * 2) * 128;
+      xl[hf * 128 + lrow] = l_run;
+      named_bar_sync(1, 256);
+      l_run += xl[(hf ^ 1) * 128 + lrow];
+      if (warp_active) {
+        ptx::mbar_wait(o_done, oc & 1); ++oc;
+        ptx::tc_fence_after();
+        const float inv = l_run > 0.f ? a.drop_scale / l_run : 0.f;
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(t_o, r);
+        ptx::tmem_ld_wait();
+        const uint32_t st = ptx::smem_u32(smem + Cfg::kOutOff) + (warp - 2) * 2048;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = 8 * j;
+          sts128u(st + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4),
+                  make_uint4(pack_bf16(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
+                             pack_bf16(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
+                             pack_bf16(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
+                             pack_bf16(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv)));
+        }
+        __syncwarp();
+        const int row_w = my_start + quarter * 32;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + (lane >> 2), cj = lane & 3, orow = row_w + rr;
+          const uint4 v = lds128u(st + rr * 64 + ((cj ^ ((rr >> 1) & 3)) << 4));
+          if (orow >= my_lo && orow < L)
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.ctx) + ((size_t)b * L + orow) * (size_t)(H * TDH) + h * TDH +
+                                      hf * 32 + cj * 8) = v;
+        }
+        __syncwarp();
+        if (active && hf == 0) a.lse[((size_t)b * H + h) * L + row] = l_run > 0.f ? (m_run + log2f(l_run)) * kLn2 : INFINITY;
+      } else {
+        ++oc;
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc<256>(tmem); }
+}
+
+// ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
 // delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]
@@ -1352,11 +1625,33 @@ static int launch_fwd2(const samk_attn_params* p, const TcArgs& a, cudaStream_t 
   return check_launch("samk_attn_fwd(tc v2)");
 }
 
+template <int KVT>
+static int launch_fwd3(const samk_attn_params* p, const TcArgs& a, cudaStream_t stream) {
+  const long long rows = (long long)a.B * a.L;
+  const int hd3 = 3 * a.H * TDH;
+  CUtensorMap tq, tkv;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&tq, p->qkv, rows, hd3, hd3, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tkv, p->qkv, rows, hd3, hd3, 64, KVT))) return rc;
+  if ((rc = set_smem(attn_fwd3_kernel<KVT>, Fwd3Cfg<KVT>::kSmem))) return rc;
+  const int n_qt = (a.L + 127) / 128;
+  const int n_bh = a.B * a.H;
+  const long long n_items = (long long)(n_qt - a.q_tile0) * n_bh;
+  if (n_items <= 0) return SAMK_OK;
+  if (n_items >= (1ll << 24)) { set_error("samk_attn_fwd: too many work items"); return SAMK_ERR_UNSUPPORTED; }
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  const int grid = (int)(n_items < 2 * sms ? n_items : 2 * sms);
+  const uint32_t magic_bh = (uint32_t)(((1ull << 32) + n_bh - 1) / n_bh), magic_h = (uint32_t)(((1ull << 32) + a.H - 1) / a.H);
+  attn_fwd3_kernel<KVT><<<grid, kFwd3Threads, Fwd3Cfg<KVT>::kSmem, stream>>>(tq, tkv, a, n_bh, (int)n_items, magic_bh, magic_h);
+  return check_launch("samk_attn_fwd(tc v3)");
+}
+
 static int attn_fwd_version() {
   static int v = -1;
   if (v < 0) {
     const char* s = getenv("SAMK_ATTN_FWD_V");
-    v = (s && s[0] == '1') ? 1 : 2;
+    v = (s && s[0] >= '1' && s[0] <= '3') ? s[0] - '0' : 0;      // 0 = pick by sequence length
   }
   return v;
 }
@@ -1367,7 +1662,14 @@ int attn_tc_fwd(const samk_attn_params* p, cudaStream_t stream) {
   if (rc) return rc;
   if (!p->qkv || !p->ctx || !p->lse) { set_error("samk_attn_fwd: null pointer"); return SAMK_ERR_ARG; }
   if (!a.B || !a.L) return SAMK_OK;
-  if (attn_fwd_version() == 2) {
+  // measured (tools/attn_bench.py --sweep): two CTAs per SM win up to ~500 keys (L=118: 31 -> 21 us, 182: 90 -> 80,
+  // 268: 162 -> 118), the two-tile CTA with its 3-stage K/V ring wins for long sequences (1036: 958 vs 1028 us)
+  const int ver = attn_fwd_version() ? attn_fwd_version() : (a.L <= 512 ? 3 : 2);
+  if (ver == 3) {
+    if (a.L > 128 && a.L <= 192) return launch_fwd3<192>(p, a, stream);
+    return launch_fwd3<128>(p, a, stream);
+  }
+  if (ver == 2) {
     if (a.L > 128 && a.L <= 192) return launch_fwd2<192>(p, a, stream);
     return launch_fwd2<128>(p, a, stream);
   }
