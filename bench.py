@@ -173,7 +173,9 @@ def run_samk(args):
     # second partial wave.  Default: one all-reduce of the flat buffer after backward (~0.9 ms exposed).
     overlap = world > 1 and os.environ.get("SAMK_DP_OVERLAP", "0") == "1"
     if overlap:
-        grads.enable_overlap()
+        # one early bucket: everything that is final when the MMT stack's backward ends (~half of the bytes) goes
+        # out while the TextBERT backward runs (its GEMMs have fewer tiles than SMs, so NCCL's CTAs cost nothing)
+        grads.enable_overlap(bucket_bytes=int(os.environ.get("SAMK_DP_BUCKET_MB", "160")) << 20)
     B = args.batch
 
     def graph_fn(boxes):
@@ -217,7 +219,7 @@ def run_samk(args):
             from sam_textvqa_b200.graph_step import GraphedTrainStep
             ex = dict(resident)
             ex["spatial_adj_matrices"] = {"3": resident_adj}
-            graphed = GraphedTrainStep(model, grads, ex)
+            graphed = GraphedTrainStep(model, grads, ex, allreduce="overlap" if overlap else None)
         except Exception as exc:                      # fall back loudly, never silently
             print("bench: CUDA-graph capture failed (%r); running the eager step" % (exc,), file=sys.stderr, flush=True)
             graphed = None
@@ -230,9 +232,7 @@ def run_samk(args):
             graphed.load(inputs)
             graphed.load({"spatial_adj_matrices": {"3": adj_dev}})
         loss = graphed.run()
-        if overlap:
-            pass
-        if world > 1:
+        if world > 1 and not overlap:
             grads.all_reduce()
         return loss
 

@@ -20,10 +20,13 @@ from ._lib import check, lib, stream_ptr
 
 
 class GraphedTrainStep(object):
-    def __init__(self, model, grads, example_batch, loss_fn=None, warmup=3):
+    def __init__(self, model, grads, example_batch, loss_fn=None, warmup=3, allreduce=None):
         """example_batch: dict of device tensors (shapes and dtypes of every later batch); may contain the
         'spatial_adj_matrices' dict.  loss_fn(scores, batch) -> scalar; default = masked BCE on targets."""
-        self.model, self.grads = model, grads
+        # allreduce: None = exchange outside (caller), "overlap" = capture the bucketed NCCL all-reduce of
+        # dp.FlatGradBuffer.enable_overlap() inside the graph as a parallel branch (first replay-able after the
+        # learning step that the eager warm-up provides)
+        self.model, self.grads, self.allreduce = model, grads, allreduce
         self.loss_fn = loss_fn or (lambda scores, b: ops.bce_with_mask_loss(scores, b["targets"], b["train_loss_mask"]))
         self.device = next(model.parameters()).device
         self.static = self._clone(example_batch)
@@ -59,12 +62,16 @@ class GraphedTrainStep(object):
 
     def _eager_step(self):
         self.grads.zero()
+        if self.allreduce == "overlap":
+            self.grads.begin_step()
         bd = dict(self.static)
         if isinstance(bd.get("spatial_adj_matrices"), dict):
             bd["spatial_adj_matrices"] = dict(bd["spatial_adj_matrices"])
         scores = self.model(bd)["textvqa_scores"]
         loss = self.loss_fn(scores, bd)
         loss.backward()
+        if self.allreduce == "overlap":
+            self.grads.finish_step()
         return loss
 
     def load(self, batch, non_blocking=True):
