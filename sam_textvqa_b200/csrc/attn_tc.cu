@@ -1063,26 +1063,28 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 
   for (int t = 0; t < n_q; ++t) {
     const int i0 = t * 128;
-    if (tid == 0) {
-      ptx::mbar_arrive_expect_tx(q_bar, 2 * 16384);
-      ptx::tma_load_2d(sQ, &tmQKV, q_bar, h * TDH, b * L + i0);
-      ptx::tma_load_2d(sDO, &tmDO, q_bar, h * TDH, b * L + i0);
+    if (warp == 0) {
+      // warp 0 converged: descriptors in uniform registers, tcgen05 / TMA under the elected lane (see gemm.cu)
+      constexpr uint64_t kStepK = 32 >> 4;
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(q_bar, 2 * 16384);
+        ptx::tma_load_2d(sQ, &tmQKV, q_bar, h * TDH, b * L + i0);
+        ptx::tma_load_2d(sDO, &tmDO, q_bar, h * TDH, b * L + i0);
+      }
+      __syncwarp();
       if (t == 0) ptx::mbar_wait(kv_bar, 0);
       ptx::mbar_wait(q_bar, t & 1);
       ptx::tc_fence_after();
+      const uint64_t dq = ptx::make_smem_desc_sw128(ptx::smem_u32(sQ), 16, 1024), dk = ptx::make_smem_desc_sw128(ptx::smem_u32(sK), 16, 1024);
+      const uint64_t dg = ptx::make_smem_desc_sw128(ptx::smem_u32(sDO), 16, 1024), dv = ptx::make_smem_desc_sw128(ptx::smem_u32(sV), 16, 1024);
+      if (ptx::elect_one()) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint64_t dq = ptx::make_smem_desc_sw128(ptx::smem_u32(sQ) + k * 32, 16, 1024);
-        const uint64_t dk = ptx::make_smem_desc_sw128(ptx::smem_u32(sK) + k * 32, 16, 1024);
-        ptx::umma_f16(tmem + kScol, dq, dk, idesc_s, k > 0);
-      }
+        for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem + kScol, dq + k * kStepK, dk + k * kStepK, idesc_s, k > 0);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint64_t dg = ptx::make_smem_desc_sw128(ptx::smem_u32(sDO) + k * 32, 16, 1024);
-        const uint64_t dv = ptx::make_smem_desc_sw128(ptx::smem_u32(sV) + k * 32, 16, 1024);
-        ptx::umma_f16(tmem + kDPcol, dg, dv, idesc_s, k > 0);
+        for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem + kDPcol, dg + k * kStepK, dv + k * kStepK, idesc_s, k > 0);
+        ptx::umma_commit(s_bar);
       }
-      ptx::umma_commit(s_bar);
+      __syncwarp();
     }
     // per-row scalars and allow words first: their global-load latency hides behind TMA + MMA
     const int i = i0 + r;
@@ -1117,29 +1119,26 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     ptx::tc_fence_before();
     ptx::fence_proxy_async_smem();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       ptx::tc_fence_after();
-      // dV[j,d] += sum_i P[i,j] dO[i,d] ; dK[j,d] += sum_i dS[i,j] Q[i,d]   (contraction over the 128 rows)
+      constexpr uint64_t kStepK = 32 >> 4, kStepMN = 2048 >> 4;
+      const uint64_t ap = ptx::make_smem_desc_sw128(ptx::smem_u32(sP), 16384, 1024), bg = ptx::make_smem_desc_sw128(ptx::smem_u32(sDO), 16384, 1024);
+      const uint64_t as_t = ptx::make_smem_desc_sw128(ptx::smem_u32(sDS), 16384, 1024), bq = ptx::make_smem_desc_sw128(ptx::smem_u32(sQ), 16384, 1024);
+      const uint64_t as0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sDS), 16, 1024), as1 = ptx::make_smem_desc_sw128(ptx::smem_u32(sDS) + 16384, 16, 1024);
+      const uint64_t bk = ptx::make_smem_desc_sw128(ptx::smem_u32(sK), 16384, 1024);
+      if (ptx::elect_one()) {
+        // dV[j,d] += sum_i P[i,j] dO[i,d] ; dK[j,d] += sum_i dS[i,j] Q[i,d]   (contraction over the 128 rows)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint64_t ap = ptx::make_smem_desc_sw128(ptx::smem_u32(sP) + k * 2048, 16384, 1024);
-        const uint64_t bg = ptx::make_smem_desc_sw128(ptx::smem_u32(sDO) + k * 2048, 16384, 1024);
-        ptx::umma_f16(tmem + kDVcol, ap, bg, idesc_kv, (t > 0 || k > 0) ? 1u : 0u);
-      }
+        for (int k = 0; k < 8; ++k) ptx::umma_f16(tmem + kDVcol, ap + k * kStepMN, bg + k * kStepMN, idesc_kv, (t > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint64_t as = ptx::make_smem_desc_sw128(ptx::smem_u32(sDS) + k * 2048, 16384, 1024);
-        const uint64_t bq = ptx::make_smem_desc_sw128(ptx::smem_u32(sQ) + k * 2048, 16384, 1024);
-        ptx::umma_f16(tmem + kDKcol, as, bq, idesc_kv, (t > 0 || k > 0) ? 1u : 0u);
-      }
-      // dQ[i,d] = sum_j dS[i,j] K[j,d]   (contraction over the 128 keys of this CTA)
+        for (int k = 0; k < 8; ++k) ptx::umma_f16(tmem + kDKcol, as_t + k * kStepMN, bq + k * kStepMN, idesc_kv, (t > 0 || k > 0) ? 1u : 0u);
+        // dQ[i,d] = sum_j dS[i,j] K[j,d]   (contraction over the 128 keys of this CTA)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint64_t as = ptx::make_smem_desc_sw128(ptx::smem_u32(sDS) + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-        const uint64_t bk = ptx::make_smem_desc_sw128(ptx::smem_u32(sK) + k * 2048, 16384, 1024);
-        ptx::umma_f16(tmem + kDQcol, as, bk, idesc_q, k > 0);
+        for (int k = 0; k < 8; ++k)
+          ptx::umma_f16(tmem + kDQcol, (k < 4 ? as0 : as1) + (k & 3) * kStepK, bk + k * kStepMN, idesc_q, k > 0);
+        ptx::umma_commit(g_bar);
       }
-      ptx::umma_commit(g_bar);
+      __syncwarp();
     }
     ptx::mbar_wait(g_bar, t & 1);
     ptx::tc_fence_after();
