@@ -336,7 +336,7 @@ class MMT(nn.Module):
 
         def rel_lookup(key):
             if key not in rel_cache:
-                rel_cache[key] = pack_relation_bits(batch_dict["spatial_adj_matrices"][key], dev)
+                rel_cache[key] = _relation_bits(batch_dict, key, dev)
             bits = rel_cache[key]
             if bits.shape[1] != O + R:
                 raise ValueError("spatial_adj_matrices[%r] is %d x %d, expected %d entities"
@@ -350,6 +350,26 @@ class MMT(nn.Module):
             "mmt_ocr_output": seq[:, T + O:T + O + R],
             "mmt_dec_output": seq[:, -D:],
         }
+
+
+def _relation_bits(batch_dict, key, dev):
+    """Packed head bits uint16 [B,A,A] for relation-matrix key "1"/"3"/"5"/"7"/"9".
+
+    Reference contract: `spatial_adj_matrices[key]` = int8 [B,A,A,12] prepared by the dataset (hours of CPU graph
+    building + a pickle cache, sam/datasets/textvqa_dataset.py:228-280, 373-409).  On-device batch preparation
+    (SURVEY 8f): when the dict (or the key) is absent the graph is built here, on the GPU, from the padded boxes the
+    batch already carries -- [pad_obj_bboxes ; pad_ocr_bboxes][..., :4], exactly the array process_spatials feeds
+    to the graph builder -- bit-identical to the reference builder + context expansion (tests/test_gpu_graph.py)."""
+    adj = batch_dict.get("spatial_adj_matrices")
+    if isinstance(adj, dict) and key in adj:
+        return pack_relation_bits(adj[key], dev)
+    if "pad_obj_bboxes" not in batch_dict or "pad_ocr_bboxes" not in batch_dict:
+        raise KeyError("spatial_adj_matrices[%r] missing and no pad_obj_bboxes / pad_ocr_bboxes to build it from" % key)
+    from . import spatial_utils
+    boxes = torch.cat([batch_dict["pad_obj_bboxes"][..., :4], batch_dict["pad_ocr_bboxes"][..., :4]], dim=1)
+    boxes = boxes.to(device=dev, dtype=torch.float32)
+    _, _, bits = spatial_utils.build_graph_batch(boxes, 0.5, context=int(key))
+    return bits
 
 
 def pack_relation_bits(adj, device):
@@ -606,7 +626,7 @@ class SAM4C(nn.Module):
 
         def rel_lookup(key):
             if key not in rel_cache:
-                rel_cache[key] = pack_relation_bits(batch_dict["spatial_adj_matrices"][key], dev)
+                rel_cache[key] = _relation_bits(batch_dict, key, dev)
             return rel_cache[key]
 
         dims = (B, L, T, O + R, D)

@@ -230,3 +230,24 @@ def test_cuda_graph_replay_matches_eager_step_and_redraws_dropout(golden):
         finally:
             from sam_textvqa_b200._lib import check, lib, stream_ptr
             check(lib().samk_set_dropout_salt(0, stream_ptr()), "salt")     # default state for the other tests
+
+
+def test_on_device_batch_preparation_matches_dataset_prepared_masks(golden):
+    """without `spatial_adj_matrices` the model builds the relation graph on the GPU from the padded
+    boxes already in the batch; the scores must be bit-identical to the run that consumes the reference-format
+    int8 [B,A,A,12] masks (which the golden fixture took from the unmodified reference builder)."""
+    from sam_textvqa_b200 import ops
+    g, mmt, tb, state, model = golden
+    model.eval()
+    ops.set_precision("bf16")
+    ops.clear_weight_cache()
+    with torch.no_grad():
+        b1 = golden_batch(g)
+        b1["train_prev_inds"] = b1["train_prev_inds"].clone()
+        s1 = model.train(False)(b1)["textvqa_scores"].clone()
+        b2 = golden_batch(g)
+        b2.pop("spatial_adj_matrices")
+        s2 = model(b2)["textvqa_scores"]
+    assert torch.equal(s1, s2)
+    assert torch.equal(b1["train_prev_inds"], b2["train_prev_inds"])      # greedy tokens
+    model.train()
