@@ -31,7 +31,7 @@ ncu)
     REPS=1 timeout 300 $FULL -k regex:gemm_tc_kernel -s 3 -c 1 -f -o $OUT/${TAG}_ncu_gemm_$shape \
         python tools/gemm_bench.py $shape > $OUT/${TAG}_ncu_gemm_$shape.out 2>&1
   done
-  timeout 400 $FULL -k regex:attn_fwd2_kernel -s 12 -c 3 -f -o $OUT/${TAG}_ncu_attn_fwd \
+  timeout 400 $FULL -k regex:attn_fwd3_kernel -s 12 -c 3 -f -o $OUT/${TAG}_ncu_attn_fwd \
       python bench.py --profile-only > $OUT/${TAG}_ncu_attn_fwd.out 2>&1
   timeout 400 $FULL -k regex:attn_bwd2_kernel -s 9 -c 2 -f -o $OUT/${TAG}_ncu_attn_bwd \
       python bench.py --profile-only > $OUT/${TAG}_ncu_attn_bwd.out 2>&1
