@@ -161,3 +161,19 @@ def test_data_parallel_gradient_allreduce_gloo_world2():
         assert p.exitcode == 0
     assert all(err < 1e-6 for _, err, _ in res)
     assert abs(res[0][2] - 1.0 / 3.0) < 1e-6 and abs(res[1][2] - 2.0 / 3.0) < 1e-6
+
+
+def test_relation_bits_contract_on_host():
+    """Reference-format masks are preferred; without them the padded boxes are required (on-device batch
+    preparation) -- the failure mode is a KeyError naming the missing inputs, not a silent default."""
+    from sam_textvqa_b200 import sa_m4c
+    with pytest.raises(KeyError):
+        sa_m4c._relation_bits({"question_mask": torch.ones(1, 20)}, "3", torch.device("cpu"))
+    with pytest.raises(KeyError):
+        sa_m4c._relation_bits({"spatial_adj_matrices": {"1": torch.zeros(1, 4, 4, 12, dtype=torch.int8)}}, "3",
+                              torch.device("cpu"))
+
+
+def test_graph_step_module_imports_without_gpu():
+    import sam_textvqa_b200.graph_step as gs
+    assert hasattr(gs.GraphedTrainStep, "run") and hasattr(gs.GraphedTrainStep, "load")
