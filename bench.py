@@ -304,7 +304,7 @@ def run_samk(args):
         if pending is not None and diag != "noitem":
             pending.item()
 
-    e2e_run(2)
+    e2e_run(max(args.warmup, 5))      # the host->device path (pinned pages, PCIe link state) needs its own warm-up
     barrier()
     s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s_ev.record()

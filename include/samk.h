@@ -32,6 +32,10 @@ int samk_sm_count(void);
  * replayed from a CUDA graph keep the (seed, offset) they were captured with; setting a new salt before each replay
  * (stream-ordered, not itself captured) gives every replay fresh masks, identical in its forward and backward. */
 int samk_set_dropout_salt(unsigned long long salt, void* stream);
+/* Device-side form: a one-thread kernel advances an on-device counter, hashes it (splitmix64) and the result becomes
+ * the salt through device-to-device copies.  Everything is stream-ordered and capturable, so a captured training
+ * step that starts with this call draws new masks on every replay with no host involvement. */
+int samk_advance_dropout_salt(void* stream);
 
 /* ---- spatial graph ------------------------------------------------------------------------
  * Replaces build_graph_using_normalized_boxes (sam/spatial_utils.py:92-218) for a batch of box

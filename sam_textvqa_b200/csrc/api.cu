@@ -31,6 +31,19 @@ int set_drop_salt_gemm(unsigned long long salt, cudaStream_t stream);
 int set_drop_salt_attn_tc(unsigned long long salt, cudaStream_t stream);
 int set_drop_salt_attn_simt(unsigned long long salt, cudaStream_t stream);
 int set_drop_salt_elementwise(unsigned long long salt, cudaStream_t stream);
+int set_drop_salt_dev_gemm(const unsigned long long* src, cudaStream_t stream);
+int set_drop_salt_dev_attn_tc(const unsigned long long* src, cudaStream_t stream);
+int set_drop_salt_dev_attn_simt(const unsigned long long* src, cudaStream_t stream);
+int set_drop_salt_dev_elementwise(const unsigned long long* src, cudaStream_t stream);
+
+// [0] = replay counter, [1] = current salt (splitmix64 of the counter)
+__device__ unsigned long long g_salt_state[2] = {0ull, 0ull};
+__global__ void advance_salt_kernel() {
+  unsigned long long z = (g_salt_state[0] += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  g_salt_state[1] = z ^ (z >> 31);
+}
 
 }  // namespace samk
 
@@ -38,6 +51,21 @@ extern "C" {
 int samk_version(void) { return 100; }
 const char* samk_last_error(void) { return samk::g_err; }
 int samk_sm_count(void) { return samk::sm_count(); }
+int samk_advance_dropout_salt(void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long* state = nullptr;
+  if (cudaGetSymbolAddress((void**)&state, samk::g_salt_state) != cudaSuccess) {
+    samk::set_error("samk_advance_dropout_salt: no symbol address: %s", cudaGetErrorString(cudaGetLastError()));
+    return SAMK_ERR_CUDA;
+  }
+  samk::advance_salt_kernel<<<1, 1, 0, s>>>();
+  if (samk::set_drop_salt_dev_gemm(state + 1, s) || samk::set_drop_salt_dev_attn_tc(state + 1, s) ||
+      samk::set_drop_salt_dev_attn_simt(state + 1, s) || samk::set_drop_salt_dev_elementwise(state + 1, s)) {
+    samk::set_error("samk_advance_dropout_salt: copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return SAMK_ERR_CUDA;
+  }
+  return samk::check_launch("samk_advance_dropout_salt");
+}
 int samk_set_dropout_salt(unsigned long long salt, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (samk::set_drop_salt_gemm(salt, s) || samk::set_drop_salt_attn_tc(salt, s) || samk::set_drop_salt_attn_simt(salt, s) ||

@@ -399,3 +399,4 @@ int attn_simt_bwd(const samk_attn_params* p, cudaStream_t stream) {
 }  // namespace samk
 
 namespace samk { int set_drop_salt_attn_simt(unsigned long long salt, cudaStream_t stream) { return set_drop_salt_tu(salt, stream); } }
+namespace samk { int set_drop_salt_dev_attn_simt(const unsigned long long* src, cudaStream_t stream) { return set_drop_salt_from_device_tu(src, stream); } }

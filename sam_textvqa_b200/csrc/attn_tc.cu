@@ -1780,3 +1780,4 @@ int samk_attn_bwd(const samk_attn_params* p, int impl, void* stream) {
 }  // extern "C"
 
 namespace samk { int set_drop_salt_attn_tc(unsigned long long salt, cudaStream_t stream) { return set_drop_salt_tu(salt, stream); } }
+namespace samk { int set_drop_salt_dev_attn_tc(const unsigned long long* src, cudaStream_t stream) { return set_drop_salt_from_device_tu(src, stream); } }

@@ -31,6 +31,10 @@ static __constant__ unsigned long long g_drop_salt = 0ull;
 static inline int set_drop_salt_tu(unsigned long long salt, cudaStream_t stream) {
   return cudaMemcpyToSymbolAsync(g_drop_salt, &salt, sizeof(salt), 0, cudaMemcpyHostToDevice, stream) == cudaSuccess ? 0 : -2;
 }
+// device-to-device form: capturable in a CUDA graph, and it does not queue behind bulk host->device input copies
+static inline int set_drop_salt_from_device_tu(const unsigned long long* src, cudaStream_t stream) {
+  return cudaMemcpyToSymbolAsync(g_drop_salt, src, sizeof(unsigned long long), 0, cudaMemcpyDeviceToDevice, stream) == cudaSuccess ? 0 : -2;
+}
 
 __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr_lo, uint32_t ctr_hi) {
   seed ^= g_drop_salt;

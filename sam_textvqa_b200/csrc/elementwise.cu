@@ -1019,3 +1019,4 @@ int samk_scale_inplace(float* x, long long n, const float* scale_dev, void* stre
 }  // extern "C"
 
 namespace samk { int set_drop_salt_elementwise(unsigned long long salt, cudaStream_t stream) { return set_drop_salt_tu(salt, stream); } }
+namespace samk { int set_drop_salt_dev_elementwise(const unsigned long long* src, cudaStream_t stream) { return set_drop_salt_from_device_tu(src, stream); } }

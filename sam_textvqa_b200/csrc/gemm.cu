@@ -845,3 +845,4 @@ extern "C" int samk_gemm_bf16(const void* A, int a_mn, long long lda, const void
 }
 
 namespace samk { int set_drop_salt_gemm(unsigned long long salt, cudaStream_t stream) { return set_drop_salt_tu(salt, stream); } }
+namespace samk { int set_drop_salt_dev_gemm(const unsigned long long* src, cudaStream_t stream) { return set_drop_salt_from_device_tu(src, stream); } }

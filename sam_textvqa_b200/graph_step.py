@@ -9,8 +9,9 @@ What makes this safe for training:
   * gradients go to the static `dp.FlatGradBuffer` (zeroed inside the graph);
   * the bf16 operand copies of the weights are re-made inside the graph (the weight cache is cleared before capture),
     so an optimizer step between replays is honoured;
-  * dropout masks change per replay through `samk_set_dropout_salt` (the captured kernels keep their seed / offset
-    arguments; the salt is XORed into the Philox key on the device).
+  * dropout masks change per replay: the captured step starts with `samk_advance_dropout_salt` (a device-side counter
+    is hashed into a salt that is XORed into every Philox key; the captured kernels keep their seed / offset
+    arguments).  No host work per replay besides the graph launch.
 The gradient all-reduce and the optimizer stay outside the graph.
 """
 import torch
@@ -61,6 +62,8 @@ class GraphedTrainStep(object):
         return out
 
     def _eager_step(self):
+        # first node of the captured step: new dropout salt for this replay, computed and installed on the device
+        check(lib().samk_advance_dropout_salt(stream_ptr()), "advance salt")
         self.grads.zero()
         if self.allreduce == "overlap":
             self.grads.begin_step()
@@ -88,6 +91,5 @@ class GraphedTrainStep(object):
     def run(self):
         """Replay on the current stream; returns the (static) loss tensor.  Gradients are in grads.flat."""
         self.replays += 1
-        check(lib().samk_set_dropout_salt(0x9E3779B97F4A7C15 * self.replays & 0xFFFFFFFFFFFFFFFF, stream_ptr()), "salt")
         self.graph.replay()
         return self.loss
