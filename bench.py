@@ -272,15 +272,27 @@ def run_samk(args):
     # side stream while step i computes (double-buffered device staging), and every step's loss is read
     # back to the host.  All K uploads and K loss reads are inside the timed region.
     copy_stream = torch.cuda.Stream()
-    staged = [None, None]
+    # two persistent device staging sets; `consumed[slot]` (compute stream) says the step that read slot has taken its
+    # inputs, `ready[slot]` (copy stream) says the next upload into slot has landed
+    staged = [({k: torch.empty_like(v) for k, v in resident.items()}, torch.empty_like(resident_adj)) for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    for ev in consumed:
+        ev.record()
 
     def stage(slot):
         with torch.cuda.stream(copy_stream):
-            staged[slot] = upload()
+            copy_stream.wait_event(consumed[slot])
+            bufs, abuf = staged[slot]
+            for k in names:
+                bufs[k].copy_(pinned[k], non_blocking=True)
+            abuf.copy_(pinned_adj, non_blocking=True)
             ready[slot].record(copy_stream)
 
     diag = os.environ.get("SAMK_E2E_DIAG", "")
+    host_loss = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_done = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_values = []
 
     def e2e_run(steps):
         if diag == "noupload":
@@ -288,21 +300,34 @@ def run_samk(args):
                 step(resident, resident_adj).item()
             return
         stage(0)
-        pending = None
         for i in range(steps):
             torch.cuda.current_stream().wait_event(ready[i % 2])
             if i + 1 < steps:
                 stage((i + 1) % 2)
             up, a = staged[i % 2]
-            loss = step(up, a)
-            # device->host read of every step's loss; the read of step i is issued after step i+1 has been
-            # enqueued so the host never drains the GPU queue (one step of latency, as a training loop's
-            # logging would do)
-            if pending is not None and diag != "noitem":
-                pending.item()
-            pending = loss
-        if pending is not None and diag != "noitem":
-            pending.item()
+            if graphed is not None:                   # inputs are taken by the device-to-device load in front of the replay
+                graphed.load(up)
+                graphed.load({"spatial_adj_matrices": {"3": a}})
+                consumed[i % 2].record()
+                loss = graphed.run()
+                if world > 1 and not overlap:
+                    grads.all_reduce()
+            else:
+                loss = eager_step(up, a)
+                consumed[i % 2].record()
+            # device->host read of EVERY step's loss: an async copy into pinned memory plus an event right behind the
+            # step; the host reads step i-1's value after it has enqueued step i, waiting on that event only
+            # (`.item()` would synchronise the whole stream, i.e. also wait for the step just enqueued, and the GPU
+            # would then idle while the host prepares the next one)
+            if diag != "noitem":
+                host_loss[i % 2].copy_(loss.detach().reshape(1), non_blocking=True)
+                loss_done[i % 2].record()
+                if i >= 1:
+                    loss_done[(i - 1) % 2].synchronize()
+                    loss_values.append(float(host_loss[(i - 1) % 2][0]))
+        if diag != "noitem" and steps >= 1:
+            loss_done[(steps - 1) % 2].synchronize()
+            loss_values.append(float(host_loss[(steps - 1) % 2][0]))
 
     e2e_run(max(args.warmup, 5))      # the host->device path (pinned pages, PCIe link state) needs its own warm-up
     barrier()
