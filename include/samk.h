@@ -191,9 +191,14 @@ typedef struct samk_attn_params {
   float* dq_accum;            /* tensor-core backward: fp32 [B*L, H*64] scratch for the dQ reduction */
   int q_begin;                /* forward only: compute query rows >= q_begin (rounded down to the kernel's
                                  row tile); 0 = all rows.  Used by the cached greedy decoder (decoder rows only). */
+  int delta_ready;            /* backward only: 1 = `delta` already holds rowsum(dctx * ctx) per (b, h, row), written by
+                                 samk_attn_delta (e.g. on another stream, beside the out-projection wgrad) */
 } samk_attn_params;
 int samk_attn_fwd(const samk_attn_params* p, int impl, void* stream);
 int samk_attn_bwd(const samk_attn_params* p, int impl, void* stream);
+/* delta[b, h, i] = sum_d dctx[b, i, h, d] * ctx[b, i, h, d] (bf16 token-major inputs, head_dim 64): the row term of the
+ * softmax backward (sa_m4c.py:578-598 differentiated), the first kernel of samk_attn_bwd when delta_ready == 0. */
+int samk_attn_delta(const void* dctx, const void* ctx, float* delta, int B, int H, int L, void* stream);
 /* allow-bit matrix shared by all layers of one kind in a step: bit (j&31) of word [b][h|0][i][j>>5] set
  * iff query i may attend key j (key validity, decoder causality, quadrants, relation bits). */
 long long samk_attn_mask_words(int B, int H, int T, int A, int D, int spatial);

@@ -32,7 +32,7 @@ class AttnParams(ctypes.Structure):
         ("delta", c_void_p), ("dtype", c_int), ("B", c_int), ("H", c_int), ("head_dim", c_int), ("T", c_int),
         ("A", c_int), ("D", c_int), ("key_valid", c_void_p), ("rel_bits", c_void_p), ("quadrant_mask", ctypes.c_uint),
         ("spatial", c_int), ("scale", c_float), ("drop_p", c_float), ("drop_seed", c_ull), ("drop_offset", c_ull),
-        ("allow_bits", c_void_p), ("dq_accum", c_void_p), ("q_begin", c_int),
+        ("allow_bits", c_void_p), ("dq_accum", c_void_p), ("q_begin", c_int), ("delta_ready", c_int),
     ]
 
 
@@ -77,6 +77,7 @@ SIGNATURES = {
     "samk_scale_inplace": (c_int, [c_void_p, c_ll, c_void_p, c_void_p]),
     "samk_attn_fwd": (c_int, [ctypes.POINTER(AttnParams), c_int, c_void_p]),
     "samk_attn_bwd": (c_int, [ctypes.POINTER(AttnParams), c_int, c_void_p]),
+    "samk_attn_delta": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "samk_attn_mask_words": (c_ll, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "samk_attn_build_mask": (c_int, [ctypes.POINTER(AttnParams), c_void_p, c_void_p]),
 }

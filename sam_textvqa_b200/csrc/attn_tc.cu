@@ -996,15 +996,19 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 // delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dctx, const __nv_bfloat16* __restrict__ ctx,
                                   float* __restrict__ delta, int B, int H, int L) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (row, head), 8 lanes... simple: 1 thread
-  if (e >= B * L * H) return;
-  const int h = e % H, rowi = e / H, b = rowi / L, i = rowi % L;
-  const uint4* pa = reinterpret_cast<const uint4*>(dctx + (size_t)rowi * H * TDH + h * TDH);
-  const uint4* pb = reinterpret_cast<const uint4*>(ctx + (size_t)rowi * H * TDH + h * TDH);
+  // 8 lanes per (row, head): a warp reads 512 contiguous bytes of each operand per instruction
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long e = t >> 3;
+  const int k = (int)(t & 7);
+  const bool live = e < (long long)B * L * H;
   float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    uint4 x = pa[k], y = pb[k];
+  int h = 0, b = 0, i = 0;
+  if (live) {
+    h = (int)(e % H);
+    const long long rowi = e / H;
+    b = (int)(rowi / L); i = (int)(rowi % L);
+    const uint4 x = reinterpret_cast<const uint4*>(dctx + (size_t)rowi * H * TDH + h * TDH)[k];
+    const uint4 y = reinterpret_cast<const uint4*>(ctx + (size_t)rowi * H * TDH + h * TDH)[k];
     const __nv_bfloat162* xa = reinterpret_cast<const __nv_bfloat162*>(&x);
     const __nv_bfloat162* ya = reinterpret_cast<const __nv_bfloat162*>(&y);
 #pragma unroll
@@ -1013,7 +1017,10 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dctx, const 
       s += f.x * g.x + f.y * g.y;
     }
   }
-  delta[((size_t)b * H + h) * L + i] = s;
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (live && k == 0) delta[((size_t)b * H + h) * L + i] = s;
 }
 
 __global__ void __launch_bounds__(256, 1)
@@ -1697,9 +1704,11 @@ int attn_tc_bwd(const samk_attn_params* p, cudaStream_t stream) {
   if (!a.B || !a.L) return SAMK_OK;
   const long long rows = (long long)a.B * a.L;
   const int hd = a.H * TDH;
-  attn_delta_kernel<<<(unsigned)((rows * a.H + 255) / 256), 256, 0, stream>>>(
-      (const __nv_bfloat16*)p->dctx, (const __nv_bfloat16*)p->ctx, p->delta, a.B, a.H, a.L);
-  if ((rc = check_launch("samk_attn_bwd(delta)"))) return rc;
+  if (!p->delta_ready) {
+    attn_delta_kernel<<<(unsigned)((rows * a.H * 8 + 255) / 256), 256, 0, stream>>>(
+        (const __nv_bfloat16*)p->dctx, (const __nv_bfloat16*)p->ctx, p->delta, a.B, a.H, a.L);
+    if ((rc = check_launch("samk_attn_bwd(delta)"))) return rc;
+  }
   CUtensorMap tqkv, tdo;
   if ((rc = make_tmap_bf16_2d(&tqkv, p->qkv, rows, 3 * hd, 3 * hd, 64, 128))) return rc;
   if ((rc = make_tmap_bf16_2d(&tdo, p->dctx, rows, hd, hd, 64, 128))) return rc;
@@ -1769,6 +1778,15 @@ int samk_attn_fwd(const samk_attn_params* p, int impl, void* stream) {
   if (!p) { samk::set_error("samk_attn_fwd: null params"); return SAMK_ERR_ARG; }
   if (impl == 0 && p->dtype == SAMK_DT_BF16) return samk::attn_tc_fwd(p, (cudaStream_t)stream);
   return samk::attn_simt_fwd(p, (cudaStream_t)stream);
+}
+
+int samk_attn_delta(const void* dctx, const void* ctx, float* delta, int B, int H, int L, void* stream) {
+  if (!dctx || !ctx || !delta || B < 0 || H <= 0 || L < 0) { samk::set_error("samk_attn_delta: bad argument"); return SAMK_ERR_ARG; }
+  const long long items = (long long)B * L * H;
+  if (!items) return SAMK_OK;
+  samk::attn_delta_kernel<<<(unsigned)((items * 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dctx, (const __nv_bfloat16*)ctx, delta, B, H, L);
+  return samk::check_launch("samk_attn_delta");
 }
 
 int samk_attn_bwd(const samk_attn_params* p, int impl, void* stream) {

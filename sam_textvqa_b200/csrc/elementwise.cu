@@ -2,6 +2,7 @@
 // TF-style LayerNorm forward/backward (fused with the dropout mask and the bias-gradient column
 // sums of the dense layer in front of it), dropout-add, column sums, and the two embedding
 // blocks (TextBert embeddings, PrevPredEmbeddings).  One warp owns one row of <= 1024 floats.
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/samk.h"
 
@@ -300,15 +301,20 @@ __global__ void dropout_add_kernel(const float* __restrict__ a, const float* __r
 // out[c] += sum_r x[r, c]
 // part_cols > 0: the columns are n consecutive groups of part_cols with separate destinations out, out1, out2
 // (bias gradients of the fused q|k|v projection are three separate parameters)
-__global__ void colsum_kernel(const void* __restrict__ x, int x_bf16, long long ld, int rows, int cols,
+__global__ void __launch_bounds__(1024) colsum_kernel(const void* __restrict__ x, int x_bf16, long long ld, int rows, int cols,
                               float* __restrict__ out, float* __restrict__ out1, float* __restrict__ out2, int part_cols) {
-  // block = 256 threads = 64 column-quads x 4 row lanes
-  const int cq = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int rl = threadIdx.x >> 6;
+  // block = 1024 threads = 64 column-quads x 16 row lanes; a warp holds 16 quads (128 contiguous bytes of a bf16 row)
+  // x 2 row lanes, reduced with one shuffle.  No shared memory and about one block per SM: on the side branch of the
+  // backward pass a block has to fit next to a resident GEMM CTA, which owns all but ~1.7 KB of the SM's shared
+  // memory (1 KB is reserved per block), so one big block per SM is what keeps enough loads in flight.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cq = blockIdx.x * 64 + (warp & 3) * 16 + (lane & 15);
+  const int rl = (warp >> 2) * 2 + (lane >> 4);
+  const int nrl = blockDim.x >> 6;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (cq * 4 < cols) {
-    const int stride = gridDim.y * 4;
-    int r = blockIdx.y * 4 + rl;
+    const int stride = gridDim.y * nrl;
+    int r = blockIdx.y * nrl + rl;
     for (; r + 3 * stride < rows; r += 4 * stride) {   // 4 independent loads in flight per thread
       float4 v0 = load_act(x, x_bf16, (size_t)r * ld + cq * 4);
       float4 v1 = load_act(x, x_bf16, (size_t)(r + stride) * ld + cq * 4);
@@ -322,20 +328,16 @@ __global__ void colsum_kernel(const void* __restrict__ x, int x_bf16, long long 
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
   }
-  __shared__ float4 red[4][64];
-  red[rl][threadIdx.x & 63] = acc;
-  __syncthreads();
-  if (rl == 0 && cq * 4 < cols) {
-    float4 t = red[0][threadIdx.x];
-#pragma unroll
-    for (int k = 1; k < 4; ++k) { float4 u = red[k][threadIdx.x]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+  acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+  acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
+  if (lane < 16 && cq * 4 < cols) {
     float* dst = out + cq * 4;
     if (part_cols > 0) {
       const int part = (cq * 4) / part_cols;
       dst = (part == 0 ? out : (part == 1 ? out1 : out2)) + (cq * 4 - part * part_cols);
     }
-    atomicAdd(dst + 0, t.x); atomicAdd(dst + 1, t.y);
-    atomicAdd(dst + 2, t.z); atomicAdd(dst + 3, t.w);
+    atomicAdd(dst + 0, acc.x); atomicAdd(dst + 1, acc.y);
+    atomicAdd(dst + 2, acc.z); atomicAdd(dst + 3, acc.w);
   }
 }
 
@@ -877,6 +879,16 @@ int samk_dropout_add(const float* a, const float* b, float* out, void* out2, int
   return check_launch(__func__);
 }
 
+static int colsum_threads() {
+  static int t = 0;
+  if (!t) {
+    const char* e = getenv("SAMK_COLSUM_THREADS");
+    const int v = e ? atoi(e) : 256;
+    t = (v == 1024 || v == 512) ? v : 256;
+  }
+  return t;
+}
+
 int samk_colsum(const void* x, int x_dtype, long long ld, int rows, int cols, float* out, void* stream) {
   SAMK_REQUIRE(x && out && rows >= 0 && cols >= 0, "bad argument");
   if (!rows || !cols) return SAMK_OK;
@@ -886,11 +898,12 @@ int samk_colsum(const void* x, int x_dtype, long long ld, int rows, int cols, fl
     return check_launch(__func__);
   }
   const int gx = (cols / 4 + 63) / 64;
-  int gy = (148 * 4 + gx - 1) / gx;
-  if (gy > (rows + 3) / 4) gy = (rows + 3) / 4;
+  const int threads = colsum_threads(), nrl = threads / 64;
+  int gy = (148 * 1024 / threads + gx - 1) / gx;       // 148 x 1024 threads in all
+  if (gy > (rows + nrl - 1) / nrl) gy = (rows + nrl - 1) / nrl;
   if (gy < 1) gy = 1;
   dim3 grid(gx, gy);
-  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_dtype == SAMK_DT_BF16, ld, rows, cols, out, nullptr, nullptr, 0);
+  colsum_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(x, x_dtype == SAMK_DT_BF16, ld, rows, cols, out, nullptr, nullptr, 0);
   return check_launch(__func__);
 }
 
@@ -902,11 +915,12 @@ int samk_colsum3(const void* x, int x_dtype, long long ld, int rows, int part_co
   if (!rows) return SAMK_OK;
   const int cols = 3 * part_cols;
   const int gx = (cols / 4 + 63) / 64;
-  int gy = (148 * 4 + gx - 1) / gx;
-  if (gy > (rows + 3) / 4) gy = (rows + 3) / 4;
+  const int threads = colsum_threads(), nrl = threads / 64;
+  int gy = (148 * 1024 / threads + gx - 1) / gx;       // 148 x 1024 threads in all
+  if (gy > (rows + nrl - 1) / nrl) gy = (rows + nrl - 1) / nrl;
   if (gy < 1) gy = 1;
   dim3 grid(gx, gy);
-  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, bf, ld, rows, cols, out0, out1, out2, part_cols);
+  colsum_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(x, bf, ld, rows, cols, out0, out1, out2, part_cols);
   return check_launch(__func__);
 }
 

@@ -277,6 +277,62 @@ def colsum_into(x2d, out):
     _count()
 
 
+# ---- side branch -------------------------------------------------------------------------------------
+# Bias-gradient column sums are L2/HBM-bound readers whose result nothing inside the backward pass consumes.  They are
+# issued on a second stream right behind the kernel that produced their input and joined before the gradients are
+# declared final, so they run beside the tensor-bound dgrad / wgrad GEMMs (a parallel branch of the captured graph;
+# colsum_kernel uses no shared memory so that its blocks fit on an SM whose shared memory a GEMM CTA owns).
+_SIDE_MODE = int(os.environ.get("SAMK_SIDE_BRANCH", "1"))      # 0 off, 1 side kernel enqueued first, 2 GEMM first
+_SIDE_BRANCH = _SIDE_MODE != 0
+_SIDE_DELTA = os.environ.get("SAMK_SIDE_DELTA", "0") != "0"
+_side_streams = {}
+_side_open = set()
+
+
+def fork_point():
+    """Mark the current position of the main stream: a later `side_branch(after=...)` depends on the work issued up to
+    here only, so the main stream's next kernel (a GEMM that wants every SM) is enqueued ahead of the side kernel."""
+    if _SIDE_MODE != 2:
+        return None
+    ev = torch.cuda.Event()
+    ev.record()
+    return ev
+
+
+class side_branch(object):
+    def __init__(self, after=None):
+        self._after = after
+
+    def __enter__(self):
+        self._cm = None
+        if not _SIDE_BRANCH:
+            return self
+        dev = torch.cuda.current_device()
+        side = _side_streams.get(dev)
+        if side is None:
+            side = _side_streams[dev] = torch.cuda.Stream(device=dev)
+        if self._after is not None:
+            side.wait_event(self._after)
+        else:
+            side.wait_stream(torch.cuda.current_stream())
+        self._cm = torch.cuda.stream(side)
+        self._cm.__enter__()
+        _side_open.add(dev)
+        return self
+
+    def __exit__(self, *exc):
+        if self._cm is not None:
+            self._cm.__exit__(*exc)
+        return False
+
+
+def join_side():
+    dev = torch.cuda.current_device()
+    if dev in _side_open:
+        _side_open.discard(dev)
+        torch.cuda.current_stream().wait_stream(_side_streams[dev])
+
+
 # ---- simple differentiable ops -----------------------------------------------------------------------
 class LinearFn(torch.autograd.Function):
     """y = x W^T + b with fp32 output (input projections, pointer-net projections)."""
@@ -302,6 +358,10 @@ class LinearFn(torch.autograd.Function):
         x2d, weight = ctx.saved_tensors
         M, N, K = ctx.dims
         dy = dy.contiguous()
+        ctx_bias = ctx.bias_ref
+        dW, db = _gbuf(weight), _gbuf(ctx_bias)
+        with side_branch():
+            colsum_into(dy, db[0])
         dy_act = dy if _PRECISION != "bf16" else cast_bf16(dy)[:, :N]
         dy_k = operand(dy_act, "a", False)          # [M, N] K-major for dgrad
         dy_mn = operand(dy_act, "a", True)          # stored [tokens, N]: MN-major for wgrad
@@ -313,10 +373,8 @@ class LinearFn(torch.autograd.Function):
                 M, K, dtype=torch.float32, device=dy.device)
             w_op = weight_operand([weight[:, :K]] if weight.shape[1] != K else [weight], True)
             gemm(dy_k, False, w_op, True, M, K, N, dx[:, :K])
-        ctx_bias = ctx.bias_ref
-        dW, db = _gbuf(weight), _gbuf(ctx_bias)
         gemm(dy_mn, True, x_mn, True, N, K, M, dW[0][:, :K], accumulate=True)
-        colsum_into(dy, db[0])
+        join_side()
         _grads_done(weight, ctx_bias)
         return dx, _ret(dW), _ret(db), None
 
@@ -530,7 +588,16 @@ def attention_fwd(qkv, valid, rel, dims, spatial, quad_mask, p, drop, allow=None
     return ctx_t, lse
 
 
-def attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, allow=None):
+def attention_delta(dctx, ctx_t, dims, delta):
+    """delta[b,h,i] = dO_i . O_i for the tensor-core backward, as its own launch (so it can sit on the side branch);
+    `delta` [B, H, L] fp32 is allocated by the caller on the stream that consumes it."""
+    B, L, H, T, A, D = dims
+    check(lib().samk_attn_delta(ptr(dctx), ptr(ctx_t), ptr(delta), B, H, L, stream_ptr()), "attn_delta")
+    _count()
+    return delta
+
+
+def attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, allow=None, delta=None):
     B, L, H, T, A, D = dims
     dq_accum = None
     if uses_tensor_core_attention(qkv.dtype):
@@ -539,9 +606,12 @@ def attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p
         if L > 256:      # long sequences: key-tile CTAs reduce dQ through an fp32 buffer
             dq_accum = torch.empty(B * L, H * 64, dtype=torch.float32, device=qkv.device)
     dqkv = torch.empty_like(qkv)
-    delta = torch.empty_like(lse)
+    delta_ready = delta is not None
+    if delta is None:
+        delta = torch.empty_like(lse)
     ap = _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, dctx, dqkv, delta,
                       allow=allow, dq_accum=dq_accum)
+    ap.delta_ready = 1 if delta_ready else 0
     if attn_profile is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -551,7 +621,7 @@ def attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p
         # Q,K,V,O,dO read + dQ,dK,dV written (bf16), allow bits, LSE + delta; 10 L^2 d FLOP
         mask_b = B * (H if spatial else 1) * L * ((L + 31) // 32) * 4
         attn_profile.append(("bwd", L, ev0, ev1, B * (8 * L * H * 64 * 2 + 2 * H * L * 4) + mask_b, 10.0 * B * L * L * H * 64))
-    _count(4 if dq_accum is not None else 2)     # delta (+ memset) + main kernel (+ dq conversion)
+    _count((4 if dq_accum is not None else 2) - (1 if delta_ready else 0))   # delta (+ memset) + main kernel (+ dq conversion)
     return dqkv
 
 
@@ -638,9 +708,15 @@ class BertLayerFn(torch.autograd.Function):
         # ---- FFN2: dgrad (fused with the stored GELU') and wgrad
         dh = torch.empty(M, F, dtype=adt, device=dev)
         gemm(operand(dY2, "a", False), False, weight_operand([o2w], True), True, M, F, d, dh, act=4, aux=h)
+        dh_ready = fork_point()
+        if dh_ready is None:
+            with side_branch():                   # b_1 gradient beside the GEMMs that follow
+                colsum_into(dh, Gib)
         gemm(operand(dY2, "a", True), True, operand(g, "b", True), True, d, F, M, Go2w, accumulate=True)
+        if dh_ready is not None:
+            with side_branch(dh_ready):
+                colsum_into(dh, Gib)
         # ---- FFN1
-        colsum_into(dh, Gib)
         da = torch.empty(M, d, dtype=torch.float32, device=dev)
         gemm(operand(dh, "a", False), False, weight_operand([iw], True), True, M, d, F, da, residual=dy2)
         gemm(operand(dh, "a", True), True, operand(a_in, "b", True), True, F, d, M, Giw, accumulate=True)
@@ -651,16 +727,38 @@ class BertLayerFn(torch.autograd.Function):
         # ---- attention output dense
         dctx = torch.empty(M, d, dtype=adt, device=dev)
         gemm(operand(dY1, "a", False), False, weight_operand([ow], True), True, M, d, d, dctx)
+        delta = None
+        side_delta = _SIDE_BRANCH and _SIDE_DELTA and uses_tensor_core_attention(adt)
+        if side_delta:                            # dO . O row sums beside the out-projection wgrad
+            delta = torch.empty(B, H, L, dtype=torch.float32, device=dev)
+            dctx_ready = fork_point()
+            if dctx_ready is None:
+                with side_branch():
+                    attention_delta(dctx, ctx_t, dims, delta)
         gemm(operand(dY1, "a", True), True, operand(ctx_t, "b", True), True, d, d, M, Gow, accumulate=True)
+        if side_delta:
+            if dctx_ready is not None:
+                with side_branch(dctx_ready):
+                    attention_delta(dctx, ctx_t, dims, delta)
+            join_side()
         # ---- attention core
-        dqkv = attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p_attn, ctx.drops[0], allow)
+        dqkv = attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p_attn, ctx.drops[0], allow,
+                             delta=delta)
         # ---- fused q|k|v projection: one dgrad, three wgrads (separate parameter gradients)
+        def qkv_bias_grads():
+            check(lib().samk_colsum3(ptr(dqkv), _dt(dqkv), dqkv.stride(0), M, d, ptr(Gqb), ptr(Gkb), ptr(Gvb),
+                                     stream_ptr()), "colsum3")
+            _count()
+        dqkv_ready = fork_point()
+        if dqkv_ready is None:
+            with side_branch():                   # q, k, v bias gradients beside the dgrad / wgrad below
+                qkv_bias_grads()
         dx = torch.empty(M, d, dtype=torch.float32, device=dev)
         gemm(operand(dqkv, "a", False), False, weight_operand([qw, kw, vw], True), True, M, d, 3 * d, dx, residual=dy1)
+        if dqkv_ready is not None:
+            with side_branch(dqkv_ready):
+                qkv_bias_grads()
         x_mn = operand(x2, "b", True)
-        check(lib().samk_colsum3(ptr(dqkv), _dt(dqkv), dqkv.stride(0), M, d, ptr(Gqb), ptr(Gkb), ptr(Gvb), stream_ptr()),
-              "colsum3")
-        _count()
         if Gqw.stride(0) == Gkw.stride(0) == Gvw.stride(0) and d % 32 == 0:
             # the three weight gradients in one launch: M = 3d output rows routed to three destinations
             gemm(operand(dqkv, "a", True), True, x_mn, True, 3 * d, d, M, Gqw, accumulate=True, out_parts=(d, Gkw, Gvw))
@@ -668,6 +766,7 @@ class BertLayerFn(torch.autograd.Function):
             for part, Gw in enumerate((Gqw, Gkw, Gvw)):
                 sl = dqkv[:, part * d:(part + 1) * d]
                 gemm(operand(sl, "a", True), True, x_mn, True, d, d, M, Gw, accumulate=True)
+        join_side()
         _grads_done(*P)
         return (dx.view(B, L, d), None, None, None) + tuple(_ret(x) for x in G)
 
