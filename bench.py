@@ -367,8 +367,9 @@ def run_samk(args):
                                "hbm_frac": rows[0][1] / (ms_k * 1e-3) / 1e9 / peak_gbs,
                                "dense_equiv_TFLOPs": rows[0][2] / (ms_k * 1e-3) / 1e12}
     attention["peak_GBs"] = peak_gbs
-    attention["ncu"] = ("profiles/r01j_ncu_summary.txt: fwd 80 us, DRAM ~108+15 MB per launch, tensor pipe ~12 %; "
-                        "bwd 176 us, DRAM 153+72 MB, tensor pipe 15.5 % (L=182 is HBM/ALU-bound, SURVEY 8d)")
+    attention["ncu"] = ("profiles/r01j_ncu_summary.txt: fwd (attn_fwd3) 80.6 us, DRAM 185+29 MB per launch, tensor pipe "
+                        "12.1 %, issue slots 50 %; bwd (attn_bwd2) 190 us, DRAM 153+73 MB, tensor pipe 14.4 % "
+                        "(L=182 is HBM/ALU-bound, SURVEY 8d)")
 
     if rank != 0:
         if world > 1:
