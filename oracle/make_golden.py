@@ -13,6 +13,11 @@ reference tree does not exist.
                     under 10 MB), seed-0 weights: teacher-forced logits, loss, selected
                     gradients, greedy-decoded tokens, per-stage activations.
   attn_unit.npz     SpatialBertSelfAttention.forward on random hidden states, B=2.
+  sam4c_usebias.npz two spatial layers with `use_bias: true` (sa_m4c.py:439-443, 600-603; off in the shipped
+                    configs), B=2, cfg1 geometry: logits, loss, gradients of the context biases and of the
+                    out-projection they fold into.  The batch is regenerated in the tests from
+                    synth.make_batch(seed=3) with the oracle graph builder; its relation types are stored
+                    here as a cross-check.
 """
 import os
 import sys
@@ -158,6 +163,32 @@ def make_sam4c_golden(M, S, registry):
     print("sam4c_cfg1.npz loss", float(loss), "greedy tokens", bd["train_prev_inds"][0].tolist())
 
 
+def make_usebias_golden(M, S, registry):
+    V = 500
+    registry.answer_vocab = ["w%d" % i for i in range(V)]
+    mmt, tb = c3_config(layer_type_list=["s", "s"], mix_list=["share3", "none"], use_bias=True,
+                        hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, obj_drop=0.0, ocr_drop=0.0)
+    tb = dict(tb, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    model = build_ref_model(M, mmt, tb, seed=4).train()
+    batch = synth.make_batch(2, T=20, O=36, R=50, D=12, V=V, seed=3, contexts=(1, 3), graph_fn=ref_graph_fn(S))
+    bd = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    scores = model(bd)["textvqa_scores"]
+    losses = torch.nn.functional.binary_cross_entropy_with_logits(scores, batch["targets"], reduction="none")
+    loss = (losses * batch["train_loss_mask"].unsqueeze(-1)).sum() / batch["train_loss_mask"].sum().clamp(min=1)
+    loss.backward()
+    out = {"types": batch["spatial_types"].numpy(), "tf/scores": scores.detach().numpy(), "tf/loss": loss.detach().numpy()}
+    grads = dict((n, p.grad) for n, p in model.named_parameters() if p.grad is not None)
+    for n in ["mmt.encoder.spatial_layers.0.attention.self.biases.weight",
+              "mmt.encoder.spatial_layers.1.attention.self.biases.weight",
+              "mmt.encoder.spatial_layers.0.attention.output.dense.bias",
+              "mmt.encoder.spatial_layers.1.attention.output.dense.weight",
+              "mmt.encoder.spatial_layers.0.attention.self.value.weight"]:
+        g = grads[n]
+        out["grad/" + n] = g.numpy() if g.numel() <= 70000 else g.flatten()[:: max(1, g.numel() // 4096)].numpy()
+    np.savez_compressed(os.path.join(GOLD, "sam4c_usebias.npz"), **out)
+    print("sam4c_usebias.npz loss", float(loss))
+
+
 def make_attn_golden(M):
     mmt, _ = c3_config(attention_probs_dropout_prob=0.0)
     cfg = M.BertConfig.from_dict(mmt)
@@ -192,6 +223,7 @@ def main():
     make_graph_golden(S)
     make_attn_golden(M)
     make_sam4c_golden(M, S, registry)
+    make_usebias_golden(M, S, registry)
 
 
 if __name__ == "__main__":

@@ -69,7 +69,10 @@ def _attend(P, pre, h, add_mask, nh, p_attn, train, spatial_add=None):
         probs = torch.softmax(scores + combined, dim=-1) * alive
     probs = _drop(probs, p_attn, train)
     ctx = torch.matmul(probs, v).permute(0, 2, 1, 3).contiguous()
-    return ctx.view(ctx.size(0), ctx.size(1), -1)
+    ctx = ctx.view(ctx.size(0), ctx.size(1), -1)
+    if spatial_add is not None and (pre + "biases.weight") in P:     # use_bias, sa_m4c.py:439-443, 600-603
+        ctx = ctx + P[pre + "biases.weight"][0]
+    return ctx
 
 
 def _bert_layer(P, pre, h, add_mask, cfg, train, spatial_add=None, nh=12):

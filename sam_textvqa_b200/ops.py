@@ -84,7 +84,7 @@ def _ret(buf_direct):
 
 def _grads_done(*params):
     if grad_ready_hook is not None:
-        grad_ready_hook([p for p in params if p is not None])
+        grad_ready_hook([p for p in params if p is not None and p.is_leaf])
 
 
 _ln_ws = {}

@@ -96,8 +96,8 @@ class SpatialBertSelfAttention(_SelfAttentionParams):
         if getattr(config, "no_drop", False):
             self.attention_probs_dropout_prob = 0.0
         self.use_bias = bool(getattr(config, "use_bias", False))
-        if self.use_bias:   # sa_m4c.py:439-443, 600-603; off in every shipped config
-            raise NotImplementedError("use_bias=True (per-head context biases) is not built")
+        if self.use_bias:   # sa_m4c.py:439-443, 600-603: one learned d-vector added to every context row
+            self.biases = nn.Embedding(1, config.hidden_size)
         qm = 0
         for q in self.mask_quadrants:
             if q not in _LEGAL_QUADRANTS:
@@ -151,8 +151,13 @@ class BertLayer(nn.Module):
 
     def _params(self):
         a, s = self.attention, self.attention.self
+        out_bias = a.output.dense.bias
+        if getattr(s, "use_bias", False):
+            # W_o (ctx + b) + b_o = W_o ctx + (W_o b + b_o): the context bias of sa_m4c.py:600-603 (added to every row,
+            # dead ones included) folds into the out-projection bias; autograd carries its gradient to b and W_o
+            out_bias = out_bias + torch.nn.functional.linear(s.biases.weight, a.output.dense.weight)[0]
         return (s.query.weight, s.query.bias, s.key.weight, s.key.bias, s.value.weight, s.value.bias,
-                a.output.dense.weight, a.output.dense.bias, a.output.LayerNorm.weight, a.output.LayerNorm.bias,
+                a.output.dense.weight, out_bias, a.output.LayerNorm.weight, a.output.LayerNorm.bias,
                 self.intermediate.dense.weight, self.intermediate.dense.bias,
                 self.output.dense.weight, self.output.dense.bias, self.output.LayerNorm.weight,
                 self.output.LayerNorm.bias)

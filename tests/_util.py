@@ -42,9 +42,11 @@ def sam4c_state_shapes(mmt, tb, V, T=20):
     def ln(name):
         out.extend([(name + ".weight", (d,)), (name + ".bias", (d,))])
 
-    def layer(pre):
+    def layer(pre, spatial=False):
         for n in ("query", "key", "value"):
             lin(pre + "attention.self." + n, d, d)
+        if spatial and mmt.get("use_bias"):          # sa_m4c.py:439-443
+            out.append((pre + "attention.self.biases.weight", (1, d)))
         lin(pre + "attention.output.dense", d, d)
         ln(pre + "attention.output.LayerNorm")
         lin(pre + "intermediate.dense", f, d)
@@ -72,7 +74,7 @@ def sam4c_state_shapes(mmt, tb, V, T=20):
     for i in range(mmt["layer_type_list"].count("n")):
         layer("mmt.encoder.normal_layers.%d." % i)
     for i in range(mmt["layer_type_list"].count("s")):
-        layer("mmt.encoder.spatial_layers.%d." % i)
+        layer("mmt.encoder.spatial_layers.%d." % i, spatial=True)
     lin("ocr_ptr_net.query", mmt["ptr_query_size"], d)
     lin("ocr_ptr_net.key", mmt["ptr_query_size"], d)
     lin("classifier", V, d)
@@ -85,3 +87,20 @@ def rel_err(a, b, mask=None):
     if mask is not None:
         a, b = a[mask], b[mask]
     return ((a - b).abs().max() / b.abs().max().clamp(min=1e-30)).item()
+
+
+def usebias_case():
+    """Config, seeded weights and batch of tests/golden/sam4c_usebias.npz (oracle/make_golden.py:make_usebias_golden);
+    the relation graph comes from the oracle builder and is checked against the types the reference produced."""
+    from oracle import graph_oracle
+    from sam_textvqa_b200 import synth
+    from sam_textvqa_b200.config import c3_config
+    g = load_golden("sam4c_usebias.npz")
+    mmt, tb = c3_config(layer_type_list=["s", "s"], mix_list=["share3", "none"], use_bias=True,
+                        hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, obj_drop=0.0, ocr_drop=0.0)
+    tb = dict(tb, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    state = synth.seeded_state(sam4c_state_shapes(mmt, tb, 500), 4)
+    graph_fn = lambda boxes: np.stack([graph_oracle.build_graph(b)["1"] for b in np.asarray(boxes)])
+    batch = synth.make_batch(2, T=20, O=36, R=50, D=12, V=500, seed=3, contexts=(1, 3), graph_fn=graph_fn)
+    assert np.array_equal(batch["spatial_types"].numpy(), g["types"])
+    return g, mmt, tb, state, batch

@@ -8,7 +8,7 @@ import torch
 from oracle import graph_oracle, sam4c_oracle
 from sam_textvqa_b200 import synth
 from sam_textvqa_b200.config import c3_config
-from tests._util import cfg1, golden_batch, load_golden, rel_err, sam4c_state_shapes
+from tests._util import cfg1, golden_batch, load_golden, rel_err, sam4c_state_shapes, usebias_case
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -109,6 +109,74 @@ def test_full_c3_stack_vs_oracle_on_fresh_batch_with_cpu_resident_masks():
         live = ref > -5000
         assert rel_err(scores.detach().cpu(), ref, live) < 1e-3
         assert torch.equal(scores.argmax(-1).cpu(), ref.argmax(-1))
+    finally:
+        ops.set_precision("bf16")
+
+
+def test_c5_dense_mask_stack_with_100_ocr_tokens_vs_oracle():
+    """BASELINE config 3 at test size: mix_list (none, none, share5 x4), 100 objects + 100 OCR tokens (L = 232, the
+    sa_m4c.py:242 zero block generalised to (B, R, 50)), relation graph from the CUDA builder expanded for c = 5;
+    logits and loss gradients against the CPU oracle."""
+    from sam_textvqa_b200 import ops, spatial_utils
+    mmt, tb = c3_config(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, obj_drop=0.0, ocr_drop=0.0,
+                        mix_list=["none", "none", "share5", "share5", "share5", "share5"])
+    tb = dict(tb, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    state = synth.seeded_state(sam4c_state_shapes(mmt, tb, V), 2)
+    model = _model(mmt, tb, state).train()
+    graph_fn = lambda boxes: spatial_utils.build_graph_batch(boxes, 0.5)[0]
+    batch = synth.make_batch(2, O=100, R=100, V=V, seed=9, contexts=(1, 5), graph_fn=graph_fn)
+    assert batch["spatial_adj_matrices"]["5"].shape == (2, 200, 200, 12)
+    ops.set_precision("bf16x3")
+    ops.clear_weight_cache()
+    try:
+        bd = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+        bd["spatial_adj_matrices"] = {k: v.to(DEV) for k, v in batch["spatial_adj_matrices"].items()}
+        scores = model(bd)["textvqa_scores"]
+        assert scores.shape == (2, 12, V + 100)
+        P = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+        ref, _, _ = sam4c_oracle.forward(P, batch, mmt, tb, train=True)
+        ref_loss = sam4c_oracle.bce_with_mask_loss(ref, batch["targets"], batch["train_loss_mask"])
+        ref_loss.backward()
+        ref = ref.detach()
+        live = ref > -5000
+        assert rel_err(scores.detach().cpu(), ref, live) < 1e-3
+        assert torch.equal(scores.argmax(-1).cpu(), ref.argmax(-1))
+        loss = ops.bce_with_mask_loss(scores, bd["targets"], bd["train_loss_mask"])
+        loss.backward()
+        assert abs(loss.item() - float(ref_loss)) <= 1e-4 * abs(float(ref_loss))
+        for name in ("classifier.weight", "mmt.encoder.spatial_layers.3.attention.self.query.weight",
+                     "linear_ocr_feat_to_mmt_in.weight", "text_bert.encoder.layer.0.intermediate.dense.weight"):
+            got = dict(model.named_parameters())[name].grad.detach().cpu()
+            assert rel_err(got, P[name].grad) < 2e-3, name
+    finally:
+        ops.set_precision("bf16")
+
+
+def test_context_biases_use_bias_true_vs_reference_golden():
+    """`use_bias: true`: the d-vector added to every context row (sa_m4c.py:600-603) is folded into the out-projection
+    bias; logits, loss and the gradients of the biases / out-projection against the unmodified reference's."""
+    from sam_textvqa_b200 import ops
+    g, mmt, tb, state, batch = usebias_case()
+    model = _model(mmt, tb, state).train()
+    assert "mmt.encoder.spatial_layers.1.attention.self.biases.weight" in model.state_dict()
+    ops.set_precision("bf16x3")
+    ops.clear_weight_cache()
+    try:
+        bd = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+        scores = model(bd)["textvqa_scores"]
+        ref = torch.from_numpy(g["tf/scores"])
+        assert rel_err(scores.detach().cpu(), ref, ref > -5000) < 1e-3
+        assert torch.equal(scores.argmax(-1).cpu(), ref.argmax(-1))
+        loss = ops.bce_with_mask_loss(scores, bd["targets"], bd["train_loss_mask"])
+        loss.backward()
+        assert abs(loss.item() - float(g["tf/loss"])) <= 1e-3 * float(g["tf/loss"])
+        params = dict(model.named_parameters())
+        for k in g.files:
+            if k.startswith("grad/"):
+                got = params[k[5:]].grad.detach().cpu()
+                if got.numel() > 70000:
+                    got = got.flatten()[:: max(1, got.numel() // 4096)]
+                assert rel_err(got, torch.from_numpy(g[k])) < 2e-3, k
     finally:
         ops.set_precision("bf16")
 

@@ -5,7 +5,7 @@ import torch
 
 from oracle import sam4c_oracle as O
 from sam_textvqa_b200 import synth
-from tests._util import cfg1, golden_batch, load_golden, rel_err, sam4c_state_shapes
+from tests._util import cfg1, golden_batch, load_golden, rel_err, sam4c_state_shapes, usebias_case
 
 
 @pytest.fixture(scope="module")
@@ -50,3 +50,21 @@ def test_text_rows_of_spatial_layer_are_dead(setup):
     g = load_golden("attn_unit.npz")
     T = int(g["T"])
     assert np.abs(g["ctx"][:, :T]).max() == 0.0
+
+
+def test_context_biases_use_bias_true():
+    """`use_bias: true` (sa_m4c.py:439-443, 600-603): two spatial layers, logits / loss / gradients of the unmodified
+    reference."""
+    g, mmt, tb, P, batch = usebias_case()
+    P = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    scores, _, _ = O.forward(P, batch, mmt, tb, train=True)
+    assert rel_err(scores, g["tf/scores"]) < 2e-6
+    loss = O.bce_with_mask_loss(scores, batch["targets"], batch["train_loss_mask"])
+    assert abs(loss.item() - float(g["tf/loss"])) < 1e-4 * float(g["tf/loss"])
+    loss.backward()
+    for k in g.files:
+        if k.startswith("grad/"):
+            got = P[k[5:]].grad
+            if got.numel() > 70000:
+                got = got.flatten()[:: max(1, got.numel() // 4096)]
+            assert rel_err(got, torch.from_numpy(g[k])) < 2e-4, k
