@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #define SAMK_OK 0
 #define SAMK_ERR_ARG -1
@@ -14,6 +15,40 @@ namespace samk {
 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with the stream-serialization attribute may start (block
+// scheduling, barrier / TMEM set-up) while its predecessor in the stream drains; pdl_wait() returns once the
+// predecessor has completed and its writes are visible, so it sits before the first global-memory access.
+// pdl_release() lets the successor start its own preamble; it is placed after pdl_wait(), so at most one kernel
+// runs ahead.  Both are no-ops for a kernel launched without the attribute.  SAMK_PDL: 0 off, 1 GEMMs, 2 + LayerNorm.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+static inline int pdl_level() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SAMK_PDL");
+    v = e ? atoi(e) : 0;
+    if (v < 0) v = 0;
+  }
+  return v;
+}
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_maybe_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                           bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-7 counter RNG (7 rounds: the fewest that pass BigCrush, Salmon et al. SC'11): the

@@ -108,6 +108,8 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
                      float eps, float* __restrict__ y, void* __restrict__ y2, int y2_bf16, int rows, int cols) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  pdl_wait();
+  pdl_release();
   for (int r = warp; r < rows; r += nwarps) {
     float4 v[kMaxVec];
     int nvec = 0;
@@ -171,6 +173,8 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
   float4* sd = sb + c4n;
   for (int c = lane; c < 3 * c4n; c += 32) sg[c] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
+  pdl_wait();
+  pdl_release();
   const bool want_d = dxd != nullptr || dbias != nullptr;
   const uint64_t row_groups = (uint64_t)((cols + 3) >> 2);
   for (int r = warp; r < rows; r += nwarps) {
@@ -845,7 +849,8 @@ int samk_layernorm_fwd(const float* x, const float* gamma, const float* beta, fl
   SAMK_REQUIRE(x && gamma && beta && (y || y2) && rows >= 0, "bad argument");
   SAMK_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 1024, "cols must be a multiple of 4, <= 1024");
   if (!rows) return SAMK_OK;
-  layernorm_fwd_kernel<<<grid_for(rows, 8), kRowThreads, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, y, y2, y2_dtype == SAMK_DT_BF16, rows, cols);
+  launch_maybe_pdl(layernorm_fwd_kernel, dim3(grid_for(rows, 8)), dim3(kRowThreads), 0, (cudaStream_t)stream,
+                   pdl_level() >= 2, x, gamma, beta, eps, y, y2, (int)(y2_dtype == SAMK_DT_BF16), rows, cols);
   return check_launch(__func__);
 }
 
@@ -858,9 +863,10 @@ int samk_layernorm_bwd(const float* dy, const float* x, const float* gamma, floa
   int grid = grid_for(rows, kLnBwdWarps * 4);
   if (grid > 592) grid = 592;   // partials workspace is sized for 592 blocks (samk_layernorm_bwd_partials)
   const int smem = kLnBwdWarps * 3 * cols * (int)sizeof(float);
-  layernorm_bwd_kernel<<<grid, kLnBwdWarps * 32, smem, (cudaStream_t)stream>>>(
-      dy, x, gamma, eps, dx, dxd, dxd_dtype == SAMK_DT_BF16, drop_p > 0.f ? drop_threshold(drop_p) : 0u,
-      drop_keep_scale(drop_p), seed, offset, dgamma, dbeta, dbias, partials, rows, cols);
+  launch_maybe_pdl(layernorm_bwd_kernel, dim3(grid), dim3(kLnBwdWarps * 32), (size_t)smem, (cudaStream_t)stream,
+                   pdl_level() >= 2, dy, x, gamma, eps, dx, dxd, (int)(dxd_dtype == SAMK_DT_BF16),
+                   drop_p > 0.f ? drop_threshold(drop_p) : 0u, drop_keep_scale(drop_p), seed, offset, dgamma, dbeta,
+                   dbias, partials, rows, cols);
   int rc = check_launch(__func__);
   if (rc || !partials) return rc;
   ln_bwd_finalize_kernel<<<dim3((cols + 31) / 32, 3), 1024, 0, (cudaStream_t)stream>>>(partials, grid, cols, dgamma, dbeta, dbias);

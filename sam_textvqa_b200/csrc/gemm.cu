@@ -400,6 +400,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();        // everything above overlapped the previous kernel's tail (programmatic dependent launch)
+  pdl_release();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -679,11 +681,13 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiArgs
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_level() >= 1 ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, M, N, K, split_k);
   if (e != cudaSuccess) {
     cudaGetLastError();

@@ -137,13 +137,13 @@ def test_c5_dense_mask_stack_with_100_ocr_tokens_vs_oracle():
         ref, _, _ = sam4c_oracle.forward(P, batch, mmt, tb, train=True)
         ref_loss = sam4c_oracle.bce_with_mask_loss(ref, batch["targets"], batch["train_loss_mask"])
         ref_loss.backward()
-        ref = ref.detach()
+        ref, ref_loss = ref.detach(), ref_loss.item()
         live = ref > -5000
         assert rel_err(scores.detach().cpu(), ref, live) < 1e-3
         assert torch.equal(scores.argmax(-1).cpu(), ref.argmax(-1))
         loss = ops.bce_with_mask_loss(scores, bd["targets"], bd["train_loss_mask"])
         loss.backward()
-        assert abs(loss.item() - float(ref_loss)) <= 1e-4 * abs(float(ref_loss))
+        assert abs(loss.item() - ref_loss) <= 1e-4 * abs(ref_loss)
         for name in ("classifier.weight", "mmt.encoder.spatial_layers.3.attention.self.query.weight",
                      "linear_ocr_feat_to_mmt_in.weight", "text_bert.encoder.layer.0.intermediate.dense.weight"):
             got = dict(model.named_parameters())[name].grad.detach().cpu()
