@@ -112,7 +112,7 @@ def cpu_port_step_fn(B, seed, threads):
         loss.backward()
         for v in P.values():
             v.grad = None
-        return float(loss)
+        return float(loss.detach())
 
     return step, "oracle port (torch CPU fp32, reference op sequence incl. dense masks, unique-check, dropout), B=%d" % B
 
