@@ -350,11 +350,38 @@ def run_samk(args):
     torch.cuda.synchronize()
     prof, ops.gemm_profile = ops.gemm_profile, None
     aprof, ops.attn_profile = ops.attn_profile, None
-    g_ms = sum(s.elapsed_time(e) for s, e, _ in prof) / 2
-    g_flop = sum(f for _, _, f in prof) / 2
+    g_ms = sum(s.elapsed_time(e) for s, e, _, _ in prof) / 2
+    g_flop = sum(f for _, _, f, _ in prof) / 2
     n_gemm = len(prof) // 2
     peak_tf, peak_gbs, peak_src = peaks()
     achieved = g_flop / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    # the same live events per GEMM shape: the five shapes that take the most time in a step, each with its algorithmic
+    # operand bytes (bf16 A and B read once, output written once) and, where profiles/ holds an `ncu --set full`
+    # capture of that shape, the measured DRAM bytes per launch
+    ncu_dram = {   # (M, N, K, a_mn, b_mn) -> (read MB, write MB, file)  -- profiles/r01j_ncu_summary.txt
+        (768, 3072, 23296, True, True): (342.2, 10.0, "r01j_ncu_gemm_ffn2_wgrad_raw.csv"),
+        (23296, 3072, 768, False, False): (40.6, 234.0, "r01j_ncu_gemm_ffn1_fwd_raw.csv"),
+        (23296, 3072, 768, False, True): (183.7, 110.0, "r01j_ncu_gemm_ffn2_dgrad_raw.csv"),
+        (23296, 2304, 768, False, False): (39.4, 54.9, "r01j_ncu_gemm_qkv_fwd_raw.csv"),
+    }
+    groups = {}
+    for s_, e_, f_, shape in prof:
+        g = groups.setdefault(shape, [0.0, 0, f_])
+        g[0] += s_.elapsed_time(e_)
+        g[1] += 1
+    by_shape = []
+    for shape, (tot_ms, cnt, f_) in sorted(groups.items(), key=lambda kv: -kv[1][0])[:5]:
+        us = tot_ms / cnt * 1e3
+        tf = f_ / (us * 1e-6) / 1e12
+        Mg, Ng, Kg, amn, bmn = shape
+        item = {"M": Mg, "N": Ng, "K": Kg, "a_mn": amn, "b_mn": bmn, "launches_per_step": cnt // 2,
+                "us_per_launch": us, "achieved": tf, "frac": tf / peak_tf, "share_of_step": tot_ms / 2 / ms if ms > 0 else None,
+                "operand_MB": (Mg * Kg + Ng * Kg) * 2 / 1e6}
+        if shape in ncu_dram and B == 128:
+            rd, wr, src = ncu_dram[shape]
+            item["traffic"] = (rd + wr) * 1e6
+            item["traffic_src"] = "profiles/" + src
+        by_shape.append(item)
     # the north-star kernel: fused masked attention of the MMT layers (L = 182), HBM-bound at this length
     Lm = CFG["T"] + CFG["O"] + CFG["R"] + CFG["D"]
     attention = {}
@@ -394,6 +421,7 @@ def run_samk(args):
                      "traffic": None, "peak_source": peak_src + " (sustained bf16)",
                      "gemm_ms_per_step": g_ms, "gemm_share_of_step": g_ms / ms if ms > 0 else None,
                      "step_flop_frac_of_peak": value / world * FLOP_PER_SAMPLE / (peak_tf * 1e12),
+                     "by_shape": by_shape,
                      "traffic_note": "aggregate over all GEMM shapes of the step, so no single per-launch figure; per-shape "
                                      "DRAM bytes from ncu --set full are in profiles/r01i_ncu_summary.txt "
                                      "(e.g. FFN2 wgrad 342+9 MB vs 322 MB algorithmic)"},

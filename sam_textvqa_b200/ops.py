@@ -24,7 +24,7 @@ _PRECISION = os.environ.get("SAMK_PRECISION", "bf16")
 _GEMM_IMPL = int(os.environ.get("SAMK_GEMM_IMPL", "0"))
 _ATTN_IMPL = int(os.environ.get("SAMK_ATTN_IMPL", "0"))
 launch_count = 0  # kernels launched through this module (bench.py reports it)
-gemm_profile = None  # bench.py: list collecting (start_event, end_event, algorithmic_flops) per GEMM launch
+gemm_profile = None  # bench.py: list collecting (start_event, end_event, algorithmic_flops, (M, N, K, a_mn, b_mn)) per GEMM launch
 grad_ready_hook = None  # dp.FlatGradBuffer.enable_overlap: called with the parameters a backward op has just finished
 attn_profile = None  # bench.py: list collecting (kind, L, start_event, end_event, algorithmic_bytes, dense_flops) per launch
 
@@ -266,7 +266,7 @@ def gemm(a, a_mn, b, b_mn, M, N, K, out, bias=None, act=0, pre=None, aux=None, d
                                ctypes.byref(ep), split_k, _GEMM_IMPL, stream_ptr()), "gemm")
     if gemm_profile is not None:
         ev1.record()
-        gemm_profile.append((ev0, ev1, 2.0 * M * N * K))
+        gemm_profile.append((ev0, ev1, 2.0 * M * N * K, (int(M), int(N), int(K), bool(a_mn), bool(b_mn))))
     _count()
     return out
 
