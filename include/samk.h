@@ -164,6 +164,17 @@ int samk_bce_loss(const float* scores, const float* targets, const float* loss_m
                   float* scratch, int rows, int ncls, void* stream);
 int samk_scale_inplace(float* x, long long n, const float* scale_dev, void* stream);
 
+/* ---- optimizer step on flat fp32 buffers ------------------------------------------------------
+ * The caller's side of the path (train.py:139-143): clip_gradients (sam/task_utils.py:33-34 = clip_grad_norm_ over all
+ * parameters, coefficient min(max_norm / (norm + 1e-6), 1)) fused into torch.optim.Adam's update (task_utils.py:42,
+ * defaults betas (0.9, 0.999), eps 1e-8, no weight decay / amsgrad).
+ * samk_sumsq:     *out_accum += sum x[i]^2 (double; zero it first; call once per gradient range).
+ * samk_adam_step: one parameter range with one learning rate (a param group of get_optimizer_parameters,
+ *                 sa_m4c.py:349-371); step = 1-based update count; grad_sumsq NULL = no clipping. grad is not modified. */
+int samk_sumsq(const float* x, long long n, double* out_accum, void* stream);
+int samk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, double lr, double beta1,
+                   double beta2, double eps, int step, const double* grad_sumsq, double max_norm, void* stream);
+
 /* ---- masked multi-head attention -------------------------------------------------------------
  * Replaces SpatialBertSelfAttention.forward steps (1),(3)-(7) (sa_m4c.py:475-552, 562-598) and
  * the BertSelfAttention of the 'n' layers / TextBert (sa_m4c.py:743, 391); the [B,L,L,H] masks are

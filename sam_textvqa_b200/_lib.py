@@ -75,6 +75,9 @@ SIGNATURES = {
                                     c_int, c_void_p]),
     "samk_bce_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "samk_scale_inplace": (c_int, [c_void_p, c_ll, c_void_p, c_void_p]),
+    "samk_sumsq": (c_int, [c_void_p, c_ll, c_void_p, c_void_p]),
+    "samk_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_double, c_double, c_double, c_double, c_int,
+                               c_void_p, c_double, c_void_p]),
     "samk_attn_fwd": (c_int, [ctypes.POINTER(AttnParams), c_int, c_void_p]),
     "samk_attn_bwd": (c_int, [ctypes.POINTER(AttnParams), c_int, c_void_p]),
     "samk_attn_delta": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

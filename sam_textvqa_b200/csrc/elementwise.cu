@@ -802,6 +802,44 @@ __global__ void scale_kernel(float* __restrict__ x, long long n, const float* __
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * blockDim.x) x[i] *= v;
 }
 
+// ---- optimizer step on flat buffers (sam/task_utils.py:33-34 clip_grad_norm_, :42 torch.optim.Adam defaults) ----
+__global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* __restrict__ out) {
+  float acc = 0.f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n; i += stride) acc += x[i] * x[i];
+  acc = warp_sum(acc);
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) atomicAdd(out, (double)t);
+  }
+}
+
+// p, m, v updated in place; g read only.  clip: g *= min(max_norm / (||g_all|| + 1e-6), 1) with ||g_all||^2 in *sumsq
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float neg_step_size, float one_minus_beta1, float beta2,
+                            float one_minus_beta2, float eps, float sqrt_bc2, const double* __restrict__ sumsq,
+                            float max_norm) {
+  float coef = 1.0f;
+  if (sumsq) {
+    const float norm = (float)sqrt(*sumsq);
+    coef = fminf(max_norm / (norm + 1e-6f), 1.0f);
+  }
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n; i += stride) {
+    const float gi = g[i] * coef;
+    const float mi = m[i] + one_minus_beta1 * (gi - m[i]);           // torch: exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = v[i] * beta2 + one_minus_beta2 * gi * gi;       // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sqrt_bc2 + eps;                  // (sqrt(v) / sqrt(1 - beta2^t)) + eps
+    p[i] = p[i] + (neg_step_size * mi) / denom;                      // addcdiv_(exp_avg, denom, value = -lr / (1 - beta1^t))
+  }
+}
+
 static inline int grid_for(long long work, int per_block) {
   long long g = (work + per_block - 1) / per_block;
   int cap = 148 * 16;
@@ -1026,6 +1064,24 @@ int samk_bce_loss(const float* scores, const float* targets, const float* loss_m
   if (!rows || !ncls) return SAMK_OK;
   sum_kernel<<<grid_for(rows, 256), 256, 0, s>>>(loss_mask, rows, scratch);
   bce_loss_kernel<<<grid_for((long long)rows * ncls, 1024), 256, 0, s>>>(scores, targets, loss_mask, dscores, loss_out, scratch, (long long)rows * ncls, ncls);
+  return check_launch(__func__);
+}
+
+int samk_sumsq(const float* x, long long n, double* out_accum, void* stream) {
+  SAMK_REQUIRE(x && out_accum && n >= 0, "bad argument");
+  if (!n) return SAMK_OK;
+  sumsq_kernel<<<grid_for(n, 2048), 256, 0, (cudaStream_t)stream>>>(x, n, out_accum);
+  return check_launch(__func__);
+}
+
+int samk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, double lr, double beta1,
+                   double beta2, double eps, int step, const double* grad_sumsq, double max_norm, void* stream) {
+  SAMK_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "bad argument");
+  if (!n) return SAMK_OK;
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  adam_kernel<<<grid_for(n, 1024), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(-lr / bc1),
+                                                                  (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
+                                                                  (float)eps, (float)sqrt(bc2), grad_sumsq, (float)max_norm);
   return check_launch(__func__);
 }
 

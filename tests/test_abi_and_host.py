@@ -177,3 +177,28 @@ def test_relation_bits_contract_on_host():
 def test_graph_step_module_imports_without_gpu():
     import sam_textvqa_b200.graph_step as gs
     assert hasattr(gs.GraphedTrainStep, "run") and hasattr(gs.GraphedTrainStep, "load")
+
+
+def test_warmup_schedule_matches_reference_formula_and_flat_adam_needs_gpu():
+    """sam/task_utils.py:46-55 restated in optim.warmup_lr_lambda; FlatAdam has no CPU path."""
+    from bisect import bisect
+    from sam_textvqa_b200 import optim
+    from sam_textvqa_b200.dp import FlatGradBuffer
+    warm, factor, miles, decay = 1000, 0.2, [14000, 19000], 0.1
+    fn = optim.warmup_lr_lambda(warm, factor, miles, decay)
+    for it in (0, 1, 500, 1000, 1001, 13999, 14000, 14001, 19000, 24000):
+        if it <= warm:
+            a = float(it) / float(warm)
+            ref = factor * (1.0 - a) + a
+        else:
+            ref = pow(decay, bisect(miles, it))
+        assert fn(it) == ref, it
+    w = torch.nn.Parameter(torch.zeros(4, 4))
+    b = torch.nn.Parameter(torch.zeros(4))
+    groups = [{"params": [b], "lr": 1e-4}, {"params": [w], "lr": 1e-5}]
+    grads = optim.flat_grad_buffer_for(groups)
+    assert [p is q for p, q in zip(grads.params, [b, w])] == [True, True]
+    with pytest.raises(RuntimeError):
+        optim.FlatAdam(groups, grads)
+    with pytest.raises(ValueError):          # layout not grouped
+        optim.FlatAdam(groups, FlatGradBuffer([w, b]))

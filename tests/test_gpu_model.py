@@ -181,6 +181,42 @@ def test_context_biases_use_bias_true_vs_reference_golden():
         ops.set_precision("bf16")
 
 
+def test_two_updates_with_flat_adam_equal_torch_adam_with_clipping(golden):
+    """train.py:139-143 on both sides: our fused clip + Adam on the flat buffers against clip_grad_norm_ +
+    torch.optim.Adam on a second copy of the model; logits after two updates must agree (this also checks that the
+    cached bf16 weight operands are refreshed after an update that wrote through raw pointers)."""
+    from sam_textvqa_b200 import ops, optim
+    g, mmt, tb, state, _ = golden
+    batch = golden_batch(g)
+    ours, theirs = _model(mmt, tb, state).train(), _model(mmt, tb, state).train()
+    groups = ours.get_optimizer_parameters(1e-4)
+    grads = optim.flat_grad_buffer_for(groups)
+    opt = optim.FlatAdam(groups, grads, max_grad_norm=0.25)
+    ref_opt = torch.optim.Adam(theirs.get_optimizer_parameters(1e-4), lr=1e-4)
+    ops.set_precision("bf16x3")
+    ops.clear_weight_cache()
+    try:
+        bd = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+        for _ in range(2):
+            for model in (ours, theirs):
+                scores = model(dict(bd))["textvqa_scores"]
+                ops.bce_with_mask_loss(scores, bd["targets"], bd["train_loss_mask"]).backward()
+            opt.step()
+            opt.zero_grad()
+            torch.nn.utils.clip_grad_norm_(theirs.parameters(), 0.25)
+            ref_opt.step()
+            ref_opt.zero_grad(set_to_none=True)
+        with torch.no_grad():
+            a = ours(dict(bd))["textvqa_scores"]
+            b = theirs(dict(bd))["textvqa_scores"]
+        live = b > -5000
+        assert rel_err(a, b, live) < 1e-4
+        first = torch.from_numpy(g["tf/scores"]).to(DEV)
+        assert rel_err(a, first, live) > 1e-3          # the updates did change the model
+    finally:
+        ops.set_precision("bf16")
+
+
 def test_dropout_training_step_runs_and_is_reproducible(golden):
     from sam_textvqa_b200 import ops
     g, mmt, tb, state, _ = golden

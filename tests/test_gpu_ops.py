@@ -293,3 +293,33 @@ def test_tcgen05_attention_matches_exact_fp32_kernel(ops, case):
     dq_ref = ops.attention_bwd(w16.float(), qkv32, ctx_ref, lse_ref, valid, bits, dims, spatial, quad, p, drop)
     dq = ops.attention_bwd(w16, qkv16, ctx, lse, valid, bits, dims, spatial, quad, p, drop)
     assert rel_err(dq.float(), dq_ref) < 1e-2
+
+
+def test_fused_clip_adam_matches_torch_adam_and_clip_grad_norm(ops):
+    """optim.FlatAdam (samk_sumsq + samk_adam_step) against the reference's optimizer side (train.py:139-143):
+    nn.utils.clip_grad_norm_ + torch.optim.Adam with two learning-rate groups, four updates."""
+    from sam_textvqa_b200 import optim
+    g = torch.Generator().manual_seed(11)
+    shapes = [(300, 768), (768,), (5, 7, 3), (1,), (2304, 768)]
+    ours = [torch.nn.Parameter(torch.randn(*s, generator=g).to(DEV)) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    split = 2
+    groups = [{"params": ours[:split], "lr": 1e-3}, {"params": ours[split:], "lr": 1e-4}]
+    grads = optim.flat_grad_buffer_for(groups)
+    opt = optim.FlatAdam(groups, grads, max_grad_norm=0.25)
+    ref_opt = torch.optim.Adam([{"params": ref[:split], "lr": 1e-3}, {"params": ref[split:], "lr": 1e-4}], lr=1e-3)
+    for step in range(4):
+        scale = 10.0 if step % 2 == 0 else 1e-3          # clipped and unclipped updates
+        for p, q in zip(ours, ref):
+            gr = (scale * torch.randn(*p.shape, generator=g)).to(DEV)
+            p.grad.copy_(gr)
+            q.grad = gr.clone()
+        norm_ref = torch.nn.utils.clip_grad_norm_(ref, 0.25)
+        assert abs(opt.grad_norm().item() - norm_ref.item()) <= 1e-5 * norm_ref.item()
+        opt.step()
+        ref_opt.step()
+        for p, q in zip(ours, ref):
+            assert (p.detach() - q.detach()).abs().max().item() <= 2e-6 * max(1.0, q.detach().abs().max().item()), step
+    assert ours[0].data.data_ptr() == opt.flat_params.data_ptr()       # parameters are views of the flat buffer
+    assert ours[0]._version >= 4                                        # weight-operand caches see the updates
+    assert opt.step_count == 4
