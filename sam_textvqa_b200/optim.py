@@ -28,10 +28,11 @@ def flat_grad_buffer_for(param_groups):
 
 
 class FlatAdam(object):
-    """param_groups: list of {"params": [...], "lr": float} (sa_m4c.py:349-371); grads: the FlatGradBuffer that holds
-    their gradients in the same order (see `flat_grad_buffer_for`)."""
+    """param_groups: list of {"params": [...], ["lr": float]} as returned by `get_optimizer_parameters`
+    (sa_m4c.py:349-371; its first group carries no "lr" and takes the optimizer default `lr`, like torch.optim.Adam);
+    grads: the FlatGradBuffer that holds their gradients in the same order (see `flat_grad_buffer_for`)."""
 
-    def __init__(self, param_groups, grads, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=None):
+    def __init__(self, param_groups, grads, lr=None, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=None):
         self.grads = grads
         self.betas, self.eps = (float(betas[0]), float(betas[1])), float(eps)
         self.max_grad_norm = None if max_grad_norm is None else float(max_grad_norm)
@@ -53,7 +54,10 @@ class FlatAdam(object):
                                  "(build it with optim.flat_grad_buffer_for)")
             begin = offs[ids[0]]
             end = offs[ids[-1]] + ps[-1].numel()
-            self.param_groups.append({"params": ps, "lr": float(g["lr"]), "initial_lr": float(g["lr"]),
+            group_lr = g.get("lr", lr)
+            if group_lr is None:
+                raise ValueError("a param group without 'lr' needs the optimizer default: FlatAdam(..., lr=base_lr)")
+            self.param_groups.append({"params": ps, "lr": float(group_lr), "initial_lr": float(group_lr),
                                       "range": (begin, end)})
             cursor += len(ids)
         if cursor != len(grads.params):

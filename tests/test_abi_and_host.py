@@ -195,10 +195,12 @@ def test_warmup_schedule_matches_reference_formula_and_flat_adam_needs_gpu():
         assert fn(it) == ref, it
     w = torch.nn.Parameter(torch.zeros(4, 4))
     b = torch.nn.Parameter(torch.zeros(4))
-    groups = [{"params": [b], "lr": 1e-4}, {"params": [w], "lr": 1e-5}]
+    groups = [{"params": [b]}, {"params": [w], "lr": 1e-5}]          # first group without lr, as get_optimizer_parameters
     grads = optim.flat_grad_buffer_for(groups)
     assert [p is q for p, q in zip(grads.params, [b, w])] == [True, True]
-    with pytest.raises(RuntimeError):
+    with pytest.raises(ValueError):          # no default lr for the group that has none
         optim.FlatAdam(groups, grads)
+    with pytest.raises(RuntimeError):
+        optim.FlatAdam(groups, grads, lr=1e-4)
     with pytest.raises(ValueError):          # layout not grouped
-        optim.FlatAdam(groups, FlatGradBuffer([w, b]))
+        optim.FlatAdam(groups, FlatGradBuffer([w, b]), lr=1e-4)

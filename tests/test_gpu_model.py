@@ -191,7 +191,7 @@ def test_two_updates_with_flat_adam_equal_torch_adam_with_clipping(golden):
     ours, theirs = _model(mmt, tb, state).train(), _model(mmt, tb, state).train()
     groups = ours.get_optimizer_parameters(1e-4)
     grads = optim.flat_grad_buffer_for(groups)
-    opt = optim.FlatAdam(groups, grads, max_grad_norm=0.25)
+    opt = optim.FlatAdam(groups, grads, lr=1e-4, max_grad_norm=0.25)
     ref_opt = torch.optim.Adam(theirs.get_optimizer_parameters(1e-4), lr=1e-4)
     ops.set_precision("bf16x3")
     ops.clear_weight_cache()
