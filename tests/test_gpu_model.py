@@ -210,7 +210,7 @@ def test_two_updates_with_flat_adam_equal_torch_adam_with_clipping(golden):
             a = ours(dict(bd))["textvqa_scores"]
             b = theirs(dict(bd))["textvqa_scores"]
         live = b > -5000
-        assert rel_err(a, b, live) < 1e-4
+        assert rel_err(a, b, live) < 5e-4          # measured < 1e-4; the wgrad split-K atomics are not run-to-run exact
         first = torch.from_numpy(g["tf/scores"]).to(DEV)
         assert rel_err(a, first, live) > 1e-3          # the updates did change the model
     finally:
