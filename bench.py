@@ -346,8 +346,15 @@ def run_samk(args):
     ops.gemm_profile = []
     ops.attn_profile = []
     for _ in range(2):
-        eager_step(resident, resident_adj)     # per-launch events cannot be recorded inside a graph replay
-    torch.cuda.synchronize()
+        # per-launch events cannot be recorded inside a graph replay, and the eager loop is launch-bound: an event pair
+        # around a kernel the GPU is waiting for also times the host's launch latency.  A spin kernel in front keeps the
+        # GPU busy while the host enqueues the whole step, so the events bracket back-to-back kernel executions.
+        try:
+            torch.cuda._sleep(int(4e7))        # ~20 ms at 1.9 GHz; the host needs ~10-15 ms to enqueue a step
+        except Exception:                      # private torch API: without it the figures are only more pessimistic
+            pass
+        eager_step(resident, resident_adj)
+        torch.cuda.synchronize()
     prof, ops.gemm_profile = ops.gemm_profile, None
     aprof, ops.attn_profile = ops.attn_profile, None
     g_ms = sum(s.elapsed_time(e) for s, e, _, _ in prof) / 2
