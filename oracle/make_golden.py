@@ -13,6 +13,10 @@ reference tree does not exist.
                     under 10 MB), seed-0 weights: teacher-forced logits, loss, selected
                     gradients, greedy-decoded tokens, per-stage activations.
   attn_unit.npz     SpatialBertSelfAttention.forward on random hidden states, B=2.
+  sam4c_c3.npz      the shipped layer schedule (n,n,s,s,s,s; share3), 100 objects (L = 182), B=3, V=500, seed-1
+                    weights, batch = synth.make_batch(3, seed=5): logits, loss, gradients.  Same model and batch as
+                    tests/test_gpu_model.py::test_full_c3_stack_vs_oracle_on_fresh_batch_with_cpu_resident_masks, so the
+                    oracle output that GPU test compares against is itself pinned to the unmodified reference.
   sam4c_usebias.npz two spatial layers with `use_bias: true` (sa_m4c.py:439-443, 600-603; off in the shipped
                     configs), B=2, cfg1 geometry: logits, loss, gradients of the context biases and of the
                     out-projection they fold into.  The batch is regenerated in the tests from
@@ -163,6 +167,32 @@ def make_sam4c_golden(M, S, registry):
     print("sam4c_cfg1.npz loss", float(loss), "greedy tokens", bd["train_prev_inds"][0].tolist())
 
 
+def make_c3_golden(M, S, registry):
+    V = 500
+    registry.answer_vocab = ["w%d" % i for i in range(V)]
+    mmt, tb = c3_config(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, obj_drop=0.0, ocr_drop=0.0)
+    tb = dict(tb, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    model = build_ref_model(M, mmt, tb, seed=1).train()
+    batch = synth.make_batch(3, V=V, seed=5, contexts=(1, 3), graph_fn=ref_graph_fn(S))
+    bd = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    scores = model(bd)["textvqa_scores"]
+    losses = torch.nn.functional.binary_cross_entropy_with_logits(scores, batch["targets"], reduction="none")
+    loss = (losses * batch["train_loss_mask"].unsqueeze(-1)).sum() / batch["train_loss_mask"].sum().clamp(min=1)
+    loss.backward()
+    out = {"types": batch["spatial_types"].numpy(), "tf/scores": scores.detach().numpy(), "tf/loss": loss.detach().numpy()}
+    grads = dict((n, p.grad) for n, p in model.named_parameters() if p.grad is not None)
+    for n in ["classifier.bias", "mmt.encoder.normal_layers.0.attention.self.query.weight",
+              "mmt.encoder.normal_layers.1.output.dense.bias",
+              "mmt.encoder.spatial_layers.0.attention.self.key.weight",
+              "mmt.encoder.spatial_layers.3.intermediate.dense.weight",
+              "text_bert.encoder.layer.2.attention.output.LayerNorm.weight",
+              "linear_obj_feat_to_mmt_in.weight"]:
+        g = grads[n]
+        out["grad/" + n] = g.numpy() if g.numel() <= 70000 else g.flatten()[:: max(1, g.numel() // 4096)].numpy()
+    np.savez_compressed(os.path.join(GOLD, "sam4c_c3.npz"), **out)
+    print("sam4c_c3.npz loss", float(loss))
+
+
 def make_usebias_golden(M, S, registry):
     V = 500
     registry.answer_vocab = ["w%d" % i for i in range(V)]
@@ -224,6 +254,7 @@ def main():
     make_attn_golden(M)
     make_sam4c_golden(M, S, registry)
     make_usebias_golden(M, S, registry)
+    make_c3_golden(M, S, registry)
 
 
 if __name__ == "__main__":

@@ -68,3 +68,31 @@ def test_context_biases_use_bias_true():
             if got.numel() > 70000:
                 got = got.flatten()[:: max(1, got.numel() // 4096)]
             assert rel_err(got, torch.from_numpy(g[k])) < 2e-4, k
+
+
+def test_shipped_c3_layer_schedule_full_stack():
+    """n,n,s,s,s,s with 100 objects (L = 182) against the unmodified reference (tests/golden/sam4c_c3.npz): the same
+    model (seed-1 weights) and batch (synth.make_batch(3, seed=5)) as the GPU test of the full c3 stack, so what that
+    test compares against is pinned here."""
+    from oracle import graph_oracle
+    from sam_textvqa_b200.config import c3_config
+    g = load_golden("sam4c_c3.npz")
+    mmt, tb = c3_config(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, obj_drop=0.0, ocr_drop=0.0)
+    tb = dict(tb, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    P = synth.seeded_state(sam4c_state_shapes(mmt, tb, 500), 1)
+    P = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    graph_fn = lambda boxes: np.stack([graph_oracle.build_graph(b)["1"] for b in np.asarray(boxes)])
+    batch = synth.make_batch(3, V=500, seed=5, contexts=(1, 3), graph_fn=graph_fn)
+    assert np.array_equal(batch["spatial_types"].numpy(), g["types"])
+    scores, _, _ = O.forward(P, batch, mmt, tb, train=True)
+    assert rel_err(scores, g["tf/scores"]) < 5e-6
+    assert torch.equal(scores.argmax(-1), torch.from_numpy(g["tf/scores"]).argmax(-1))
+    loss = O.bce_with_mask_loss(scores, batch["targets"], batch["train_loss_mask"])
+    assert abs(loss.item() - float(g["tf/loss"])) < 1e-4 * float(g["tf/loss"])
+    loss.backward()
+    for k in g.files:
+        if k.startswith("grad/"):
+            got = P[k[5:]].grad
+            if got.numel() > 70000:
+                got = got.flatten()[:: max(1, got.numel() // 4096)]
+            assert rel_err(got, torch.from_numpy(g[k])) < 5e-4, k
