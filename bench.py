@@ -29,6 +29,7 @@ FLOP_PER_SAMPLE = 52.356e9      # fwd+bwd, cfg2, torch Flo
 METRIC = "SA-M4C fwd+bwd samples/sec"
 UNIT = "samples/s"
 CFG = dict(T=20, O=100, R=50, D=12, V=5000)
+WORKLOAD = "c3 yml SA-M4C (n,n,s,s,s,s), 20+100+50+12 tokens, d=768, V=5000, train fwd+bwd, dropout 0.1"   # both arms
 
 
 def peaks():
@@ -134,7 +135,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "c3 yml SA-M4C (n,n,s,s,s,s), 20+100+50+12 tokens, d=768, V=5000, train fwd+bwd",
+            "config": {"workload": WORKLOAD,
                        "sample_batch": B},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -415,7 +416,7 @@ def run_samk(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3", "data": "synthetic",
-        "config": {"workload": "c3 yml SA-M4C (n,n,s,s,s,s), 20+100+50+12 tokens, d=768, V=5000, train fwd+bwd, dropout 0.1",
+        "config": {"workload": WORKLOAD,
                    "batch_per_gpu": B, "global_batch": world * B, "parallelism": "dp%d" % world,
                    "launch": "cuda-graph replay of the captured step" if graphed is not None else "eager",
                    "l2": "per-step working set (~6 GB of activations) >> 126 MB L2; no explicit flush"},
