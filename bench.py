@@ -415,7 +415,7 @@ def run_samk(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f16" if args.precision == "f16" else "bf16x3", "data": "synthetic",
         "config": {"workload": WORKLOAD,
                    "batch_per_gpu": B, "global_batch": world * B, "parallelism": "dp%d" % world,
                    "launch": "cuda-graph replay of the captured step" if graphed is not None else "eager",
@@ -459,7 +459,7 @@ def main():
     ap.add_argument("--impl", default="samk", choices=["samk", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="samples per GPU")
     ap.add_argument("--ref-batch", type=int, default=16, help="bounded CPU sample size")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
+    ap.add_argument("--precision", default="f16", choices=["f16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="run 3 bare steps and exit (for ncu launch lists)")
     args = ap.parse_args()

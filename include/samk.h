@@ -10,7 +10,12 @@
  * sizes / leading dimensions (in elements); the last argument is a cudaStream_t passed as void*.
  * Entry points return 0 on success or a negative SAMK_ERR_* code, never throw, never
  * synchronise and never allocate device memory; samk_last_error() gives a thread-local message.
- * bf16 = IEEE bfloat16 bit pattern (uint16_t storage).
+ * bf16 = bfloat16 bit pattern, f16 = IEEE binary16 bit pattern (both uint16_t storage).  The tensor-core path stores
+ * forward activations and weight operands as f16 (11 significant bits: logits within 1e-3 of the fp32 reference,
+ * sa_m4c.py:179-202) and gradients as bf16 (fp32 exponent range).  A tcgen05 product needs both operands in ONE
+ * format, so where a gradient meets a saved f16 activation either the activation has a bf16 copy (written by the
+ * LayerNorm that produced it) or the gradient is re-expressed in f16 with an exactly computed power-of-two scale
+ * (samk_cast_scaled_f16; attention backward: one scale per (sample, head)).  There is no global loss scale.
  */
 #ifndef SAMK_H_
 #define SAMK_H_
@@ -23,6 +28,7 @@ extern "C" {
 
 #define SAMK_DT_F32 0
 #define SAMK_DT_BF16 1
+#define SAMK_DT_F16 2   /* IEEE half: forward activations and weight operands (11 significant bits) */
 
 int samk_version(void);
 const char* samk_last_error(void);
@@ -96,6 +102,8 @@ typedef struct samk_gemm_epilogue {
   int part_rows;
   void* out_part1;
   void* out_part2;
+  const float* alpha_dev; /* optional DEVICE scalar multiplied into alpha by the kernel: 1 / scale of an operand that
+                             samk_cast_scaled_f16 scaled into the f16 range (weight gradients from f16-scaled dY) */
 } samk_gemm_epilogue;
 
 /* split_k >= 1 partitions K over CTAs (requires atomic_add and a pre-zeroed or accumulating out).
@@ -103,22 +111,33 @@ typedef struct samk_gemm_epilogue {
  * GPU unit tests to cross-check the tensor-core kernel. */
 int samk_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major, long long ldb,
                    int M, int N, int K, const samk_gemm_epilogue* ep, int split_k, int impl, void* stream);
+/* same with the 16-bit storage format of the operands given (SAMK_DT_BF16 or SAMK_DT_F16; A and B must agree --
+ * tcgen05.mma kind::f16 faults on mixed formats, measured on B200).  Forward products are f16 x f16; dgrad is
+ * bf16 dY x bf16 weight copy; wgrad is either bf16 dY x bf16 activation copy or f16-scaled dY x f16 activation. */
+int samk_gemm_16(const void* A, int a_dtype, int a_mn_major, long long lda, const void* B, int b_dtype, int b_mn_major,
+                 long long ldb, int M, int N, int K, const samk_gemm_epilogue* ep, int split_k, int impl, void* stream);
 
 /* ---- HBM-bound row kernels ------------------------------------------------------------------
  * fp32 -> bf16 operand cast; fp32 -> three bf16 planes (hi,hi,lo | hi,lo,hi) so that a plain bf16
  * GEMM over the 3x longer K reproduces fp32 products to ~2^-16 ("bf16x3" parity mode). */
 int samk_cast_bf16(const float* x, long long ldx, void* y, long long ldy, int rows, int cols, void* stream);
+int samk_cast_16(const float* x, long long ldx, void* y, long long ldy, int y_dtype, int rows, int cols, void* stream);
+/* y = half(x * S) with S = the power of two that puts max|x| into [2^11, 2^12) (computed on the device, two passes,
+ * saturating conversion); x contiguous, n % 4 == 0, x_dtype F32 or BF16.  scale2: 3 floats of device workspace,
+ * scale2[0] = S, scale2[1] = 1/S (pass as samk_gemm_epilogue.alpha_dev of the product that consumes y). */
+int samk_cast_scaled_f16(const void* x, int x_dtype, long long n, void* y, float* scale2, void* stream);
 int samk_split3_bf16(const float* x, long long ldx, void* y, long long ldy, int rows, int cols, int order,
                      int along_rows, void* stream);
 /* F.normalize(x, dim=-1) of sa_m4c.py:208-209,224-238 (normalize=0: plain copy/cast) */
 int samk_l2norm(const float* x, long long ldx, void* y, long long ldy, int y_dtype, int rows, int cols, int normalize,
                 void* stream);
 /* BertLayerNorm (sa_m4c.py:1016-1028; eps inside the sqrt, biased variance).  y fp32 and/or y2 in
- * y2_dtype.  Backward: dx fp32; optional dxd = dropout_mask(dx) in dxd_dtype (gradient of the dense
+ * y2_dtype and/or y3 in y3_dtype (the f16 copy the next contraction reads and the bf16 copy its weight-gradient
+ * product reads, written in the same pass).  Backward: dx fp32; optional dxd = dropout_mask(dx) in dxd_dtype (gradient of the dense
  * output under the dropout of BertSelfOutput/BertOutput); dgamma, dbeta, dbias (= colsum(dxd)) are
  * ACCUMULATED (+=) into fp32 [cols] buffers (each may be NULL). */
 int samk_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y, void* y2,
-                       int y2_dtype, int rows, int cols, void* stream);
+                       int y2_dtype, void* y3, int y3_dtype, int rows, int cols, void* stream);
 int samk_layernorm_bwd(const float* dy, const float* x, const float* gamma, float eps, float* dx, void* dxd,
                        int dxd_dtype, float drop_p, unsigned long long seed, unsigned long long offset, float* dgamma,
                        float* dbeta, float* dbias, float* partials, int rows, int cols, void* stream);
@@ -163,6 +182,8 @@ int samk_ptr_scores_bwd(const float* dscores, long long ldds, int col_off, const
 int samk_bce_loss(const float* scores, const float* targets, const float* loss_mask, float* dscores, float* loss_out,
                   float* scratch, int rows, int ncls, void* stream);
 int samk_scale_inplace(float* x, long long n, const float* scale_dev, void* stream);
+/* out = [a ; b ; c], n floats each: the three nn.Linear biases of the fused q|k|v projection (sa_m4c.py:429-431) */
+int samk_concat3_f32(const float* a, const float* b, const float* c, float* out, int n, void* stream);
 
 /* ---- optimizer step on flat fp32 buffers ------------------------------------------------------
  * The caller's side of the path (train.py:139-143): clip_gradients (sam/task_utils.py:33-34 = clip_grad_norm_ over all
@@ -183,12 +204,13 @@ int samk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
  *   rel_bits uint16 [B,A,A] (bit h = head h may attend i->j; NULL when spatial == 0),
  *   quadrant_mask bit (3*seg_i+seg_j), seg 0/1/2 = text/entity/decoder (attention_mask_quadrants q
  *   of the yml maps to bit q-1).  Backward: dctx -> dqkv (same layout), delta [B,H,L] scratch.
- * impl 0 = product kernel for the dtype (bf16: tensor cores; f32: exact fp32), 1 = force the exact
- * fp32 SIMT kernel (used as on-device cross-check). */
+ * impl 0 = product kernel for the dtype (f16 q|k|v + bf16 gradients: tensor cores; f32: exact fp32), 1 = force the
+ * exact fp32-arithmetic SIMT kernel on the same storage formats (on-device cross-check of the tensor-core kernels). */
 typedef struct samk_attn_params {
   const void* qkv; void* ctx; float* lse;
   const void* dctx; void* dqkv; float* delta;
-  int dtype;                 /* SAMK_DT_* of qkv/ctx/dctx/dqkv */
+  int dtype;                 /* SAMK_DT_* of qkv / ctx: F16 (tensor-core kernels) or F32 (exact kernel) */
+  int grad_dtype;            /* SAMK_DT_* of dctx / dqkv: BF16 (tensor-core kernels) or F32 (exact kernel) */
   int B, H, head_dim;
   int T, A, D;
   const uint8_t* key_valid;
@@ -202,14 +224,20 @@ typedef struct samk_attn_params {
   float* dq_accum;            /* tensor-core backward: fp32 [B*L, H*64] scratch for the dQ reduction */
   int q_begin;                /* forward only: compute query rows >= q_begin (rounded down to the kernel's
                                  row tile); 0 = all rows.  Used by the cached greedy decoder (decoder rows only). */
-  int delta_ready;            /* backward only: 1 = `delta` already holds rowsum(dctx * ctx) per (b, h, row), written by
-                                 samk_attn_delta (e.g. on another stream, beside the out-projection wgrad) */
+  int delta_ready;            /* reserved (0) */
+  const uint32_t* keep_bits;  /* tensor-core path with drop_p > 0: [B, H, L, ceil(L/32)] dropout keep bits of the
+                                 attention probabilities from samk_attn_build_keep (same (seed, offset) stream as the
+                                 exact kernel draws inline); shared by the forward and the backward launch */
+  void* do_f16;               /* tensor-core backward workspace: f16 [B*L, H*64], dctx of every (sample, head) scaled by
+                                 an exact power of two into the half range (written by the first kernel of samk_attn_bwd) */
+  float* do_inv_scale;        /* tensor-core backward workspace: [B*H] floats, 1 / scale per (sample, head) */
 } samk_attn_params;
 int samk_attn_fwd(const samk_attn_params* p, int impl, void* stream);
 int samk_attn_bwd(const samk_attn_params* p, int impl, void* stream);
-/* delta[b, h, i] = sum_d dctx[b, i, h, d] * ctx[b, i, h, d] (bf16 token-major inputs, head_dim 64): the row term of the
- * softmax backward (sa_m4c.py:578-598 differentiated), the first kernel of samk_attn_bwd when delta_ready == 0. */
-int samk_attn_delta(const void* dctx, const void* ctx, float* delta, int B, int H, int L, void* stream);
+/* keep_bits[b, h, i, w] bit k = attention probability (i, 32 w + k) survives dropout(p->drop_p) of sa_m4c.py:588 for
+ * the stream (p->drop_seed, p->drop_offset); uses B, H, T, A, D, drop_* of p only.  One launch per layer and step,
+ * typically beside the q|k|v projection GEMM. */
+int samk_attn_build_keep(const samk_attn_params* p, uint32_t* keep_bits, void* stream);
 /* allow-bit matrix shared by all layers of one kind in a step: bit (j&31) of word [b][h|0][i][j>>5] set
  * iff query i may attend key j (key validity, decoder causality, quadrants, relation bits). */
 long long samk_attn_mask_words(int B, int H, int T, int A, int D, int spatial);

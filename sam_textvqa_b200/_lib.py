@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libsamk.so")
 c_void_p, c_int, c_ll, c_float, c_double, c_ull = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong,
                                                    ctypes.c_float, ctypes.c_double, ctypes.c_ulonglong)
 
-DT_F32, DT_BF16 = 0, 1
+DT_F32, DT_BF16, DT_F16 = 0, 1, 2
 
 
 class GemmEpilogue(ctypes.Structure):
@@ -22,17 +22,18 @@ class GemmEpilogue(ctypes.Structure):
         ("bias", c_void_p), ("pre", c_void_p), ("ldpre", c_ll), ("pre_dtype", c_int), ("act", c_int),
         ("aux", c_void_p), ("ldaux", c_ll), ("aux_dtype", c_int), ("drop_p", c_float),
         ("drop_seed", c_ull), ("drop_offset", c_ull), ("residual", c_void_p), ("ldres", c_ll),
-        ("part_rows", c_int), ("out_part1", c_void_p), ("out_part2", c_void_p),
+        ("part_rows", c_int), ("out_part1", c_void_p), ("out_part2", c_void_p), ("alpha_dev", c_void_p),
     ]
 
 
 class AttnParams(ctypes.Structure):
     _fields_ = [
         ("qkv", c_void_p), ("ctx", c_void_p), ("lse", c_void_p), ("dctx", c_void_p), ("dqkv", c_void_p),
-        ("delta", c_void_p), ("dtype", c_int), ("B", c_int), ("H", c_int), ("head_dim", c_int), ("T", c_int),
+        ("delta", c_void_p), ("dtype", c_int), ("grad_dtype", c_int), ("B", c_int), ("H", c_int), ("head_dim", c_int), ("T", c_int),
         ("A", c_int), ("D", c_int), ("key_valid", c_void_p), ("rel_bits", c_void_p), ("quadrant_mask", ctypes.c_uint),
         ("spatial", c_int), ("scale", c_float), ("drop_p", c_float), ("drop_seed", c_ull), ("drop_offset", c_ull),
         ("allow_bits", c_void_p), ("dq_accum", c_void_p), ("q_begin", c_int), ("delta_ready", c_int),
+        ("keep_bits", c_void_p), ("do_f16", c_void_p), ("do_inv_scale", c_void_p),
     ]
 
 
@@ -51,10 +52,15 @@ SIGNATURES = {
     "samk_types_to_bits": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "samk_gemm_bf16": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_int, c_ll, c_int, c_int, c_int,
                                ctypes.POINTER(GemmEpilogue), c_int, c_int, c_void_p]),
+    "samk_gemm_16": (c_int, [c_void_p, c_int, c_int, c_ll, c_void_p, c_int, c_int, c_ll, c_int, c_int, c_int,
+                             ctypes.POINTER(GemmEpilogue), c_int, c_int, c_void_p]),
     "samk_cast_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p]),
+    "samk_cast_16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
+    "samk_cast_scaled_f16": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p]),
     "samk_split3_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
     "samk_l2norm": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
-    "samk_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "samk_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
+                                   c_int, c_void_p]),
     "samk_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_float, c_ull,
                                    c_ull, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "samk_layernorm_bwd_partials": (c_ll, [c_int]),
@@ -75,12 +81,13 @@ SIGNATURES = {
                                     c_int, c_void_p]),
     "samk_bce_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "samk_scale_inplace": (c_int, [c_void_p, c_ll, c_void_p, c_void_p]),
+    "samk_concat3_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "samk_sumsq": (c_int, [c_void_p, c_ll, c_void_p, c_void_p]),
     "samk_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_double, c_double, c_double, c_double, c_int,
                                c_void_p, c_double, c_void_p]),
     "samk_attn_fwd": (c_int, [ctypes.POINTER(AttnParams), c_int, c_void_p]),
     "samk_attn_bwd": (c_int, [ctypes.POINTER(AttnParams), c_int, c_void_p]),
-    "samk_attn_delta": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "samk_attn_build_keep": (c_int, [ctypes.POINTER(AttnParams), c_void_p, c_void_p]),
     "samk_attn_mask_words": (c_ll, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "samk_attn_build_mask": (c_int, [ctypes.POINTER(AttnParams), c_void_p, c_void_p]),
 }

@@ -25,7 +25,7 @@ constexpr int kAttnThreads = 256;
 struct AttnArgs {
   const void* qkv; void* ctx; float* lse;
   const void* dctx; void* dqkv; float* delta;
-  int in_bf16, out_bf16;
+  int in_bf16, out_bf16;   // SAMK_DT_* codes: in = qkv / ctx (activations), out = dctx / dqkv (gradients)
   int B, H;
   float scale;
   uint32_t drop_thresh; float drop_scale; unsigned long long seed, off;
@@ -34,10 +34,10 @@ struct AttnArgs {
 };
 
 __device__ __forceinline__ float ld_elem(const void* p, int bf16, size_t i) {
-  return bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]) : reinterpret_cast<const float*>(p)[i];
+  return bf16 ? ld_16(reinterpret_cast<const uint16_t*>(p) + i, bf16 == SAMK_DT_F16) : reinterpret_cast<const float*>(p)[i];
 }
 __device__ __forceinline__ void st_elem(void* p, int bf16, size_t i, float v) {
-  if (bf16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  if (bf16) st_16(reinterpret_cast<uint16_t*>(p) + i, v, bf16 == SAMK_DT_F16);
   else reinterpret_cast<float*>(p)[i] = v;
 }
 
@@ -58,8 +58,7 @@ __device__ __forceinline__ void load_tile(float (*dst)[DH + 1], const void* src,
       const size_t o = base + (size_t)(r0 + r) * ld + c;
       if (bf16) {
         uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(src) + o);
-        float2 x = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.x));
-        float2 y = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.y));
+        float2 x = unpack_16(u.x, bf16 == SAMK_DT_F16), y = unpack_16(u.y, bf16 == SAMK_DT_F16);
         v = make_float4(x.x, x.y, y.x, y.y);
       } else {
         v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + o);
@@ -103,7 +102,7 @@ attn_rows_kernel(const AttnArgs a) {
     for (int r = 0; r < 4; ++r) {
       const int i = row0 + r;
       q[r] = i < L ? ld_elem(a.qkv, a.in_bf16, qbase + (size_t)i * ld + d) : 0.f;
-      g[r] = (kBwd && i < L) ? ld_elem(a.dctx, a.in_bf16, cbase + (size_t)i * ldc + d) : 0.f;
+      g[r] = (kBwd && i < L) ? ld_elem(a.dctx, a.out_bf16, cbase + (size_t)i * ldc + d) : 0.f;
     }
     Q4[warp][d] = make_float4(q[0], q[1], q[2], q[3]);
     if (kBwd) G4[warp][d] = make_float4(g[0], g[1], g[2], g[3]);
@@ -120,7 +119,7 @@ attn_rows_kernel(const AttnArgs a) {
       float t = 0.f;
       if (i < L) {
         for (int d = lane; d < DH; d += 32)
-          t += ld_elem(a.dctx, a.in_bf16, cbase + (size_t)i * ldc + d) * ld_elem(a.ctx, a.in_bf16, cbase + (size_t)i * ldc + d);
+          t += ld_elem(a.dctx, a.out_bf16, cbase + (size_t)i * ldc + d) * ld_elem(a.ctx, a.in_bf16, cbase + (size_t)i * ldc + d);
       }
       delta_r[r] = warp_sum(t);
       lse_r[r] = i < L ? a.lse[((size_t)b * a.H + h) * L + i] : INFINITY;
@@ -212,8 +211,8 @@ attn_rows_kernel(const AttnArgs a) {
     if (i >= L) continue;
     if (!kBwd) {
       const float inv = lrow[r] > 0.f ? 1.0f / lrow[r] : 0.f;
-      st_elem(a.ctx, a.out_bf16, cbase + (size_t)i * ldc + lane, acc[r][0] * inv);
-      st_elem(a.ctx, a.out_bf16, cbase + (size_t)i * ldc + lane + 32, acc[r][1] * inv);
+      st_elem(a.ctx, a.in_bf16, cbase + (size_t)i * ldc + lane, acc[r][0] * inv);
+      st_elem(a.ctx, a.in_bf16, cbase + (size_t)i * ldc + lane + 32, acc[r][1] * inv);
       if (lane == 0) a.lse[((size_t)b * a.H + h) * L + i] = lrow[r] > 0.f ? mrow[r] + logf(lrow[r]) : INFINITY;
     } else {
       st_elem(a.dqkv, a.out_bf16, qbase + (size_t)i * ld + lane, acc[r][0]);
@@ -269,7 +268,7 @@ attn_dkv_kernel(const AttnArgs a) {
   for (int i0 = 0; i0 < L; i0 += KT) {
     __syncthreads();
     load_tile(Qs, a.qkv, a.in_bf16, qbase, ld, i0, KT, L);
-    load_tile(Gs, a.dctx, a.in_bf16, cbase, ldc, i0, KT, L);
+    load_tile(Gs, a.dctx, a.out_bf16, cbase, ldc, i0, KT, L);
     for (int i = threadIdx.x; i < KT; i += blockDim.x) {
       lse_s[i] = (i0 + i < L) ? a.lse[((size_t)b * a.H + h) * L + i0 + i] : INFINITY;
       delta_s[i] = (i0 + i < L) ? a.delta[((size_t)b * a.H + h) * L + i0 + i] : 0.f;
@@ -356,7 +355,7 @@ static int fill_args(AttnArgs& a, const samk_attn_params* p) {
   if (p->T < 0 || p->A < 0 || p->D < 0 || p->B < 0 || p->H <= 0 || p->H > 16) { set_error("samk_attn: bad sizes"); return SAMK_ERR_ARG; }
   if (p->spatial && p->A > 0 && !p->rel_bits) { set_error("samk_attn: spatial layer needs rel_bits"); return SAMK_ERR_ARG; }
   a.qkv = p->qkv; a.ctx = p->ctx; a.lse = p->lse; a.dctx = p->dctx; a.dqkv = p->dqkv; a.delta = p->delta;
-  a.in_bf16 = p->dtype == SAMK_DT_BF16; a.out_bf16 = a.in_bf16;
+  a.in_bf16 = p->dtype; a.out_bf16 = p->grad_dtype;
   a.B = p->B; a.H = p->H; a.scale = p->scale;
   a.drop_thresh = p->drop_p > 0.f ? drop_threshold(p->drop_p) : 0u;
   a.drop_scale = drop_keep_scale(p->drop_p);

@@ -1,4 +1,10 @@
-// Fused masked multi-head attention on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), bf16 I/O.
+// Fused masked multi-head attention on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+// Storage formats: q|k|v, P and ctx are IEEE half (11 significant bits: the forward pass stays within 1e-3 of the
+// fp32 reference).  The gradients dctx (in) and dq|dk|dv (out) are bfloat16.  tcgen05.mma kind::f16 needs A and B in
+// ONE format (mixed f16 x bf16 faults on sm_100a), so the backward runs every product in half: attn_bwd_prep_kernel
+// re-expresses dO of each (sample, head) in half with an exactly computed power-of-two scale s_bh (max|dO| s in [8,16)),
+// everything downstream (delta, dP, dS, dQ, dK, dV) lives in that scaled domain -- all contractions of the backward
+// are within one (sample, head), so s_bh factors out -- and the drains multiply by 1/s_bh before rounding to bf16.
 //
 // Replaces SpatialBertSelfAttention.forward steps (3)-(7) (/root/reference/sam/sa_m4c.py:562-598) and
 // the plain BertSelfAttention of the 'n' layers / TextBert, forward and backward.
@@ -99,6 +105,8 @@ struct TcArgs {
   const float* delta;               // bwd
   void* dqkv; float* dq_accum;      // bwd outputs
   const uint32_t* allow; int Hm, W;
+  const uint32_t* keep;             // dropout keep bits [B, H, L, W] (samk_attn_build_keep) or nullptr = keep all
+  const float* inv_scale;           // bwd: 1 / s_bh per (sample, head), from attn_bwd_prep_kernel
   int B, H, L;
   int q_tile0;                      // forward: first 128-row query tile to compute
   float scale_log2;                 // scale * log2(e)
@@ -115,183 +123,44 @@ __device__ __forceinline__ uint32_t allow_word(const TcArgs& a, int b, int h, in
 
 // dropout keep flags for 32 consecutive keys j0..j0+31 of probability row (b,h,i): bit k = keep
 __device__ __forceinline__ uint32_t keep_word(const TcArgs& a, int b, int h, int i, int j0) {
-  if (!a.drop_thresh) return 0xffffffffu;
-  const uint64_t row = ((uint64_t)(b * a.H + h) * a.L + i) * (uint64_t)((a.L + 7) >> 3);   // groups of 8 keys
+  const int w = j0 >> 5;
+  if (!a.keep || i >= a.L || w >= a.W) return 0xffffffffu;
+  return a.keep[(((size_t)b * a.H + h) * a.L + i) * a.W + w];
+}
+
+// Dropout keep bits of the attention probabilities, one word per (b, h, query row, 32 keys): bit k = element
+// (i, 32 w + k) is kept.  The same Philox stream as the exact-fp32 kernel (attn_simt.cu: group of 8 keys g = j >> 3 of
+// row ((b H + h) L + i) ngrp), evaluated ONCE per layer and step by this kernel -- beside the q|k|v projection GEMM,
+// whose tensor-bound CTAs leave the integer pipes idle -- instead of once in the forward and once in the backward
+// attention kernel, where the 7 Philox rounds were a third of all issued instructions.
+__global__ void attn_build_keep_kernel(uint32_t* __restrict__ out, long long n_words, int L, int W, uint32_t thresh,
+                                       unsigned long long seed, unsigned long long off) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_words) return;
+  const int w = (int)(e % W);
+  const long long row = e / W;                    // (b H + h) L + i
+  const uint32_t ngrp = (uint32_t)((L + 7) >> 3);
   uint32_t kw = 0;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) kw |= dropout_keep8(a.seed, a.off, row + (uint64_t)((j0 >> 3) + q), a.drop_thresh) << (8 * q);
-  return kw;
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t g = (uint32_t)(4 * w + q);
+    if (g < ngrp) kw |= dropout_keep8(seed, off, (uint64_t)row * ngrp + g, thresh) << (8 * q);
+  }
+  out[e] = kw;
 }
 
 // write 32 consecutive bf16 values (keys 32*c32 .. +31 of the tile) of row r into a [rows][64-key block]
 // 128B-swizzled tile set: block kb = c32/2 (16 KB each, 128 rows x 128 B), chunk16 = (c32&1)*4 + q
+template <bool F16>
 __device__ __forceinline__ void store_p_chunk(uint8_t* tile_base, int r, int c32, const float* v) {
   uint8_t* rowp = tile_base + (c32 >> 1) * 16384 + r * 128;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int chunk = ((c32 & 1) * 4 + q) ^ (r & 7);
-    uint4 u = make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
-                         pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+    uint4 u = make_uint4(pack_16<F16>(v[8 * q], v[8 * q + 1]), pack_16<F16>(v[8 * q + 2], v[8 * q + 3]),
+                         pack_16<F16>(v[8 * q + 4], v[8 * q + 5]), pack_16<F16>(v[8 * q + 6], v[8 * q + 7]));
     *reinterpret_cast<uint4*>(rowp + chunk * 16) = u;
   }
-}
-
-// ---------------------------------------------------------------------------------------------
-// forward
-// ---------------------------------------------------------------------------------------------
-template <int KVT>
-__global__ void __launch_bounds__(128, 2)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const TcArgs a) {
-  // two CTAs per SM (112 KB each at KVT=192): no alignment slack, the 1024-byte alignment the 128B
-  // swizzle needs comes from the declaration and is checked below
-  extern __shared__ __align__(1024) uint8_t smem_fwd[];
-  uint8_t* smem = smem_fwd;
-  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* sQ = smem;                       // 128 x 64 bf16
-  uint8_t* sK = sQ + 16384;                 // KVT x 64
-  uint8_t* sV = sK + KVT * 128;             // KVT x 64
-  uint8_t* sP = sV + KVT * 128;             // (KVT/64) blocks of 128 x 64
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (KVT / 64) * 16384);
-  uint64_t* tma_bar = bars; uint64_t* s_bar = bars + 1; uint64_t* o_bar = bars + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-  constexpr int kTmemCols = 256;            // S: KVT (<=192) columns, O: 64 columns at offset 192
-  constexpr uint32_t kOcol = 192;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q0 = (blockIdx.x + a.q_tile0) * 128, h = blockIdx.y, b = blockIdx.z;
-  const int L = a.L, H = a.H;
-  const int n_kv = (L + KVT - 1) / KVT;
-
-  if (tid == 0) {
-    ptx::prefetch_tensormap(&tmQ); ptx::prefetch_tensormap(&tmKV);
-    ptx::mbar_init(tma_bar, 1); ptx::mbar_init(s_bar, 1); ptx::mbar_init(o_bar, 1);
-    ptx::fence_barrier_init();
-  }
-  if (warp == 0) ptx::tmem_alloc<kTmemCols>(tmem_slot);
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
-
-  const int row = q0 + tid;                 // query row of this thread
-  constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, KVT, 0, 0);
-  constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, 64, 0, 1);
-  float m_run = -INFINITY, l_run = 0.f;
-
-  for (int t = 0; t < n_kv; ++t) {
-    const int k0 = t * KVT;
-    if (tid == 0) {
-      ptx::mbar_arrive_expect_tx(tma_bar, (t == 0 ? 16384 : 0) + 2 * KVT * 128);
-      if (t == 0) ptx::tma_load_2d(sQ, &tmQ, tma_bar, h * TDH, b * L + q0);
-      ptx::tma_load_2d(sK, &tmKV, tma_bar, (H + h) * TDH, b * L + k0);
-      ptx::tma_load_2d(sV, &tmKV, tma_bar, (2 * H + h) * TDH, b * L + k0);
-    }
-    // allow-bit words of this row for the whole key tile: issued before the waits so the global-load
-    // latency hides behind TMA + MMA
-    uint32_t aw_t[KVT / 32];
-#pragma unroll
-    for (int c = 0; c < KVT / 32; ++c) aw_t[c] = allow_word(a, b, h, row, k0 + c * 32);
-    ptx::mbar_wait(tma_bar, t & 1);
-    if (tid == 0) {
-      ptx::tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        ptx::umma_f16(tmem, ptx::make_smem_desc_sw128(ptx::smem_u32(sQ) + k * 32, 16, 1024),
-                      ptx::make_smem_desc_sw128(ptx::smem_u32(sK) + k * 32, 16, 1024), idesc_s, k > 0);
-      ptx::umma_commit(s_bar);
-    }
-    ptx::mbar_wait(s_bar, t & 1);
-    ptx::tc_fence_after();
-
-    // ---- pass 1: masked row maximum of this key tile
-    float tmax = -INFINITY;
-#pragma unroll
-    for (int c = 0; c < KVT / 32; ++c) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(t_lane + c * 32, r);
-      ptx::tmem_ld_wait();
-      const uint32_t aw = aw_t[c];
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if ((aw >> i) & 1u) tmax = fmaxf(tmax, __uint_as_float(r[i]));
-    }
-    tmax *= a.scale_log2;                   // scale > 0: max commutes with the scaling
-    const float m_new = fmaxf(m_run, tmax);
-    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-    if (t > 0) {
-      // rescale the running sum and the O accumulator (whole CTA takes this path together)
-      const float corr = (m_run == -INFINITY) ? 1.f : fast_exp2(m_run - m_use);
-      l_run *= corr;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(t_lane + kOcol + c * 32, r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
-        tmem_st_32x32(t_lane + kOcol + c * 32, r);
-      }
-      tmem_st_wait();
-    }
-    m_run = m_new;
-    // ---- pass 2: probabilities -> bf16 P tile (dropout applied), running sum from undropped p
-#pragma unroll
-    for (int c = 0; c < KVT / 32; ++c) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(t_lane + c * 32, r);
-      ptx::tmem_ld_wait();
-      const uint32_t aw = aw_t[c];
-      const uint32_t kw = aw ? keep_word(a, b, h, row, k0 + c * 32) : 0u;
-      float p[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float e = ((aw >> i) & 1u) ? fast_exp2(__uint_as_float(r[i]) * a.scale_log2 - m_use) : 0.f;
-        l_run += e;
-        p[i] = ((kw >> i) & 1u) ? e * a.drop_scale : 0.f;
-      }
-      store_p_chunk(sP, tid, c, p);
-    }
-    ptx::tc_fence_before();
-    ptx::fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      ptx::tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < KVT / 16; ++k)
-        ptx::umma_f16(tmem + kOcol,
-                      ptx::make_smem_desc_sw128(ptx::smem_u32(sP) + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                      ptx::make_smem_desc_sw128(ptx::smem_u32(sV) + k * 2048, 16384, 1024), idesc_o,
-                      (t > 0 || k > 0) ? 1u : 0u);
-      ptx::umma_commit(o_bar);
-    }
-    ptx::mbar_wait(o_bar, t & 1);
-    ptx::tc_fence_after();
-  }
-
-  // ---- epilogue: ctx = O / l, lse = ln(sum exp)
-  const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-  __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(a.ctx) + ((size_t)b * L + row) * (size_t)(H * TDH) + h * TDH;
-#pragma unroll 1
-  for (int c = 0; c < 2; ++c) {
-    uint32_t r[32];
-    ptx::tmem_ld_32x32(t_lane + kOcol + c * 32, r);
-    ptx::tmem_ld_wait();
-    if (row < L) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 8)
-        *reinterpret_cast<uint4*>(crow + c * 32 + i) =
-            make_uint4(pack_bf16(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
-                       pack_bf16(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
-                       pack_bf16(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
-                       pack_bf16(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv));
-    }
-  }
-  if (row < L) a.lse[((size_t)b * H + h) * L + row] = l_run > 0.f ? (m_run + log2f(l_run)) * kLn2 : INFINITY;
-
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc<kTmemCols>(tmem); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -357,8 +226,17 @@ __device__ __forceinline__ uint4 lds128u(uint32_t addr) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
 }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+// The two key halves of one TMEM lane quarter (warps w and w + 4) meet on their own 64-thread barrier
+// `first + quarter` instead of a barrier across all softmax warps of the tile: a pair never waits for the slowest of
+// four.  Immediate barrier ids so that ptxas reserves only the barriers that are used.
+template <int kFirst>
+__device__ __forceinline__ void pair_bar_sync(int quarter) {
+  switch (quarter) {
+    case 0: asm volatile("bar.sync %0, 64;" ::"n"(kFirst) : "memory"); break;
+    case 1: asm volatile("bar.sync %0, 64;" ::"n"(kFirst + 1) : "memory"); break;
+    case 2: asm volatile("bar.sync %0, 64;" ::"n"(kFirst + 2) : "memory"); break;
+    default: asm volatile("bar.sync %0, 64;" ::"n"(kFirst + 3) : "memory"); break;
+  }
 }
 
 __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
@@ -380,34 +258,24 @@ __device__ __forceinline__ float masked_max16(const uint32_t (&r)[16], uint32_t 
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
-// 16 scores -> probabilities (masked, dropout applied) as 8 packed bf16 pairs; returns the sum of the
-// undropped probabilities.  grp0 = Philox group index of the first of the two 8-key groups.
-__device__ __forceinline__ float softmax_chunk16(const uint32_t (&r)[16], uint32_t aw, float sl2, float m_use,
-                                                 bool drop, uint64_t seed, uint32_t off, uint64_t grp0, uint32_t th16,
+// 16 scores -> probabilities (masked, dropout applied) as 8 packed half pairs; returns the sum of the
+// undropped probabilities.  aw / kw: allow and dropout-keep bits of these 16 keys in the low half.
+__device__ __forceinline__ float softmax_chunk16(const uint32_t (&r)[16], uint32_t aw, uint32_t kw, float sl2, float m_use,
                                                  uint32_t (&pk)[8]) {
   float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+  kw &= aw;
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
-    float e[8];
+    float e[8], p[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float x = fmaf(__uint_as_float(r[8 * q + i]), sl2, -m_use);
-      e[i] = ((aw >> (8 * q + i)) & 1u) ? fast_exp2(x) : 0.f;
+      const float x = fast_exp2(fmaf(__uint_as_float(r[8 * q + i]), sl2, -m_use));
+      e[i] = ((aw >> (8 * q + i)) & 1u) ? x : 0.f;
+      p[i] = ((kw >> (8 * q + i)) & 1u) ? x : 0.f;
     }
     l0 += e[0] + e[4]; l1 += e[1] + e[5]; l2 += e[2] + e[6]; l3 += e[3] + e[7];
-    if (drop) {
-      const uint4 rnd = philox4x32(seed, grp0 + (uint64_t)q, off);
-      e[0] = (rnd.x << 16) >= th16 ? e[0] : 0.f;
-      e[1] = rnd.x >= th16 ? e[1] : 0.f;
-      e[2] = (rnd.y << 16) >= th16 ? e[2] : 0.f;
-      e[3] = rnd.y >= th16 ? e[3] : 0.f;
-      e[4] = (rnd.z << 16) >= th16 ? e[4] : 0.f;
-      e[5] = rnd.z >= th16 ? e[5] : 0.f;
-      e[6] = (rnd.w << 16) >= th16 ? e[6] : 0.f;
-      e[7] = rnd.w >= th16 ? e[7] : 0.f;
-    }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pk[4 * q + i] = pack_bf16(e[2 * i], e[2 * i + 1]);
+    for (int i = 0; i < 4; ++i) pk[4 * q + i] = pack_f16(p[2 * i], p[2 * i + 1]);
   }
   return (l0 + l1) + (l2 + l3);
 }
@@ -499,8 +367,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // The whole warp runs the loop converged and computes the warp-uniform descriptors; only the tcgen05
     // instructions sit under the elected-lane predicate, so they issue back to back from uniform registers.
     {
-      constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, KVT, 0, 0);
-      constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, 64, 0, 1);
+      constexpr uint32_t idesc_s = ptx::make_idesc_16(128, KVT, 0, 0, ptx::kFmtF16, ptx::kFmtF16);
+      constexpr uint32_t idesc_o = ptx::make_idesc_16(128, 64, 0, 1, ptx::kFmtF16, ptx::kFmtF16);
       constexpr uint64_t kStepK = 32 >> 4, kStepMN = 2048 >> 4;   // k-step increments of the descriptor address field
       const int g = warp - 1;
       int iter = 0; uint32_t kvc = 0; uint32_t pc = 0;
@@ -560,17 +428,14 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int lrow = quarter * 32 + lane;
     const uint32_t t_s = tmem + g * 256 + ((uint32_t)(quarter * 32) << 16);   // S columns of this tile
     const uint32_t t_o = t_s + 192 + hf * 32;                                    // this half's 32 output columns
-    const uint32_t th16 = a.drop_thresh << 16;
-    const bool drop = a.drop_thresh != 0;
     const float sl2 = a.scale_log2;
-    const uint32_t ngrp = (uint32_t)((L + 7) >> 3);
     uint32_t sc = 0, oc = 0, xc = 0;
     int iter = 0;
     // allow-bit words of this thread's (row, key half), fetched one (item, key tile) ahead of their use
-    uint32_t aw_nx[NC / 2];
+    uint32_t aw_nx[NC / 2], kw_nx[NC / 2];
     auto fetch_allow = [&](int item_, int iter_, int t_) {
 #pragma unroll
-      for (int c = 0; c < NC / 2; ++c) aw_nx[c] = 0u;
+      for (int c = 0; c < NC / 2; ++c) { aw_nx[c] = 0u; kw_nx[c] = 0xffffffffu; }
       if (item_ >= n_items) return;
       int b_, h_, s0, s1, l0, l1;
       decode(item_, iter_, b_, h_, s0, s1, l0, l1);
@@ -581,6 +446,11 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int w0 = (t_ * KVT + hf * (KVT / 2)) >> 5;
 #pragma unroll
       for (int c = 0; c < NC / 2; ++c) if (w0 + c < a.W) aw_nx[c] = ld_allow(ar + w0 + c);
+      if (a.keep) {
+        const uint32_t* kr = a.keep + (((size_t)b_ * H + h_) * L + row_) * a.W;
+#pragma unroll
+        for (int c = 0; c < NC / 2; ++c) if (w0 + c < a.W) kw_nx[c] = ld_allow(kr + w0 + c);
+      }
     };
     fetch_allow(blockIdx.x, 0, 0);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++iter) {
@@ -591,13 +461,11 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int row = my_start + lrow;
       const bool active = row >= my_lo && row < L;
       const bool warp_active = __any_sync(0xffffffffu, active);
-      const uint64_t drow = ((uint64_t)(b * H + h) * L + (uint64_t)row) * ngrp;
       float m_run = -INFINITY, l_run = 0.f;
       for (int t = 0; t < n_kv; ++t) {
-        const int k0 = t * KVT + hf * (KVT / 2);        // first key of this thread's half
-        uint32_t aw_t[NC / 2];
+        uint32_t aw_t[NC / 2], kw_t[NC / 2];
 #pragma unroll
-        for (int c = 0; c < NC / 2; ++c) aw_t[c] = aw_nx[c];
+        for (int c = 0; c < NC / 2; ++c) { aw_t[c] = aw_nx[c]; kw_t[c] = kw_nx[c]; }
         if (t + 1 < n_kv) fetch_allow(item, iter, t + 1); else fetch_allow(item + gridDim.x, iter + 1, 0);
         if (warp == 3 && lane == 0) TL_STAMP(8, iter);
         ptx::mbar_wait(&s_full[g], sc & 1); ++sc;
@@ -622,7 +490,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         float* xm = xch + (((0 * 2 + (xc & 1)) * 2 + g) * 2) * 128;
         xm[hf * 128 + lrow] = tmax;
         if (warp == 3 && lane == 0) TL_STAMP(10, iter);
-        named_bar_sync(1 + g, 256);
+        if (g) pair_bar_sync<5>(quarter); else pair_bar_sync<1>(quarter);
         if (warp == 3 && lane == 0) TL_STAMP(11, iter);
         tmax = fmaxf(tmax, xm[(hf ^ 1) * 128 + lrow]);
         ++xc;
@@ -654,8 +522,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int c = 0; c < NC; ++c) {
             if (c + 1 < NC) ptx::tmem_ld_32x16(t_sh + (c + 1) * 16, (c & 1) ? rA : rB);
             uint32_t pk[8];
-            l_run += softmax_chunk16((c & 1) ? rB : rA, aw_t[c >> 1] >> (16 * (c & 1)), sl2, m_use, drop, a.seed,
-                                     (uint32_t)a.off, drow + (uint64_t)((k0 >> 3) + c * 2), th16, pk);
+            l_run += softmax_chunk16((c & 1) ? rB : rA, aw_t[c >> 1] >> (16 * (c & 1)), kw_t[c >> 1] >> (16 * (c & 1)), sl2,
+                                     m_use, pk);
             if (c + 1 < NC) ptx::tmem_ld_wait();      // also orders the P store below after the S load of the same columns
             tmem_st_32x8(t_sh + c * 8, pk);   // P of this half overlays the first columns of its own S half
           }
@@ -671,7 +539,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // ---- epilogue: ctx = O * keep_scale / l, lse = ln(sum exp); the halves add their partial sums
       float* xl = xch + (((1 * 2 + (iter & 1)) * 2 + g) * 2) * 128;
       xl[hf * 128 + lrow] = l_run;
-      named_bar_sync(1 + g, 256);
+      if (g) pair_bar_sync<5>(quarter); else pair_bar_sync<1>(quarter);
       l_run += xl[(hf ^ 1) * 128 + lrow];
       if (warp == 3 && lane == 0) TL_STAMP(13, iter);
       if (warp_active) {
@@ -688,10 +556,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int j = 0; j < 4; ++j) {
           const int i = 8 * j;
           sts128u(st + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4),
-                  make_uint4(pack_bf16(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
-                             pack_bf16(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
-                             pack_bf16(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
-                             pack_bf16(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv)));
+                  make_uint4(pack_f16(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
+                             pack_f16(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
+                             pack_f16(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
+                             pack_f16(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv)));
         }
         __syncwarp();
         const int row_w = my_start + quarter * 32;      // first row of this warp
@@ -700,7 +568,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const int rr = it * 8 + (lane >> 2), cj = lane & 3, orow = row_w + rr;
           const uint4 v = lds128u(st + rr * 64 + ((cj ^ ((rr >> 1) & 3)) << 4));
           if (orow >= my_lo && orow < L)
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.ctx) + ((size_t)b * L + orow) * (size_t)(H * TDH) + h * TDH +
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(a.ctx) + ((size_t)b * L + orow) * (size_t)(H * TDH) + h * TDH +
                                       hf * 32 + cj * 8) = v;
         }
         __syncwarp();
@@ -809,8 +677,8 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp converged, tcgen05 under the elected lane) =====================
-    constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, KVT, 0, 0);
-    constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, 64, 0, 1);
+    constexpr uint32_t idesc_s = ptx::make_idesc_16(128, KVT, 0, 0, ptx::kFmtF16, ptx::kFmtF16);
+    constexpr uint32_t idesc_o = ptx::make_idesc_16(128, 64, 0, 1, ptx::kFmtF16, ptx::kFmtF16);
     constexpr uint64_t kStepK = 32 >> 4, kStepMN = 2048 >> 4;
     int iter = 0; uint32_t kvc = 0, pc = 0;
     const uint32_t sk = ptx::smem_u32(sKV), sv = sk + KVT * 128;
@@ -849,16 +717,13 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int lrow = quarter * 32 + lane;
     const uint32_t t_s = tmem + ((uint32_t)(quarter * 32) << 16);
     const uint32_t t_o = t_s + 192 + hf * 32;
-    const uint32_t th16 = a.drop_thresh << 16;
-    const bool drop = a.drop_thresh != 0;
     const float sl2 = a.scale_log2;
-    const uint32_t ngrp = (uint32_t)((L + 7) >> 3);
     uint32_t sc = 0, oc = 0, xc = 0;
     int iter = 0;
-    uint32_t aw_nx[NC / 2];
+    uint32_t aw_nx[NC / 2], kw_nx[NC / 2];
     auto fetch_allow = [&](int item_, int iter_, int t_) {
 #pragma unroll
-      for (int c = 0; c < NC / 2; ++c) aw_nx[c] = 0u;
+      for (int c = 0; c < NC / 2; ++c) { aw_nx[c] = 0u; kw_nx[c] = 0xffffffffu; }
       if (item_ >= n_items) return;
       int b_, h_, st, lo;
       decode(item_, iter_, b_, h_, st, lo);
@@ -868,6 +733,11 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int w0 = (t_ * KVT + hf * (KVT / 2)) >> 5;
 #pragma unroll
       for (int c = 0; c < NC / 2; ++c) if (w0 + c < a.W) aw_nx[c] = ld_allow(ar + w0 + c);
+      if (a.keep) {
+        const uint32_t* kr = a.keep + (((size_t)b_ * H + h_) * L + row_) * a.W;
+#pragma unroll
+        for (int c = 0; c < NC / 2; ++c) if (w0 + c < a.W) kw_nx[c] = ld_allow(kr + w0 + c);
+      }
     };
     fetch_allow(blockIdx.x, 0, 0);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++iter) {
@@ -876,13 +746,11 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int row = my_start + lrow;
       const bool active = row >= my_lo && row < L;
       const bool warp_active = __any_sync(0xffffffffu, active);
-      const uint64_t drow = ((uint64_t)(b * H + h) * L + (uint64_t)row) * ngrp;
       float m_run = -INFINITY, l_run = 0.f;
       for (int t = 0; t < n_kv; ++t) {
-        const int k0 = t * KVT + hf * (KVT / 2);
-        uint32_t aw_t[NC / 2];
+        uint32_t aw_t[NC / 2], kw_t[NC / 2];
 #pragma unroll
-        for (int c = 0; c < NC / 2; ++c) aw_t[c] = aw_nx[c];
+        for (int c = 0; c < NC / 2; ++c) { aw_t[c] = aw_nx[c]; kw_t[c] = kw_nx[c]; }
         if (t + 1 < n_kv) fetch_allow(item, iter, t + 1); else fetch_allow(item + gridDim.x, iter + 1, 0);
         ptx::mbar_wait(s_full, sc & 1); ++sc;
         ptx::tc_fence_after();
@@ -902,7 +770,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         float* xm = xch + ((0 * 2 + (xc & 1)) * 2) * 128;
         xm[hf * 128 + lrow] = tmax;
-        named_bar_sync(1, 256);
+        pair_bar_sync<1>(quarter);
         tmax = fmaxf(tmax, xm[(hf ^ 1) * 128 + lrow]);
         ++xc;
         if (warp_active) {
@@ -932,8 +800,8 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int c = 0; c < NC; ++c) {
             if (c + 1 < NC) ptx::tmem_ld_32x16(t_sh + (c + 1) * 16, (c & 1) ? rA : rB);
             uint32_t pk[8];
-            l_run += softmax_chunk16((c & 1) ? rB : rA, aw_t[c >> 1] >> (16 * (c & 1)), sl2, m_use, drop, a.seed,
-                                     (uint32_t)a.off, drow + (uint64_t)((k0 >> 3) + c * 2), th16, pk);
+            l_run += softmax_chunk16((c & 1) ? rB : rA, aw_t[c >> 1] >> (16 * (c & 1)), kw_t[c >> 1] >> (16 * (c & 1)), sl2,
+                                     m_use, pk);
             if (c + 1 < NC) ptx::tmem_ld_wait();
             tmem_st_32x8(t_sh + c * 8, pk);
           }
@@ -948,7 +816,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // ---- epilogue
       float* xl = xch + ((1 * 2 + (iter & 1)) * 2) * 128;
       xl[hf * 128 + lrow] = l_run;
-      named_bar_sync(1, 256);
+      pair_bar_sync<1>(quarter);
       l_run += xl[(hf ^ 1) * 128 + lrow];
       if (warp_active) {
         ptx::mbar_wait(o_done, oc & 1); ++oc;
@@ -962,10 +830,10 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int j = 0; j < 4; ++j) {
           const int i = 8 * j;
           sts128u(st + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4),
-                  make_uint4(pack_bf16(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
-                             pack_bf16(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
-                             pack_bf16(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
-                             pack_bf16(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv)));
+                  make_uint4(pack_f16(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
+                             pack_f16(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
+                             pack_f16(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
+                             pack_f16(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv)));
         }
         __syncwarp();
         const int row_w = my_start + quarter * 32;
@@ -974,7 +842,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const int rr = it * 8 + (lane >> 2), cj = lane & 3, orow = row_w + rr;
           const uint4 v = lds128u(st + rr * 64 + ((cj ^ ((rr >> 1) & 3)) << 4));
           if (orow >= my_lo && orow < L)
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.ctx) + ((size_t)b * L + orow) * (size_t)(H * TDH) + h * TDH +
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(a.ctx) + ((size_t)b * L + orow) * (size_t)(H * TDH) + h * TDH +
                                       hf * 32 + cj * 8) = v;
         }
         __syncwarp();
@@ -993,34 +861,56 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
-// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]
-__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dctx, const __nv_bfloat16* __restrict__ ctx,
-                                  float* __restrict__ delta, int B, int H, int L) {
-  // 8 lanes per (row, head): a warp reads 512 contiguous bytes of each operand per instruction
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long e = t >> 3;
-  const int k = (int)(t & 7);
-  const bool live = e < (long long)B * L * H;
-  float s = 0.f;
-  int h = 0, b = 0, i = 0;
-  if (live) {
-    h = (int)(e % H);
-    const long long rowi = e / H;
-    b = (int)(rowi / L); i = (int)(rowi % L);
-    const uint4 x = reinterpret_cast<const uint4*>(dctx + (size_t)rowi * H * TDH + h * TDH)[k];
-    const uint4 y = reinterpret_cast<const uint4*>(ctx + (size_t)rowi * H * TDH + h * TDH)[k];
+// Backward preparation, one CTA per (sample, head): max|dO| over the item -> s = 2^k with max|dO| s in [8, 16);
+// dO16 = half(dO s) (what the tensor cores read); delta[b,h,i] = sum_d dO16[i,d] O[i,d] (the row term of the softmax
+// backward, in the scaled domain, from the very values the MMAs see); inv_scale[b,h] = 1/s.  dO rows of one head are
+// 128 contiguous bytes: 8 lanes x 16 bytes per row, both passes hit L1/L2 (an item is <= 33 KB at L = 256).
+__global__ void __launch_bounds__(256)
+attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dctx, const __half* __restrict__ ctx, __half* __restrict__ do16,
+                     float* __restrict__ delta, float* __restrict__ inv_scale, int H, int L) {
+  __shared__ float red[8];
+  const int item = blockIdx.x, b = item / H, h = item - b * H;
+  const int t = threadIdx.x, k8 = t & 7;
+  const size_t ld = (size_t)H * TDH;
+  const size_t base = (size_t)b * L * ld + (size_t)h * TDH + (size_t)k8 * 8;
+  float m = 0.f;
+  for (int i = t >> 3; i < L; i += 32) {
+    const uint4 x = *reinterpret_cast<const uint4*>(dctx + base + (size_t)i * ld);
     const __nv_bfloat162* xa = reinterpret_cast<const __nv_bfloat162*>(&x);
-    const __nv_bfloat162* ya = reinterpret_cast<const __nv_bfloat162*>(&y);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float2 f = __bfloat1622float2(xa[q]), g = __bfloat1622float2(ya[q]);
-      s += f.x * g.x + f.y * g.y;
-    }
+    for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(xa[q]); m = fmaxf(m, fmaxf(fabsf(f.x), fabsf(f.y))); }
   }
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
-  s += __shfl_xor_sync(0xffffffffu, s, 4);
-  if (live && k == 0) delta[((size_t)b * H + h) * L + i] = s;
+  m = warp_max(m);
+  if ((t & 31) == 0) red[t >> 5] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+  const float s = pow2_scale_for(m, 4);
+  if (t == 0) inv_scale[item] = 1.0f / s;
+  for (int i0 = 0; i0 < L; i0 += 32) {
+    const int i = i0 + (t >> 3);
+    float acc = 0.f;
+    if (i < L) {
+      const uint4 x = *reinterpret_cast<const uint4*>(dctx + base + (size_t)i * ld);
+      const uint4 y = *reinterpret_cast<const uint4*>(ctx + base + (size_t)i * ld);
+      const __nv_bfloat162* xa = reinterpret_cast<const __nv_bfloat162*>(&x);
+      const __half2* ya = reinterpret_cast<const __half2*>(&y);
+      uint32_t o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(xa[q]);
+        o[q] = pack_f16_sat(f.x * s, f.y * s);
+        const float2 r = __half22float2(*reinterpret_cast<const __half2*>(&o[q])), g = __half22float2(ya[q]);
+        acc += r.x * g.x + r.y * g.y;
+      }
+      *reinterpret_cast<uint4*>(do16 + base + (size_t)i * ld) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (i < L && k8 == 0) delta[((size_t)b * H + h) * L + i] = acc;
+  }
 }
 
 __global__ void __launch_bounds__(256, 1)
@@ -1044,6 +934,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   const int j0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int L = a.L, H = a.H;
   const int n_q = (L + 127) / 128;
+  const float inv_s = __ldg(a.inv_scale + b * H + h);          // dO16 = dO * s_bh: the results leave the scaled domain here
 
   if (tid == 0) {
     ptx::prefetch_tensormap(&tmQKV); ptx::prefetch_tensormap(&tmDO);
@@ -1058,9 +949,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   const uint32_t t_lane = tmem + ((uint32_t)(lq * 32) << 16);
   const int r = lq * 32 + lane;                        // tile row handled by this thread (query row / key row)
 
-  constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, 128, 0, 0);    // S, dP
-  constexpr uint32_t idesc_kv = ptx::make_idesc_bf16(128, 64, 1, 1);    // dV, dK : A = P^T / dS^T (MN-major), B MN-major
-  constexpr uint32_t idesc_q = ptx::make_idesc_bf16(128, 64, 0, 1);     // dQ : A = dS (K-major), B = K (MN-major)
+  using ptx::kFmtF16;
+  constexpr uint32_t idesc_s = ptx::make_idesc_16(128, 128, 0, 0, kFmtF16, kFmtF16);     // S = Q K^T (half x half)
+  constexpr uint32_t idesc_dp = idesc_s;                                                  // dP = dO16 V^T
+  constexpr uint32_t idesc_dv = ptx::make_idesc_16(128, 64, 1, 1, kFmtF16, kFmtF16);     // dV: A = Pd^T (MN-major), B = dO16 (MN-major)
+  constexpr uint32_t idesc_dk = idesc_dv;                                                 // dK: A = dS^T (MN-major), B = Q (MN-major)
+  constexpr uint32_t idesc_q = ptx::make_idesc_16(128, 64, 0, 1, kFmtF16, kFmtF16);      // dQ: A = dS (K-major), B = K (MN-major)
 
   if (tid == 0) {
     ptx::mbar_arrive_expect_tx(kv_bar, 2 * 16384);
@@ -1088,7 +982,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 #pragma unroll
         for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem + kScol, dq + k * kStepK, dk + k * kStepK, idesc_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem + kDPcol, dg + k * kStepK, dv + k * kStepK, idesc_s, k > 0);
+        for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem + kDPcol, dg + k * kStepK, dv + k * kStepK, idesc_dp, k > 0);
         ptx::umma_commit(s_bar);
       }
       __syncwarp();
@@ -1120,8 +1014,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         pv[k] = p * keep;
         dsv[k] = p * (__uint_as_float(d[k]) * keep - dlt) * a.scale;
       }
-      store_p_chunk(sP, r, c, pv);
-      store_p_chunk(sDS, r, c, dsv);
+      store_p_chunk<true>(sP, r, c, pv);
+      store_p_chunk<true>(sDS, r, c, dsv);
     }
     ptx::tc_fence_before();
     ptx::fence_proxy_async_smem();
@@ -1136,9 +1030,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       if (ptx::elect_one()) {
         // dV[j,d] += sum_i P[i,j] dO[i,d] ; dK[j,d] += sum_i dS[i,j] Q[i,d]   (contraction over the 128 rows)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) ptx::umma_f16(tmem + kDVcol, ap + k * kStepMN, bg + k * kStepMN, idesc_kv, (t > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < 8; ++k) ptx::umma_f16(tmem + kDVcol, ap + k * kStepMN, bg + k * kStepMN, idesc_dv, (t > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) ptx::umma_f16(tmem + kDKcol, as_t + k * kStepMN, bq + k * kStepMN, idesc_kv, (t > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < 8; ++k) ptx::umma_f16(tmem + kDKcol, as_t + k * kStepMN, bq + k * kStepMN, idesc_dk, (t > 0 || k > 0) ? 1u : 0u);
         // dQ[i,d] = sum_j dS[i,j] K[j,d]   (contraction over the 128 keys of this CTA)
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -1158,8 +1052,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         float* dst = a.dq_accum + ((size_t)b * L + i) * (size_t)(H * TDH) + h * TDH + half * 32;
 #pragma unroll
         for (int k = 0; k < 32; k += 4)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + k), "f"(__uint_as_float(q[k])),
-                       "f"(__uint_as_float(q[k + 1])), "f"(__uint_as_float(q[k + 2])), "f"(__uint_as_float(q[k + 3]))
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + k), "f"(__uint_as_float(q[k]) * inv_s),
+                       "f"(__uint_as_float(q[k + 1]) * inv_s), "f"(__uint_as_float(q[k + 2]) * inv_s), "f"(__uint_as_float(q[k + 3]) * inv_s)
                        : "memory");
       }
     }
@@ -1182,10 +1076,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 #pragma unroll
         for (int k = 0; k < 32; k += 8)
           *reinterpret_cast<uint4*>(dst + c * 32 + k) =
-              make_uint4(pack_bf16(__uint_as_float(v[k]), __uint_as_float(v[k + 1])),
-                         pack_bf16(__uint_as_float(v[k + 2]), __uint_as_float(v[k + 3])),
-                         pack_bf16(__uint_as_float(v[k + 4]), __uint_as_float(v[k + 5])),
-                         pack_bf16(__uint_as_float(v[k + 6]), __uint_as_float(v[k + 7])));
+              make_uint4(pack_bf16(__uint_as_float(v[k]) * inv_s, __uint_as_float(v[k + 1]) * inv_s),
+                         pack_bf16(__uint_as_float(v[k + 2]) * inv_s, __uint_as_float(v[k + 3]) * inv_s),
+                         pack_bf16(__uint_as_float(v[k + 4]) * inv_s, __uint_as_float(v[k + 5]) * inv_s),
+                         pack_bf16(__uint_as_float(v[k + 6]) * inv_s, __uint_as_float(v[k + 7]) * inv_s));
       }
     }
   }
@@ -1322,9 +1216,12 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
       const uint32_t sQ = ptx::smem_u32(smem + SM::kQ), sDO = ptx::smem_u32(smem + SM::kDO);
       const uint32_t sK = ptx::smem_u32(smem + SM::kK), sV = ptx::smem_u32(smem + SM::kV);
       const uint32_t sP = ptx::smem_u32(smem + SM::kP), sDS = ptx::smem_u32(smem + SM::kDS);
-      constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, 64, 0, 0);    // S, dP of a 64-key sub-block
-      constexpr uint32_t idesc_kv = ptx::make_idesc_bf16(128, 64, 1, 1);   // dV, dK: A = Pd^T / dS^T (MN-major), B MN-major
-      constexpr uint32_t idesc_q = ptx::make_idesc_bf16(128, 64, 0, 1);    // dQ: A = dS (K-major), B = K (MN-major)
+      using ptx::kFmtF16;
+      constexpr uint32_t idesc_s = ptx::make_idesc_16(128, 64, 0, 0, kFmtF16, kFmtF16);     // S = Q K^T of a 64-key sub-block
+      constexpr uint32_t idesc_dp = idesc_s;                                                 // dP = dO16 V^T
+      constexpr uint32_t idesc_dv = ptx::make_idesc_16(128, 64, 1, 1, kFmtF16, kFmtF16);    // dV: A = Pd^T (MN-major), B = dO16 (MN-major)
+      constexpr uint32_t idesc_dk = idesc_dv;                                                // dK: A = dS^T (MN-major), B = Q (MN-major)
+      constexpr uint32_t idesc_q = ptx::make_idesc_16(128, 64, 0, 1, kFmtF16, kFmtF16);     // dQ: A = dS (K-major), B = K (MN-major)
       // k-step increments of the descriptor start-address field (bytes >> 4)
       constexpr uint64_t kStepK = 32 >> 4, kStepMN = 2048 >> 4;
       auto issue_sdp = [&](int u) {
@@ -1338,7 +1235,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) ptx::umma_f16(tmem + col, dq + kk * kStepK, dk + kk * kStepK, idesc_s, kk > 0);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) ptx::umma_f16(tmem + col + 64, dg + kk * kStepK, dv + kk * kStepK, idesc_s, kk > 0);
+          for (int kk = 0; kk < 4; ++kk) ptx::umma_f16(tmem + col + 64, dg + kk * kStepK, dv + kk * kStepK, idesc_dp, kk > 0);
           ptx::umma_commit(&s_full[u & 1]);
         }
         __syncwarp();
@@ -1369,10 +1266,10 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
               // block (jt, it) complete: dV_jt[j,d] += sum_i Pd[i,j] dO[i,d] ; dK_jt[j,d] += sum_i dS[i,j] Q[i,d]
 #pragma unroll
               for (int kk = 0; kk < 8; ++kk)
-                ptx::umma_f16(tmem + kDVcol, a_p + kk * kStepMN, b_do + kk * kStepMN, idesc_kv, kk > 0 ? 1u : first_kv);
+                ptx::umma_f16(tmem + kDVcol, a_p + kk * kStepMN, b_do + kk * kStepMN, idesc_dv, kk > 0 ? 1u : first_kv);
 #pragma unroll
               for (int kk = 0; kk < 8; ++kk)
-                ptx::umma_f16(tmem + kDKcol, a_dst + kk * kStepMN, b_q + kk * kStepMN, idesc_kv, kk > 0 ? 1u : first_kv);
+                ptx::umma_f16(tmem + kDKcol, a_dst + kk * kStepMN, b_q + kk * kStepMN, idesc_dk, kk > 0 ? 1u : first_kv);
             }
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
@@ -1394,10 +1291,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
     const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16);
     const uint32_t sP = ptx::smem_u32(smem + SM::kP), sDS = ptx::smem_u32(smem + SM::kDS);
     const uint32_t st_out = ptx::smem_u32(smem + SM::kOut) + (warp - 2) * 2048;
-    const uint32_t th16 = a.drop_thresh << 16;
-    const bool drop = a.drop_thresh != 0;
     const float sl2 = a.scale_log2, ds = a.drop_scale;
-    const uint32_t ngrp = (uint32_t)((L + 7) >> 3);
     __nv_bfloat16* dqkv = reinterpret_cast<__nv_bfloat16*>(a.dqkv);
     const long long ld3 = 3ll * H * TDH;
 
@@ -1405,10 +1299,12 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
     // of sub-block (jt, jh) are keys jt*128 + jh*64 + slice*16 .. +15: bits (jh*64 + slice*16) & 31 .. of word
     // 4 jt + 2 jh + slice/2 of its allow row; aw_nx[t][jt] holds them for jh = 0 (low half) and jh = 1 (high half)
     float lse2_nx[2], dlt_nx[2];
-    uint32_t aw_nx[2][2];
+    uint32_t aw_nx[2][2], kw_nx[2][2];      // kw: dropout keep bits, same packing as the allow bits
     auto fetch_rows = [&](int item_) {
 #pragma unroll
-      for (int t = 0; t < 2; ++t) { lse2_nx[t] = INFINITY; dlt_nx[t] = 0.f; aw_nx[t][0] = aw_nx[t][1] = 0u; }
+      for (int t = 0; t < 2; ++t) {
+        lse2_nx[t] = INFINITY; dlt_nx[t] = 0.f; aw_nx[t][0] = aw_nx[t][1] = 0u; kw_nx[t][0] = kw_nx[t][1] = 0xffffffffu;
+      }
       if (item_ >= n_items) return;
       const int b_ = (int)__umulhi((uint32_t)item_, magic_h), h_ = item_ - b_ * H;
 #pragma unroll
@@ -1426,6 +1322,13 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
             if (w0 < a.W) lo = (__ldg(ar + w0) >> sh) & 0xffffu;
             if (w1 < a.W) hi = (__ldg(ar + w1) >> sh) & 0xffffu;
             aw_nx[t][jt] = lo | (hi << 16);
+            if (a.keep) {
+              const uint32_t* kr = a.keep + (((size_t)b_ * H + h_) * L + i) * a.W;
+              uint32_t klo = 0u, khi = 0u;
+              if (w0 < a.W) klo = (__ldg(kr + w0) >> sh) & 0xffffu;
+              if (w1 < a.W) khi = (__ldg(kr + w1) >> sh) & 0xffffu;
+              kw_nx[t][jt] = klo | (khi << 16);
+            }
           }
         }
       }
@@ -1435,12 +1338,15 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
     int iter = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++iter) {
       const int b = (int)__umulhi((uint32_t)item, magic_h), h = item - b * H;
+      const float inv_s = __ldg(a.inv_scale + item);           // item = b H + h: leave the scaled domain at the drains
       float lse2[2], dlt[2];
-      uint32_t aw[2][2];
+      uint32_t aw[2][2], kwd[2][2];
 #pragma unroll
-      for (int t = 0; t < 2; ++t) { lse2[t] = lse2_nx[t]; dlt[t] = dlt_nx[t]; aw[t][0] = aw_nx[t][0]; aw[t][1] = aw_nx[t][1]; }
+      for (int t = 0; t < 2; ++t) {
+        lse2[t] = lse2_nx[t]; dlt[t] = dlt_nx[t]; aw[t][0] = aw_nx[t][0]; aw[t][1] = aw_nx[t][1];
+        kwd[t][0] = kw_nx[t][0]; kwd[t][1] = kw_nx[t][1];
+      }
       fetch_rows(item + gridDim.x);
-      const uint64_t drow_b = (uint64_t)(b * H + h) * L;
       for (int u = 0; u < n_sub; ++u) {
         int jt, it, jh, nh;
         decode_sub(u, jt, it, jh, nh);
@@ -1450,8 +1356,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
         const float my_lse2 = it ? lse2[1] : lse2[0], my_dlt = it ? dlt[1] : dlt[0];
         const uint32_t my_aw = it ? (jt ? aw[1][1] : aw[1][0]) : (jt ? aw[0][1] : aw[0][0]);
         const uint32_t awc = active ? ((my_aw >> (16 * jh)) & 0xffffu) : 0u;
-        const int col0 = jt * 128 + jh * 64 + slice * 16;      // first key of this thread's 16 columns
-        const uint64_t grp_base = (drow_b + (uint64_t)i) * ngrp + (uint64_t)(col0 >> 3);
+        const uint32_t my_kw = it ? (jt ? kwd[1][1] : kwd[1][0]) : (jt ? kwd[0][1] : kwd[0][0]);
+        const uint32_t kwc = (my_kw >> (16 * jh)) & 0xffffu;
         if (warp == 2 && lane == 0) TL_STAMP(20, (int)(cs0 + cs1));
         if (u & 1) { ptx::mbar_wait(&s_full[1], cs1 & 1); ++cs1; } else { ptx::mbar_wait(&s_full[0], cs0 & 1); ++cs0; }
         ptx::tc_fence_after();
@@ -1471,20 +1377,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
               const float arg = fmaf(__uint_as_float(rs[8 * q + x]), sl2, -my_lse2);
               e[x] = ((awc >> (8 * q + x)) & 1u) ? fast_exp2(arg) : 0.f;
             }
-            if (drop) {
-              const uint4 rnd = philox4x32(a.seed, grp_base + (uint64_t)q, (uint32_t)a.off);
-              kf[0] = (rnd.x << 16) >= th16 ? ds : 0.f;
-              kf[1] = rnd.x >= th16 ? ds : 0.f;
-              kf[2] = (rnd.y << 16) >= th16 ? ds : 0.f;
-              kf[3] = rnd.y >= th16 ? ds : 0.f;
-              kf[4] = (rnd.z << 16) >= th16 ? ds : 0.f;
-              kf[5] = rnd.z >= th16 ? ds : 0.f;
-              kf[6] = (rnd.w << 16) >= th16 ? ds : 0.f;
-              kf[7] = rnd.w >= th16 ? ds : 0.f;
-            } else {
 #pragma unroll
-              for (int x = 0; x < 8; ++x) kf[x] = 1.f;
-            }
+            for (int x = 0; x < 8; ++x) kf[x] = ((kwc >> (8 * q + x)) & 1u) ? ds : 0.f;
 #pragma unroll
             for (int x = 0; x < 8; ++x) {
               uu[x] = e[x] * fmaf(__uint_as_float(rd[8 * q + x]), kf[x], -my_dlt);   // dS / scale
@@ -1492,8 +1386,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
             }
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
-              pk[4 * q + x] = pack_bf16(e[2 * x], e[2 * x + 1]);
-              dk_[4 * q + x] = pack_bf16(uu[2 * x], uu[2 * x + 1]);
+              pk[4 * q + x] = pack_f16(e[2 * x], e[2 * x + 1]);
+              dk_[4 * q + x] = pack_f16_sat(uu[2 * x], uu[2 * x + 1]);
             }
           }
         } else {
@@ -1529,7 +1423,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
             if (j0 < L) {
               const bool is_k = slice < 2;
               const int hc = (slice & 1) * 32;
-              drain32_bf16(t_lane + (is_k ? kDKcol : kDVcol) + hc, is_k ? a.scale : 1.f, st_out,
+              drain32_bf16(t_lane + (is_k ? kDKcol : kDVcol) + hc, is_k ? a.scale * inv_s : inv_s, st_out,
                            dqkv + (size_t)((is_k ? H : 2 * H) + h) * TDH + hc, ld3, (long long)b * L + j0, 0, min(32, L - j0), lane);
             }
             ptx::tc_fence_before();
@@ -1543,7 +1437,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
         const int t = slice >> 1, hc = (slice & 1) * 32;
         const int i0 = t * 128 + quarter * 32;
         if (t < n_t && i0 < L)
-          drain32_bf16(t_lane + kDQcol + t * 64 + hc, a.scale, st_out, dqkv + (size_t)h * TDH + hc, ld3, (long long)b * L + i0, 0,
+          drain32_bf16(t_lane + kDQcol + t * 64 + hc, a.scale * inv_s, st_out, dqkv + (size_t)h * TDH + hc, ld3, (long long)b * L + i0, 0,
                        min(32, L - i0), lane);
         ptx::tc_fence_before();
       }
@@ -1571,7 +1465,10 @@ __global__ void attn_dq_store_kernel(const float* __restrict__ acc, __nv_bfloat1
 static int fill_tc(TcArgs& a, const samk_attn_params* p) {
   if (!p->allow_bits) { set_error("samk_attn: tensor-core path needs allow_bits (samk_attn_build_mask)"); return SAMK_ERR_ARG; }
   a.ctx = p->ctx; a.lse = p->lse; a.delta = p->delta; a.dqkv = p->dqkv; a.dq_accum = p->dq_accum;
+  a.inv_scale = p->do_inv_scale;
   a.allow = p->allow_bits; a.Hm = p->spatial ? p->H : 1;
+  a.keep = p->drop_p > 0.f ? p->keep_bits : nullptr;
+  if (p->drop_p > 0.f && !p->keep_bits) { set_error("samk_attn: tensor-core path with dropout needs keep_bits (samk_attn_build_keep)"); return SAMK_ERR_ARG; }
   a.B = p->B; a.H = p->H; a.L = p->T + p->A + p->D; a.W = (a.L + 31) / 32;
   a.scale = p->scale; a.scale_log2 = p->scale * kLog2e;
   a.drop_thresh = p->drop_p > 0.f ? drop_threshold(p->drop_p) : 0u;
@@ -1588,21 +1485,6 @@ static int set_smem(K kern, int bytes) {
     return SAMK_ERR_CUDA;
   }
   return SAMK_OK;
-}
-
-template <int KVT>
-static int launch_fwd(const samk_attn_params* p, const TcArgs& a, cudaStream_t stream) {
-  const long long rows = (long long)a.B * a.L;
-  const int hd3 = 3 * a.H * TDH;
-  CUtensorMap tq, tkv;
-  int rc;
-  if ((rc = make_tmap_bf16_2d(&tq, p->qkv, rows, hd3, hd3, 64, 128))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tkv, p->qkv, rows, hd3, hd3, 64, KVT))) return rc;
-  constexpr int smem = 16384 + 2 * KVT * 128 + (KVT / 64) * 16384 + 64;
-  if ((rc = set_smem(attn_fwd_tc_kernel<KVT>, smem))) return rc;
-  dim3 grid((a.L + 127) / 128 - a.q_tile0, a.H, a.B);
-  attn_fwd_tc_kernel<KVT><<<grid, 128, smem, stream>>>(tq, tkv, a);
-  return check_launch("samk_attn_fwd(tc)");
 }
 
 int sm_count();
@@ -1657,7 +1539,7 @@ static int attn_fwd_version() {
   static int v = -1;
   if (v < 0) {
     const char* s = getenv("SAMK_ATTN_FWD_V");
-    v = (s && s[0] >= '1' && s[0] <= '3') ? s[0] - '0' : 0;      // 0 = pick by sequence length
+    v = (s && s[0] >= '2' && s[0] <= '3') ? s[0] - '0' : 0;      // 0 = pick by sequence length
   }
   return v;
 }
@@ -1675,13 +1557,8 @@ int attn_tc_fwd(const samk_attn_params* p, cudaStream_t stream) {
     if (a.L > 128 && a.L <= 192) return launch_fwd3<192>(p, a, stream);
     return launch_fwd3<128>(p, a, stream);
   }
-  if (ver == 2) {
-    if (a.L > 128 && a.L <= 192) return launch_fwd2<192>(p, a, stream);
-    return launch_fwd2<128>(p, a, stream);
-  }
-  // one 192-key tile covers the shipped L=182; otherwise stream 128-key tiles
-  if (a.L > 128 && a.L <= 192) return launch_fwd<192>(p, a, stream);
-  return launch_fwd<128>(p, a, stream);
+  if (a.L > 128 && a.L <= 192) return launch_fwd2<192>(p, a, stream);
+  return launch_fwd2<128>(p, a, stream);
 }
 
 static int attn_bwd_version() {
@@ -1697,21 +1574,19 @@ int attn_tc_bwd(const samk_attn_params* p, cudaStream_t stream) {
   TcArgs a;
   int rc = fill_tc(a, p);
   if (rc) return rc;
-  if (!p->qkv || !p->ctx || !p->lse || !p->dctx || !p->dqkv || !p->delta) {
-    set_error("samk_attn_bwd: null pointer");
+  if (!p->qkv || !p->ctx || !p->lse || !p->dctx || !p->dqkv || !p->delta || !p->do_f16 || !p->do_inv_scale) {
+    set_error("samk_attn_bwd: null pointer (the tensor-core path needs the do_f16 / do_inv_scale workspaces)");
     return SAMK_ERR_ARG;
   }
   if (!a.B || !a.L) return SAMK_OK;
   const long long rows = (long long)a.B * a.L;
   const int hd = a.H * TDH;
-  if (!p->delta_ready) {
-    attn_delta_kernel<<<(unsigned)((rows * a.H * 8 + 255) / 256), 256, 0, stream>>>(
-        (const __nv_bfloat16*)p->dctx, (const __nv_bfloat16*)p->ctx, p->delta, a.B, a.H, a.L);
-    if ((rc = check_launch("samk_attn_bwd(delta)"))) return rc;
-  }
+  attn_bwd_prep_kernel<<<a.B * a.H, 256, 0, stream>>>((const __nv_bfloat16*)p->dctx, (const __half*)p->ctx, (__half*)p->do_f16,
+                                                     p->delta, p->do_inv_scale, a.H, a.L);
+  if ((rc = check_launch("samk_attn_bwd(prep)"))) return rc;
   CUtensorMap tqkv, tdo;
   if ((rc = make_tmap_bf16_2d(&tqkv, p->qkv, rows, 3 * hd, 3 * hd, 64, 128))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tdo, p->dctx, rows, hd, hd, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tdo, p->do_f16, rows, hd, hd, 64, 128))) return rc;
 
   if (a.L <= 256 && attn_bwd_version() == 2) {
     // whole (sample, head) per CTA: dQ, dK, dV complete in TMEM, written once
@@ -1774,24 +1649,29 @@ int samk_attn_build_mask(const samk_attn_params* p, uint32_t* allow_bits, void* 
   return check_launch("samk_attn_build_mask");
 }
 
-int samk_attn_fwd(const samk_attn_params* p, int impl, void* stream) {
-  if (!p) { samk::set_error("samk_attn_fwd: null params"); return SAMK_ERR_ARG; }
-  if (impl == 0 && p->dtype == SAMK_DT_BF16) return samk::attn_tc_fwd(p, (cudaStream_t)stream);
-  return samk::attn_simt_fwd(p, (cudaStream_t)stream);
+int samk_attn_build_keep(const samk_attn_params* p, uint32_t* keep_bits, void* stream) {
+  using namespace samk;
+  if (!p || !keep_bits) { set_error("samk_attn_build_keep: null pointer"); return SAMK_ERR_ARG; }
+  const int L = p->T + p->A + p->D, W = (L + 31) / 32;
+  const long long n = (long long)p->B * p->H * L * W;
+  if (!n) return SAMK_OK;
+  const uint32_t thresh = p->drop_p > 0.f ? drop_threshold(p->drop_p) : 0u;
+  attn_build_keep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(keep_bits, n, L, W, thresh, p->drop_seed,
+                                                                                       p->drop_offset);
+  return check_launch("samk_attn_build_keep");
 }
 
-int samk_attn_delta(const void* dctx, const void* ctx, float* delta, int B, int H, int L, void* stream) {
-  if (!dctx || !ctx || !delta || B < 0 || H <= 0 || L < 0) { samk::set_error("samk_attn_delta: bad argument"); return SAMK_ERR_ARG; }
-  const long long items = (long long)B * L * H;
-  if (!items) return SAMK_OK;
-  samk::attn_delta_kernel<<<(unsigned)((items * 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)dctx, (const __nv_bfloat16*)ctx, delta, B, H, L);
-  return samk::check_launch("samk_attn_delta");
+int samk_attn_fwd(const samk_attn_params* p, int impl, void* stream) {
+  if (!p) { samk::set_error("samk_attn_fwd: null params"); return SAMK_ERR_ARG; }
+  if (impl == 0 && p->dtype == SAMK_DT_F16) return samk::attn_tc_fwd(p, (cudaStream_t)stream);
+  if (impl == 0 && p->dtype != SAMK_DT_F32) { samk::set_error("samk_attn_fwd: the tensor-core kernels take f16 q|k|v"); return SAMK_ERR_UNSUPPORTED; }
+  return samk::attn_simt_fwd(p, (cudaStream_t)stream);
 }
 
 int samk_attn_bwd(const samk_attn_params* p, int impl, void* stream) {
   if (!p) { samk::set_error("samk_attn_bwd: null params"); return SAMK_ERR_ARG; }
-  if (impl == 0 && p->dtype == SAMK_DT_BF16) return samk::attn_tc_bwd(p, (cudaStream_t)stream);
+  if (impl == 0 && p->dtype == SAMK_DT_F16 && p->grad_dtype == SAMK_DT_BF16) return samk::attn_tc_bwd(p, (cudaStream_t)stream);
+  if (impl == 0 && p->dtype != SAMK_DT_F32) { samk::set_error("samk_attn_bwd: the tensor-core kernels take f16 q|k|v / ctx and bf16 gradients"); return SAMK_ERR_UNSUPPORTED; }
   return samk::attn_simt_bwd(p, (cudaStream_t)stream);
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -184,6 +185,43 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  __half2 t = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// 16-bit storage formats of the tensor-core operands: F16 = IEEE half (forward activations and weights: 11 significant
+// bits, logits within 1e-3 of the fp32 reference), BF16 = bfloat16 (gradients: fp32 exponent range, no loss scaling)
+template <bool F16> __device__ __forceinline__ uint32_t pack_16(float a, float b) {
+  if constexpr (F16) return pack_f16(a, b); else return pack_bf16(a, b);
+}
+__device__ __forceinline__ uint32_t pack_16(float a, float b, bool f16) { return f16 ? pack_f16(a, b) : pack_bf16(a, b); }
+template <bool F16> __device__ __forceinline__ float2 unpack_16(uint32_t u) {
+  if constexpr (F16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+  else return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+}
+__device__ __forceinline__ float2 unpack_16(uint32_t u, bool f16) { return f16 ? unpack_16<true>(u) : unpack_16<false>(u); }
+__device__ __forceinline__ float ld_16(const void* p, bool f16) {
+  return f16 ? __half2float(*reinterpret_cast<const __half*>(p)) : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p));
+}
+__device__ __forceinline__ void st_16(void* p, float v, bool f16) {
+  if (f16) *reinterpret_cast<__half*>(p) = __float2half_rn(v); else *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ float pow2_scale_for(float amax, int target_exp) {
+  // S = 2^(target_exp - e) with amax = f * 2^e, f in [0.5, 1): amax * S in [2^(target_exp-1), 2^target_exp)
+  if (!(amax > 0.f) || !isfinite(amax)) return 1.0f;
+  int e;
+  frexpf(amax, &e);
+  int k = target_exp - e;
+  k = k > 120 ? 120 : (k < -120 ? -120 : k);
+  return ldexpf(1.0f, k);
+}
+__device__ __forceinline__ uint32_t pack_f16_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
 template <class T> struct Elem;
 template <> struct Elem<float> {
   static __device__ __forceinline__ float ld(const float* p) { return *p; }
@@ -192,6 +230,11 @@ template <> struct Elem<float> {
 template <> struct Elem<__nv_bfloat16> {
   static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
   static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+template <> struct Elem<__half> {
+  static __device__ __forceinline__ float ld(const __half* p) { return __half2float(*p); }
+  static __device__ __forceinline__ void st(__half* p, float v) { *p = __float2half_rn(v); }
 };
 
 }  // namespace samk

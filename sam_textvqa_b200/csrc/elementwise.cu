@@ -11,9 +11,11 @@ namespace samk {
 constexpr int kRowThreads = 256;           // 8 warps per block
 constexpr int kMaxVec = 8;                 // float4 per lane -> cols <= 1024
 
+// `bf16` arguments below carry the SAMK_DT_* code of the buffer: 0 = fp32, 1 = bf16, 2 = f16
 __device__ __forceinline__ void store_act(void* base, int bf16, size_t idx, float4 v) {
   if (bf16) {
-    uint2 u = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    const bool h = bf16 == SAMK_DT_F16;
+    uint2 u = make_uint2(pack_16(v.x, v.y, h), pack_16(v.z, v.w, h));
     *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = u;
   } else {
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx) = v;
@@ -22,8 +24,8 @@ __device__ __forceinline__ void store_act(void* base, int bf16, size_t idx, floa
 __device__ __forceinline__ float4 load_act(const void* base, int bf16, size_t idx) {
   if (bf16) {
     uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx);
-    float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.x));
-    float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.y));
+    const bool h = bf16 == SAMK_DT_F16;
+    float2 a = unpack_16(u.x, h), b = unpack_16(u.y, h);
     return make_float4(a.x, a.y, b.x, b.y);
   }
   return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
@@ -46,12 +48,12 @@ __device__ __forceinline__ float4 ld4(const float* p, int vec) {
 }
 
 __global__ void cast_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy,
-                            int rows, int cols, int vec) {
+                            int rows, int cols, int vec, int f16) {
   const int c4 = cols >> 2;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)rows * c4; i += (size_t)gridDim.x * blockDim.x) {
     int r = (int)(i / c4), c = (int)(i % c4) * 4;
     float4 v = ld4(x + (size_t)r * ldx + c, vec);
-    *reinterpret_cast<uint2*>(y + (size_t)r * ldy + c) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    *reinterpret_cast<uint2*>(y + (size_t)r * ldy + c) = make_uint2(pack_16(v.x, v.y, f16 != 0), pack_16(v.z, v.w, f16 != 0));
   }
 }
 
@@ -105,7 +107,8 @@ __global__ void l2norm_kernel(const float* __restrict__ x, long long ldx, void* 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRowThreads)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                     float eps, float* __restrict__ y, void* __restrict__ y2, int y2_bf16, int rows, int cols) {
+                     float eps, float* __restrict__ y, void* __restrict__ y2, int y2_bf16, void* __restrict__ y3, int y3_bf16,
+                     int rows, int cols) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   pdl_wait();
@@ -144,6 +147,7 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
       o.w = g.w * ((v[i].w - mean) * rstd) + b.w;
       if (y) *reinterpret_cast<float4*>(y + (size_t)r * cols + c) = o;
       if (y2) store_act(y2, y2_bf16, (size_t)r * cols + c, o);
+      if (y3) store_act(y3, y3_bf16, (size_t)r * cols + c, o);
     }
   }
 }
@@ -353,7 +357,7 @@ __global__ void colsum_scalar_kernel(const void* __restrict__ x, int x_bf16, lon
   float acc = 0.f;
   for (int r = lane; r < rows; r += 32) {
     const size_t i = (size_t)r * ld + col;
-    acc += x_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[i]) : reinterpret_cast<const float*>(x)[i];
+    acc += x_bf16 ? ld_16(reinterpret_cast<const uint16_t*>(x) + i, x_bf16 == SAMK_DT_F16) : reinterpret_cast<const float*>(x)[i];
   }
   acc = warp_sum(acc);
   if (lane == 0) atomicAdd(out + col, acc);
@@ -851,17 +855,55 @@ static inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 using namespace samk;
 
+// ---------------------------------------------------------------------------------------------
+// Exactly scaled f16 copy of a gradient tensor: pass 1 finds max|x| (non-negative floats order like their bit
+// patterns, so an unsigned atomicMax does it), pass 2 multiplies by the power of two that puts the maximum into
+// [2^11, 2^12) and rounds to IEEE half (saturating).  scale2 = {S, 1/S}; 1/S is the alpha of the consuming GEMM.
+// ---------------------------------------------------------------------------------------------
+__global__ void amax_kernel(const void* __restrict__ x, int dt, long long n4, unsigned int* __restrict__ amax_bits) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = load_act(x, dt, (size_t)i * 4);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));
+}
+__global__ void cast_scaled_f16_kernel(const void* __restrict__ x, int dt, long long n4, const unsigned int* __restrict__ amax_bits,
+                                       __half* __restrict__ y, float* __restrict__ scale2) {
+  const float S = pow2_scale_for(__uint_as_float(*amax_bits), 12);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { scale2[0] = S; scale2[1] = 1.0f / S; }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = load_act(x, dt, (size_t)i * 4);
+    *reinterpret_cast<uint2*>(y + i * 4) = make_uint2(pack_f16_sat(v.x * S, v.y * S), pack_f16_sat(v.z * S, v.w * S));
+  }
+}
+
+// out[0:n] = a, out[n:2n] = b, out[2n:3n] = c (the three biases of the fused q|k|v projection)
+__global__ void concat3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                               float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * n) return;
+  out[i] = i < n ? a[i] : (i < 2 * n ? b[i - n] : c[i - 2 * n]);
+}
+
 #define SAMK_REQUIRE(cond, msg) \
   do { if (!(cond)) { set_error("%s: %s", __func__, msg); return SAMK_ERR_ARG; } } while (0)
 
 extern "C" {
 
-int samk_cast_bf16(const float* x, long long ldx, void* y, long long ldy, int rows, int cols, void* stream) {
+int samk_cast_16(const float* x, long long ldx, void* y, long long ldy, int y_dtype, int rows, int cols, void* stream) {
   SAMK_REQUIRE(x && y && rows >= 0 && cols >= 0, "bad argument");
+  SAMK_REQUIRE(y_dtype == SAMK_DT_BF16 || y_dtype == SAMK_DT_F16, "y_dtype must be a 16-bit format");
   SAMK_REQUIRE(cols % 4 == 0 && ldy % 4 == 0 && ((uintptr_t)y & 7) == 0, "cols/ldy must be multiples of 4");
   if (!rows || !cols) return SAMK_OK;
-  cast_kernel<<<grid_for((long long)rows * cols / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, (__nv_bfloat16*)y, ldy, rows, cols, (ldx % 4 == 0 && al16(x)) ? 1 : 0);
+  cast_kernel<<<grid_for((long long)rows * cols / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, ldx, (__nv_bfloat16*)y, ldy, rows, cols, (ldx % 4 == 0 && al16(x)) ? 1 : 0, y_dtype == SAMK_DT_F16 ? 1 : 0);
   return check_launch(__func__);
+}
+
+int samk_cast_bf16(const float* x, long long ldx, void* y, long long ldy, int rows, int cols, void* stream) {
+  return samk_cast_16(x, ldx, y, ldy, SAMK_DT_BF16, rows, cols, stream);
 }
 
 int samk_split3_bf16(const float* x, long long ldx, void* y, long long ldy, int rows, int cols, int order,
@@ -878,17 +920,17 @@ int samk_l2norm(const float* x, long long ldx, void* y, long long ldy, int y_dty
   SAMK_REQUIRE(x && y && rows >= 0 && cols >= 0, "bad argument");
   SAMK_REQUIRE(cols % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && al16(x) && ((uintptr_t)y & 7) == 0, "cols/ld must be multiples of 4");
   if (!rows || !cols) return SAMK_OK;
-  l2norm_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, y_dtype == SAMK_DT_BF16, rows, cols, normalize);
+  l2norm_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, y_dtype, rows, cols, normalize);
   return check_launch(__func__);
 }
 
 int samk_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y, void* y2,
-                       int y2_dtype, int rows, int cols, void* stream) {
-  SAMK_REQUIRE(x && gamma && beta && (y || y2) && rows >= 0, "bad argument");
+                       int y2_dtype, void* y3, int y3_dtype, int rows, int cols, void* stream) {
+  SAMK_REQUIRE(x && gamma && beta && (y || y2 || y3) && rows >= 0, "bad argument");
   SAMK_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 1024, "cols must be a multiple of 4, <= 1024");
   if (!rows) return SAMK_OK;
   launch_maybe_pdl(layernorm_fwd_kernel, dim3(grid_for(rows, 8)), dim3(kRowThreads), 0, (cudaStream_t)stream,
-                   pdl_level() >= 2, x, gamma, beta, eps, y, y2, (int)(y2_dtype == SAMK_DT_BF16), rows, cols);
+                   pdl_level() >= 2, x, gamma, beta, eps, y, y2, y2_dtype, y3, y3_dtype, rows, cols);
   return check_launch(__func__);
 }
 
@@ -902,7 +944,7 @@ int samk_layernorm_bwd(const float* dy, const float* x, const float* gamma, floa
   if (grid > 592) grid = 592;   // partials workspace is sized for 592 blocks (samk_layernorm_bwd_partials)
   const int smem = kLnBwdWarps * 3 * cols * (int)sizeof(float);
   launch_maybe_pdl(layernorm_bwd_kernel, dim3(grid), dim3(kLnBwdWarps * 32), (size_t)smem, (cudaStream_t)stream,
-                   pdl_level() >= 2, dy, x, gamma, eps, dx, dxd, (int)(dxd_dtype == SAMK_DT_BF16),
+                   pdl_level() >= 2, dy, x, gamma, eps, dx, dxd, dxd_dtype,
                    drop_p > 0.f ? drop_threshold(drop_p) : 0u, drop_keep_scale(drop_p), seed, offset, dgamma, dbeta,
                    dbias, partials, rows, cols);
   int rc = check_launch(__func__);
@@ -918,7 +960,7 @@ int samk_dropout_add(const float* a, const float* b, float* out, void* out2, int
   SAMK_REQUIRE(a && (out || out2) && rows >= 0 && cols >= 0 && cols % 4 == 0, "bad argument");
   if (!rows || !cols) return SAMK_OK;
   dropout_add_kernel<<<grid_for((long long)rows * cols / 4, 256), 256, 0, (cudaStream_t)stream>>>(
-      a, b, out, out2, out2_dtype == SAMK_DT_BF16, rows, cols, drop_p > 0.f ? drop_threshold(drop_p) : 0u,
+      a, b, out, out2, out2_dtype, rows, cols, drop_p > 0.f ? drop_threshold(drop_p) : 0u,
       drop_keep_scale(drop_p), seed, offset);
   return check_launch(__func__);
 }
@@ -936,9 +978,9 @@ static int colsum_threads() {
 int samk_colsum(const void* x, int x_dtype, long long ld, int rows, int cols, float* out, void* stream) {
   SAMK_REQUIRE(x && out && rows >= 0 && cols >= 0, "bad argument");
   if (!rows || !cols) return SAMK_OK;
-  const bool bf = x_dtype == SAMK_DT_BF16;
+  const bool bf = x_dtype != SAMK_DT_F32;
   if (cols % 4 || ld % 4 || ((uintptr_t)x & (bf ? 7 : 15))) {
-    colsum_scalar_kernel<<<(cols * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, bf, ld, rows, cols, out);
+    colsum_scalar_kernel<<<(cols * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, x_dtype, ld, rows, cols, out);
     return check_launch(__func__);
   }
   const int gx = (cols / 4 + 63) / 64;
@@ -947,14 +989,14 @@ int samk_colsum(const void* x, int x_dtype, long long ld, int rows, int cols, fl
   if (gy > (rows + nrl - 1) / nrl) gy = (rows + nrl - 1) / nrl;
   if (gy < 1) gy = 1;
   dim3 grid(gx, gy);
-  colsum_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(x, x_dtype == SAMK_DT_BF16, ld, rows, cols, out, nullptr, nullptr, 0);
+  colsum_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(x, x_dtype, ld, rows, cols, out, nullptr, nullptr, 0);
   return check_launch(__func__);
 }
 
 int samk_colsum3(const void* x, int x_dtype, long long ld, int rows, int part_cols, float* out0, float* out1, float* out2,
                  void* stream) {
   SAMK_REQUIRE(x && out0 && out1 && out2 && rows >= 0 && part_cols > 0, "bad argument");
-  const bool bf = x_dtype == SAMK_DT_BF16;
+  const bool bf = x_dtype != SAMK_DT_F32;
   SAMK_REQUIRE(part_cols % 4 == 0 && ld % 4 == 0 && ((uintptr_t)x & (bf ? 7 : 15)) == 0, "needs 4-column aligned parts");
   if (!rows) return SAMK_OK;
   const int cols = 3 * part_cols;
@@ -964,7 +1006,7 @@ int samk_colsum3(const void* x, int x_dtype, long long ld, int rows, int part_co
   if (gy > (rows + nrl - 1) / nrl) gy = (rows + nrl - 1) / nrl;
   if (gy < 1) gy = 1;
   dim3 grid(gx, gy);
-  colsum_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(x, bf, ld, rows, cols, out0, out1, out2, part_cols);
+  colsum_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(x, x_dtype, ld, rows, cols, out0, out1, out2, part_cols);
   return check_launch(__func__);
 }
 
@@ -976,7 +1018,7 @@ int samk_bert_embed_fwd(const long long* ids, const float* word, const float* po
   SAMK_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 1024 && T > 0, "bad size");
   if (!rows) return SAMK_OK;
   bert_embed_fwd_kernel<<<grid_for(rows, 8), kRowThreads, 0, (cudaStream_t)stream>>>(
-      ids, word, pos, type, gamma, beta, eps, out, out2, out2_dtype == SAMK_DT_BF16, rows, T, cols,
+      ids, word, pos, type, gamma, beta, eps, out, out2, out2_dtype, rows, T, cols,
       drop_p > 0.f ? drop_threshold(drop_p) : 0u, drop_keep_scale(drop_p), seed, offset);
   return check_launch(__func__);
 }
@@ -1082,6 +1124,27 @@ int samk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
   adam_kernel<<<grid_for(n, 1024), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(-lr / bc1),
                                                                   (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
                                                                   (float)eps, (float)sqrt(bc2), grad_sumsq, (float)max_norm);
+  return check_launch(__func__);
+}
+
+int samk_cast_scaled_f16(const void* x, int x_dtype, long long n, void* y, float* scale2, void* stream) {
+  SAMK_REQUIRE(x && y && scale2 && n >= 0, "bad argument");
+  SAMK_REQUIRE(n % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 7) == 0, "n must be a multiple of 4, aligned buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  // scale2[0] doubles as the amax accumulator of pass 1 (bit pattern), overwritten with S by pass 2 ... no: a reader
+  // of pass 2 in another block could see S instead of amax, so the accumulator is the third float of the workspace
+  if (cudaMemsetAsync(scale2 + 2, 0, sizeof(float), st) != cudaSuccess) { set_error("%s: memset failed", __func__); return SAMK_ERR_CUDA; }
+  if (!n) { cast_scaled_f16_kernel<<<1, 32, 0, st>>>(x, x_dtype, 0, reinterpret_cast<unsigned int*>(scale2 + 2), (__half*)y, scale2); return check_launch(__func__); }
+  const int grid = grid_for(n / 4, 2048) > 1184 ? 1184 : grid_for(n / 4, 2048);
+  amax_kernel<<<grid, 256, 0, st>>>(x, x_dtype, n / 4, reinterpret_cast<unsigned int*>(scale2 + 2));
+  cast_scaled_f16_kernel<<<grid, 256, 0, st>>>(x, x_dtype, n / 4, reinterpret_cast<const unsigned int*>(scale2 + 2), (__half*)y, scale2);
+  return check_launch(__func__);
+}
+
+int samk_concat3_f32(const float* a, const float* b, const float* c, float* out, int n, void* stream) {
+  SAMK_REQUIRE(a && b && c && out && n >= 0, "bad argument");
+  if (!n) return SAMK_OK;
+  concat3_kernel<<<(3 * n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a, b, c, out, n);
   return check_launch(__func__);
 }
 

@@ -1,4 +1,5 @@
-// tcgen05 GEMM with fused epilogues: C[M,N] = epi(alpha * A[M,K] * B[N,K]^T), bf16 x bf16 -> fp32.
+// tcgen05 GEMM with fused epilogues: C[M,N] = epi(alpha * A[M,K] * B[N,K]^T), 16-bit operands (IEEE half or
+// bfloat16, the same for A and B) -> fp32 accumulation.
 //
 // Persistent, warp-specialised, one CTA per SM (a CTA pair per 256 x 256 tile for the large shapes, see CL below):
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128B swizzle, kStages-deep mbarrier ring)
@@ -42,11 +43,16 @@ enum : int {
   F_ATOMIC = 1 << 11,     // red.global.add into fp32 out
   F_ALPHA = 1 << 12,      // alpha != 1
   F_VEC = 1 << 13,        // all pointers / pitches vector friendly and N % 8 == 0: no scalar tails
+  // the 16-bit buffers are IEEE half instead of bfloat16 (F_OUT_BF16 / F_PRE_BF16 / F_AUX_BF16 then mean "16-bit")
+  F_OUT_F16 = 1 << 14,
+  F_PRE_F16 = 1 << 15,
+  F_AUX_F16 = 1 << 16,
 };
 constexpr int EPI_DYNAMIC = -1;
 
 struct EpiArgs {
   void* out; long long ldo; float alpha;
+  const float* alpha_dev;   // optional device scalar multiplied into alpha (1 / scale of an f16-scaled gradient operand)
   const float* bias;
   void* pre; long long ldpre;
   const void* aux; long long ldaux;
@@ -69,7 +75,7 @@ struct EpiRow {
 struct EpiIn {       // operands fetched from global memory ahead of the accumulator (kept raw: no use before compute)
   float res[8];    // residual
   float aux[8];    // aux operand (act 2 / 4), fp32 form
-  uint4 auxp;      // aux operand, packed bf16 form (vector path)
+  uint4 auxp;      // aux operand, packed 16-bit form (vector path)
 };
 
 template <int EPI>
@@ -92,7 +98,7 @@ __device__ __forceinline__ void epi_load(const EpiArgs& ep, EpiIn& e, int row, i
       if (full) {
         e.auxp = *reinterpret_cast<const uint4*>(p);
       } else {
-        _Pragma("unroll") for (int i = 0; i < 8; ++i) e.aux[i] = i < cnt ? __bfloat162float(p[i]) : 0.f;
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) e.aux[i] = i < cnt ? ld_16(p + i, (F & F_AUX_F16) != 0) : 0.f;
       }
     } else {
       const float* p = reinterpret_cast<const float*>(ep.aux) + (size_t)row * ep.ldaux + col;
@@ -104,13 +110,13 @@ __device__ __forceinline__ void epi_load(const EpiArgs& ep, EpiIn& e, int row, i
 // w: second output (pre-activation copy, or gelu' when act == 3)
 template <int EPI>
 __device__ __forceinline__ void epi_compute(const EpiArgs& ep, EpiRow& e, const EpiIn& in, float* w, const float* bias8,
-                                            int row, int col, int cnt, int N) {
+                                            int row, int col, int cnt, int N, float alpha) {
   const int F = epi_flags<EPI>(ep);
   const bool full = (F & F_VEC) && cnt == 8;
   float* v = e.v;
   if (F & F_ALPHA) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] *= ep.alpha;
+    for (int i = 0; i < 8; ++i) v[i] *= alpha;
   }
   if (F & F_BIAS) {
 #pragma unroll
@@ -130,10 +136,10 @@ __device__ __forceinline__ void epi_compute(const EpiArgs& ep, EpiRow& e, const 
   } else if (F & (F_MULAUX | F_DGELU)) {
     float x[8];
     if ((F & F_AUX_BF16) && full) {
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&in.auxp);
+      const uint32_t* h = reinterpret_cast<const uint32_t*>(&in.auxp);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(h[j]);
+        const float2 f = unpack_16(h[j], (F & F_AUX_F16) != 0);
         x[2 * j] = f.x; x[2 * j + 1] = f.y;
       }
     } else {
@@ -173,11 +179,12 @@ __device__ __forceinline__ void epi_store(const EpiArgs& ep, const EpiRow& e, co
   if (F & (F_PRE | F_GELU_PAIR)) {
     if (F & F_PRE_BF16) {
       __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.pre) + (size_t)row * ep.ldpre + col;
+      const bool hf = (F & F_PRE_F16) != 0;
       if (full) {
-        *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]),
-                                                  pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
+        *reinterpret_cast<uint4*>(p) = make_uint4(pack_16(w[0], w[1], hf), pack_16(w[2], w[3], hf),
+                                                  pack_16(w[4], w[5], hf), pack_16(w[6], w[7], hf));
       } else {
-        _Pragma("unroll") for (int i = 0; i < 8; ++i) if (i < cnt) p[i] = __float2bfloat16_rn(w[i]);
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) if (i < cnt) st_16(p + i, w[i], hf);
       }
     } else {
       float* p = reinterpret_cast<float*>(ep.pre) + (size_t)row * ep.ldpre + col;
@@ -206,11 +213,12 @@ __device__ __forceinline__ void epi_store(const EpiArgs& ep, const EpiRow& e, co
     }
   } else if (F & F_OUT_BF16) {
     __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldo + col;
+    const bool hf = (F & F_OUT_F16) != 0;
     if (full) {
-      *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                                                pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      *reinterpret_cast<uint4*>(p) = make_uint4(pack_16(v[0], v[1], hf), pack_16(v[2], v[3], hf),
+                                                pack_16(v[4], v[5], hf), pack_16(v[6], v[7], hf));
     } else {
-      _Pragma("unroll") for (int i = 0; i < 8; ++i) if (i < cnt) p[i] = __float2bfloat16_rn(v[i]);
+      _Pragma("unroll") for (int i = 0; i < 8; ++i) if (i < cnt) st_16(p + i, v[i], hf);
     }
   } else {
     float* p = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col;
@@ -246,7 +254,7 @@ __device__ __forceinline__ void epilogue_8(const EpiArgs& ep, const float* acc, 
   for (int i = 0; i < 8; ++i) e.v[i] = acc[i];
   epi_load_bias<EPI_DYNAMIC>(ep, bias8, col, cnt);
   epi_load<EPI_DYNAMIC>(ep, in, row, col, cnt);
-  epi_compute<EPI_DYNAMIC>(ep, e, in, w, bias8, row, col, cnt, N);
+  epi_compute<EPI_DYNAMIC>(ep, e, in, w, bias8, row, col, cnt, N, ep.alpha_dev ? ep.alpha * *ep.alpha_dev : ep.alpha);
   epi_store<EPI_DYNAMIC>(ep, e, w, row, col, cnt);
 }
 
@@ -297,7 +305,7 @@ __device__ __forceinline__ void chunk_prefetch(const EpiArgs& ep, ChunkIn<STAGED
 
 template <int EPI, bool STAGED>
 __device__ __forceinline__ void chunk_finish(const EpiArgs& ep, const ChunkIn<STAGED>& c, uint32_t stage, const uint32_t (&r)[32],
-                                             bool zero, int row0, int col0, int M, int N, int lane) {
+                                             bool zero, int row0, int col0, int M, int N, int lane, float alpha) {
   EpiRow e[4];
   if constexpr (STAGED) {
     const uint32_t srow = stage + lane * 128;
@@ -332,7 +340,7 @@ __device__ __forceinline__ void chunk_finish(const EpiArgs& ep, const ChunkIn<ST
     if (row < M && col < N) {
       float w[8];
       const int cnt = min(8, N - col);
-      epi_compute<EPI>(ep, e[it], c.in[it], w, c.bias[STAGED ? 0 : it], row, col, cnt, N);
+      epi_compute<EPI>(ep, e[it], c.in[it], w, c.bias[STAGED ? 0 : it], row, col, cnt, N, alpha);
       epi_store<EPI>(ep, e[it], w, row, col, cnt);
     }
   }
@@ -358,7 +366,7 @@ template <int BN, int CL = 1> struct GemmCfg {
 template <int BN, int A_MN, int B_MN, int CL, int EPI, bool STAGED>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const EpiArgs ep, int M, int N, int K, int split_k) {
+               const EpiArgs ep, int M, int N, int K, int split_k, uint32_t ab_fmt) {
   using Cfg = GemmCfg<BN, CL>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -455,7 +463,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (CTA pair: the leader CTA only) =====================
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(BM * CL, BN, A_MN, B_MN);
+    // ab_fmt: operand formats (bit 0: A is bf16, bit 1: B is bf16; 0 = IEEE half) -- a kernel argument, so uniform
+    const uint32_t idesc = ptx::make_idesc_16(BM * CL, BN, A_MN, B_MN, ab_fmt & 1u, (ab_fmt >> 1) & 1u);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     if (CL == 1 || cta_rank == 0) {
@@ -512,6 +521,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue =====================
     const int lane_grp = warp & 3;          // TMEM lane quarter this warp may access (warp id % 4)
     const int col_half = (warp - 2) >> 2;   // which half of the tile's columns this warp drains
+    const float alpha = ((epi_flags<EPI>(ep) & F_ALPHA) && ep.alpha_dev) ? ep.alpha * __ldg(ep.alpha_dev) : ep.alpha;
     int acc = 0; uint32_t acc_phase = 0;
     for (int w = work0; w < num_work; w += work_stride) {
       const int split = w % split_k;
@@ -544,7 +554,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               uint32_t r[32];
               ptx::tmem_ld_32x32(taddr + (cbase + i) * 32, r);
               ptx::tmem_ld_wait();
-              chunk_finish<EPI, STAGED>(ep, cin[i & 1], stage, r, !has_k, row0, col0, M, N, lane);
+              chunk_finish<EPI, STAGED>(ep, cin[i & 1], stage, r, !has_k, row0, col0, M, N, lane, alpha);
             }
           }
         } else {
@@ -556,7 +566,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t r[32];
             ptx::tmem_ld_32x32(taddr + (cbase + i) * 32, r);
             ptx::tmem_ld_wait();
-            chunk_finish<EPI, STAGED>(ep, cin[0], stage, r, !has_k, row0, col0, M, N, lane);
+            chunk_finish<EPI, STAGED>(ep, cin[0], stage, r, !has_k, row0, col0, M, N, lane, alpha);
           }
         }
       }
@@ -585,7 +595,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, int a_mn, long long lda,
                                  const __nv_bfloat16* __restrict__ B, int b_mn, long long ldb,
-                                 const EpiArgs ep, int M, int N, int K) {
+                                 const EpiArgs ep, int M, int N, int K, uint32_t ab_fmt) {
+  const bool a_f16 = !(ab_fmt & 1u), b_f16 = !(ab_fmt & 2u);
   // one thread = one row x 32-column chunk, so the epilogue code path is shared
   const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
   const int chunks_per_row = (N + 31) / 32;
@@ -596,9 +607,9 @@ __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, int a_mn, 
   float v[32];
   for (int i = 0; i < 32; ++i) v[i] = 0.f;
   for (int k = 0; k < K; ++k) {
-    float a = __bfloat162float(a_mn ? A[(size_t)k * lda + row] : A[(size_t)row * lda + k]);
+    float a = ld_16(a_mn ? &A[(size_t)k * lda + row] : &A[(size_t)row * lda + k], a_f16);
     for (int i = 0; i < cnt; ++i) {
-      float b = __bfloat162float(b_mn ? B[(size_t)k * ldb + col0 + i] : B[(size_t)(col0 + i) * ldb + k]);
+      float b = ld_16(b_mn ? &B[(size_t)k * ldb + col0 + i] : &B[(size_t)(col0 + i) * ldb + k], b_f16);
       v[i] = fmaf(a, b, v[i]);
     }
   }
@@ -659,7 +670,7 @@ int sm_count() {
 
 template <int BN, int A_MN, int B_MN, int CL, int EPI, bool STAGED>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiArgs& ep, int M, int N, int K, int split_k,
-                     cudaStream_t stream) {
+                     uint32_t ab_fmt, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CL>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CL, EPI, STAGED>;
   static bool attr_set = false;
@@ -688,13 +699,13 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiArgs
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_level() >= 1 ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, M, N, K, split_k);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, M, N, K, split_k, ab_fmt);
   if (e != cudaSuccess) {
     cudaGetLastError();
-    set_error("samk_gemm_bf16: launch failed: %s", cudaGetErrorString(e));
+    set_error("samk_gemm: launch failed: %s", cudaGetErrorString(e));
     return SAMK_ERR_CUDA;
   }
-  return check_launch("samk_gemm_bf16");
+  return check_launch("samk_gemm");
 }
 
 // CTA-pair tiles (cta_group::2): SAMK_GEMM_2CTA=0/1 overrides the default
@@ -708,39 +719,54 @@ static int gemm_2cta() {
 }
 
 // the epilogue combinations of the SA-M4C layers that get a compile-time specialised kernel
-constexpr int M_QKV = F_OUT_BF16 | F_BIAS | F_VEC;                                        // fused q|k|v projection
+// (forward activations are stored as IEEE half, gradients as bfloat16: see ops.py "Precision modes")
+constexpr int M_QKV = F_OUT_BF16 | F_OUT_F16 | F_BIAS | F_VEC;                            // fused q|k|v projection
 constexpr int M_OUTPROJ = F_BIAS | F_DROP | F_RES | F_VEC;                                // W_o / FFN2 forward (train)
-constexpr int M_FFN1 = F_OUT_BF16 | F_BIAS | F_GELU_PAIR | F_PRE_BF16 | F_VEC;           // FFN1 forward (train)
+constexpr int M_FFN1 = F_OUT_BF16 | F_OUT_F16 | F_BIAS | F_GELU_PAIR | F_PRE_BF16 | F_PRE_F16 | F_VEC;   // FFN1 forward (train)
 constexpr int M_BF16 = F_OUT_BF16 | F_VEC;                                                // W_o dgrad
 constexpr int M_F32_BIAS = F_BIAS | F_VEC;                                                // input projections, heads
 constexpr int M_F32_BIAS_RES = F_BIAS | F_RES | F_VEC;                                    // inference W_o / FFN2
-constexpr int M_GELU = F_OUT_BF16 | F_BIAS | F_GELU | F_VEC;                              // inference FFN1
-constexpr int M_MULAUX = F_OUT_BF16 | F_MULAUX | F_AUX_BF16 | F_VEC;                      // FFN2 dgrad * gelu'
+constexpr int M_GELU = F_OUT_BF16 | F_OUT_F16 | F_BIAS | F_GELU | F_VEC;                  // inference FFN1
+constexpr int M_MULAUX = F_OUT_BF16 | F_MULAUX | F_AUX_BF16 | F_AUX_F16 | F_VEC;          // FFN2 dgrad * gelu'
 constexpr int M_F32_RES = F_RES | F_VEC;                                                  // FFN1 / qkv dgrad + skip grad
 constexpr int M_F32 = F_VEC;
-constexpr int M_ATOMIC = F_ATOMIC | F_VEC;                                                // wgrad accumulation
+constexpr int M_ATOMIC = F_ATOMIC | F_ALPHA | F_VEC;                                      // wgrad accumulation (alpha: 1 / gradient scale)
 
 }  // namespace samk
 
 extern "C" int samk_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb, int M,
                               int N, int K, const samk_gemm_epilogue* e, int split_k, int impl, void* stream_) {
+  return samk_gemm_16(A, SAMK_DT_BF16, a_mn, lda, B, SAMK_DT_BF16, b_mn, ldb, M, N, K, e, split_k, impl, stream_);
+}
+
+extern "C" int samk_gemm_16(const void* A, int a_dtype, int a_mn, long long lda, const void* B, int b_dtype, int b_mn,
+                            long long ldb, int M, int N, int K, const samk_gemm_epilogue* e, int split_k, int impl,
+                            void* stream_) {
   using namespace samk;
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!A || !B || !e || !e->out) { set_error("samk_gemm_bf16: null pointer"); return SAMK_ERR_ARG; }
-  if (M < 0 || N < 0 || K < 0) { set_error("samk_gemm_bf16: negative size"); return SAMK_ERR_ARG; }
+  auto is16 = [](int dt) { return dt == SAMK_DT_BF16 || dt == SAMK_DT_F16; };
+  if (!is16(a_dtype) || !is16(b_dtype)) { set_error("samk_gemm_16: operands must be bf16 or f16"); return SAMK_ERR_ARG; }
+  if (a_dtype != b_dtype) {
+    // measured on B200: tcgen05.mma kind::f16 with a_format != b_format raises an illegal-instruction fault
+    set_error("samk_gemm_16: A and B must share one 16-bit format (mixed f16 x bf16 products fault on sm_100a)");
+    return SAMK_ERR_UNSUPPORTED;
+  }
+  const uint32_t ab_fmt = (a_dtype == SAMK_DT_BF16 ? 1u : 0u) | (b_dtype == SAMK_DT_BF16 ? 2u : 0u);
+  if (!A || !B || !e || !e->out) { set_error("samk_gemm: null pointer"); return SAMK_ERR_ARG; }
+  if (M < 0 || N < 0 || K < 0) { set_error("samk_gemm: negative size"); return SAMK_ERR_ARG; }
   if (M == 0 || N == 0) return SAMK_OK;
   if (split_k < 1) split_k = 1;
-  if (split_k > 1 && !e->atomic_add) { set_error("samk_gemm_bf16: split_k>1 needs atomic_add"); return SAMK_ERR_ARG; }
-  if (e->atomic_add && e->out_dtype != SAMK_DT_F32) { set_error("samk_gemm_bf16: atomic_add needs fp32 out"); return SAMK_ERR_ARG; }
+  if (split_k > 1 && !e->atomic_add) { set_error("samk_gemm: split_k>1 needs atomic_add"); return SAMK_ERR_ARG; }
+  if (e->atomic_add && e->out_dtype != SAMK_DT_F32) { set_error("samk_gemm: atomic_add needs fp32 out"); return SAMK_ERR_ARG; }
   if ((lda % 8) || (ldb % 8) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) {
-    set_error("samk_gemm_bf16: operands need 16-byte aligned base and ld %% 8 == 0 (lda=%lld ldb=%lld)", lda, ldb);
+    set_error("samk_gemm: operands need 16-byte aligned base and ld %% 8 == 0 (lda=%lld ldb=%lld)", lda, ldb);
     return SAMK_ERR_ARG;
   }
-  if ((e->act == 2 || e->act == 4) && !e->aux) { set_error("samk_gemm_bf16: act=2/4 needs aux"); return SAMK_ERR_ARG; }
-  if (e->act == 3 && !e->pre) { set_error("samk_gemm_bf16: act=3 needs pre"); return SAMK_ERR_ARG; }
-  if (e->act < 0 || e->act > 4) { set_error("samk_gemm_bf16: unknown act %d", e->act); return SAMK_ERR_ARG; }
+  if ((e->act == 2 || e->act == 4) && !e->aux) { set_error("samk_gemm: act=2/4 needs aux"); return SAMK_ERR_ARG; }
+  if (e->act == 3 && !e->pre) { set_error("samk_gemm: act=3 needs pre"); return SAMK_ERR_ARG; }
+  if (e->act < 0 || e->act > 4) { set_error("samk_gemm: unknown act %d", e->act); return SAMK_ERR_ARG; }
   EpiArgs ep;
-  ep.out = e->out; ep.ldo = e->ldo; ep.alpha = e->alpha; ep.bias = e->bias;
+  ep.out = e->out; ep.ldo = e->ldo; ep.alpha = e->alpha; ep.alpha_dev = e->alpha_dev; ep.bias = e->bias;
   ep.pre = e->pre; ep.ldpre = e->ldpre;
   ep.aux = e->aux; ep.ldaux = e->ldaux;
   ep.drop_thresh = e->drop_p > 0.f ? drop_threshold(e->drop_p) : 0u;
@@ -750,7 +776,7 @@ extern "C" int samk_gemm_bf16(const void* A, int a_mn, long long lda, const void
   ep.part_rows = 0; ep.out1 = ep.out2 = nullptr;
   if (e->part_rows > 0) {
     if (!e->atomic_add || !e->out_part1 || !e->out_part2 || e->part_rows % 32 || M > 3 * e->part_rows) {
-      set_error("samk_gemm_bf16: part_rows needs atomic_add, two more outputs, part_rows %% 32 == 0 and M <= 3*part_rows");
+      set_error("samk_gemm: part_rows needs atomic_add, two more outputs, part_rows %% 32 == 0 and M <= 3*part_rows");
       return SAMK_ERR_ARG;
     }
     ep.part_rows = e->part_rows; ep.out1 = e->out_part1; ep.out2 = e->out_part2;
@@ -761,19 +787,19 @@ extern "C" int samk_gemm_bf16(const void* A, int a_mn, long long lda, const void
                       (!ep.pre || (al16(ep.pre) && ep.ldpre % 8 == 0)) && (!ep.aux || (al16(ep.aux) && ep.ldaux % 8 == 0)) &&
                       (!ep.residual || (al16(ep.residual) && ep.ldres % 4 == 0));
   int flags = 0;
-  if (e->out_dtype == SAMK_DT_BF16) flags |= F_OUT_BF16;
+  if (e->out_dtype != SAMK_DT_F32) flags |= F_OUT_BF16 | (e->out_dtype == SAMK_DT_F16 ? F_OUT_F16 : 0);
   if (ep.bias) flags |= F_BIAS;
   if (ep.drop_thresh) flags |= F_DROP;
   if (ep.residual) flags |= F_RES;
   if (e->act == 3) flags |= F_GELU_PAIR;
   else if (ep.pre) flags |= F_PRE;
-  if (ep.pre && e->pre_dtype == SAMK_DT_BF16) flags |= F_PRE_BF16;
+  if (ep.pre && e->pre_dtype != SAMK_DT_F32) flags |= F_PRE_BF16 | (e->pre_dtype == SAMK_DT_F16 ? F_PRE_F16 : 0);
   if (e->act == 4) flags |= F_MULAUX;
   if (e->act == 2) flags |= F_DGELU;
-  if ((e->act == 2 || e->act == 4) && e->aux_dtype == SAMK_DT_BF16) flags |= F_AUX_BF16;
+  if ((e->act == 2 || e->act == 4) && e->aux_dtype != SAMK_DT_F32) flags |= F_AUX_BF16 | (e->aux_dtype == SAMK_DT_F16 ? F_AUX_F16 : 0);
   if (e->act == 1) flags |= F_GELU;
   if (e->atomic_add) flags |= F_ATOMIC;
-  if (ep.alpha != 1.0f) flags |= F_ALPHA;
+  if (ep.alpha != 1.0f || ep.alpha_dev || e->atomic_add) flags |= F_ALPHA;   // (accumulating launches always: one specialisation)
   if (vec_ok) flags |= F_VEC;
   ep.flags = flags;
   if (K == 0 && !e->atomic_add) split_k = 1;
@@ -781,8 +807,8 @@ extern "C" int samk_gemm_bf16(const void* A, int a_mn, long long lda, const void
   if (impl == 1) {
     long long chunks = (long long)M * ((N + 31) / 32);
     gemm_simt_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, stream>>>(
-        (const __nv_bfloat16*)A, a_mn, lda, (const __nv_bfloat16*)B, b_mn, ldb, ep, M, N, K);
-    return check_launch("samk_gemm_bf16(simt)");
+        (const __nv_bfloat16*)A, a_mn, lda, (const __nv_bfloat16*)B, b_mn, ldb, ep, M, N, K, ab_fmt);
+    return check_launch("samk_gemm(simt)");
   }
 
   // tile width: 256 unless that leaves most of the machine idle
@@ -813,9 +839,9 @@ extern "C" int samk_gemm_bf16(const void* A, int a_mn, long long lda, const void
   // row-per-thread layout for every combination below (tools/gemm_bench.py)
 #define SAMK_SPEC(AM_, BM_, MASK_)                                                                        \
   if (a_mn == AM_ && b_mn == BM_ && flags == (MASK_)) {                                                    \
-    if (pair) return launch_tc<256, AM_, BM_, 2, MASK_, true>(ta, tb, ep, M, N, K, split_k, stream);      \
-    if (bn == 256) return launch_tc<256, AM_, BM_, 1, MASK_, true>(ta, tb, ep, M, N, K, split_k, stream); \
-    return launch_tc<128, AM_, BM_, 1, MASK_, true>(ta, tb, ep, M, N, K, split_k, stream);                \
+    if (pair) return launch_tc<256, AM_, BM_, 2, MASK_, true>(ta, tb, ep, M, N, K, split_k, ab_fmt, stream);      \
+    if (bn == 256) return launch_tc<256, AM_, BM_, 1, MASK_, true>(ta, tb, ep, M, N, K, split_k, ab_fmt, stream); \
+    return launch_tc<128, AM_, BM_, 1, MASK_, true>(ta, tb, ep, M, N, K, split_k, ab_fmt, stream);                \
   }
   SAMK_SPEC(0, 0, M_QKV)
   SAMK_SPEC(0, 0, M_OUTPROJ)
@@ -833,7 +859,7 @@ extern "C" int samk_gemm_bf16(const void* A, int a_mn, long long lda, const void
 #undef SAMK_SPEC
 
   // anything else: runtime-flag epilogue
-#define SAMK_DYN(BN_, AM_, BM_) return launch_tc<BN_, AM_, BM_, 1, EPI_DYNAMIC, false>(ta, tb, ep, M, N, K, split_k, stream)
+#define SAMK_DYN(BN_, AM_, BM_) return launch_tc<BN_, AM_, BM_, 1, EPI_DYNAMIC, false>(ta, tb, ep, M, N, K, split_k, ab_fmt, stream)
   if (bn == 256) {
     if (!a_mn && !b_mn) SAMK_DYN(256, 0, 0);
     if (!a_mn && b_mn) SAMK_DYN(256, 0, 1);

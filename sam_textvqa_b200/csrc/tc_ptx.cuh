@@ -224,6 +224,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with the operand formats spelled out: fmt 0 = F16 (IEEE half), 1 = BF16; A and B may differ (the backward
+// products multiply bf16 gradients with f16 activations / weights)
+constexpr uint32_t kFmtF16 = 0u, kFmtBF16 = 1u;
+__host__ __device__ constexpr uint32_t make_idesc_16(int M, int N, int a_mn_major, int b_mn_major, uint32_t a_fmt, uint32_t b_fmt) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 }  // namespace ptx
 }  // namespace samk

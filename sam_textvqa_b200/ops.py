@@ -5,22 +5,35 @@ Every function here launches hand-written CUDA kernels on the caller's current d
 fallback: CPU tensors are rejected and a missing library raises.
 
 Precision modes (``set_precision`` / env ``SAMK_PRECISION``):
-  "bf16"    activations that feed a contraction are stored in bf16, tcgen05 bf16 MMAs, fp32
-            accumulation / residual stream / LayerNorm / softmax.  The throughput mode.
-  "bf16x3"  activations stay fp32; every contraction runs as a 3-term bf16 split
+  "f16"     the product mode.  Forward activations and weight operands that feed a contraction are IEEE half
+            (11 significant bits), gradients bfloat16 (fp32 exponent range); fp32 accumulation in TMEM, fp32 residual
+            stream / LayerNorm / softmax statistics.  tcgen05 needs both operands of a product in one format (mixed
+            f16 x bf16 faults on sm_100a), so in the backward pass dgrad multiplies bf16 dY with a bf16 weight copy,
+            wgrad multiplies bf16 dY with the bf16 activation copy LayerNorm wrote next to the f16 one -- or, where the
+            saved activation is the big one (GELU output, attention context), an exactly scaled f16 copy of the small
+            dY with the f16 activation -- and attention backward runs in f16 with one exact power-of-two scale per
+            (sample, head).  No global loss scale.  The small projections whose rounding dominates the logit error
+            (OCR pointer network, obj / ocr input encoders, classifier: 2 % of the FLOPs) run as the 3-term split
+            below.  Measured on the c3 golden: logits within 1e-3 of the fp32 reference, argmax identical
+            (error budget per component in DESIGN.md).
+  "bf16x3"  the strict mode.  Activations stay fp32; every contraction runs as a 3-term bf16 split
             (A_hi*B_hi + A_hi*B_lo + A_lo*B_hi, one tcgen05 GEMM over a 3x longer K) and attention
-            runs in exact fp32.  The parity mode: logits within 1e-3 of the fp32 reference.
+            runs in exact fp32: ~2e-5 on the logits.
+(The round-1 "bf16" mode -- bf16 forward operands, 4e-3 on the logits -- is gone: half operands cost the same.)
 """
 import ctypes
 import math
 import os
+import threading
 
 import torch
 
 from . import _lib
-from ._lib import DT_BF16, DT_F32, GemmEpilogue, check, lib, ptr, stream_ptr
+from ._lib import DT_BF16, DT_F16, DT_F32, GemmEpilogue, check, lib, ptr, stream_ptr
 
-_PRECISION = os.environ.get("SAMK_PRECISION", "bf16")
+_PRECISION = os.environ.get("SAMK_PRECISION", "f16")
+if _PRECISION not in ("f16", "bf16x3"):
+    raise ValueError("SAMK_PRECISION must be 'f16' or 'bf16x3'")
 _GEMM_IMPL = int(os.environ.get("SAMK_GEMM_IMPL", "0"))
 _ATTN_IMPL = int(os.environ.get("SAMK_ATTN_IMPL", "0"))
 launch_count = 0  # kernels launched through this module (bench.py reports it)
@@ -31,8 +44,8 @@ attn_profile = None  # bench.py: list collecting (kind, L, start_event, end_even
 
 def set_precision(mode):
     global _PRECISION
-    if mode not in ("bf16", "bf16x3"):
-        raise ValueError("precision must be 'bf16' or 'bf16x3'")
+    if mode not in ("f16", "bf16x3"):
+        raise ValueError("precision must be 'f16' or 'bf16x3'")
     _PRECISION = mode
 
 
@@ -41,15 +54,23 @@ def get_precision():
 
 
 def act_dtype():
-    return torch.bfloat16 if _PRECISION == "bf16" else torch.float32
+    """storage dtype of forward activations that feed a contraction"""
+    return torch.float16 if _PRECISION == "f16" else torch.float32
+
+
+def grad_dtype():
+    """storage dtype of gradients that feed a contraction"""
+    return torch.bfloat16 if _PRECISION == "f16" else torch.float32
+
+
+_DT = {torch.bfloat16: DT_BF16, torch.float32: DT_F32, torch.float16: DT_F16}
 
 
 def _dt(t):
-    if t.dtype == torch.bfloat16:
-        return DT_BF16
-    if t.dtype == torch.float32:
-        return DT_F32
-    raise TypeError("unsupported dtype %s" % t.dtype)
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError("unsupported dtype %s" % t.dtype)
 
 
 def _cuda(*ts):
@@ -87,14 +108,11 @@ def _grads_done(*params):
         grad_ready_hook([p for p in params if p is not None and p.is_leaf])
 
 
-_ln_ws = {}
-
-
 def _ln_partials(dev, cols):
-    key = (dev, cols)
-    if key not in _ln_ws:
-        _ln_ws[key] = torch.empty(int(lib().samk_layernorm_bwd_partials(cols)), dtype=torch.float32, device=dev)
-    return _ln_ws[key]
+    ws = _state(dev).ln_ws
+    if cols not in ws:
+        ws[cols] = torch.empty(int(lib().samk_layernorm_bwd_partials(cols)), dtype=torch.float32, device=dev)
+    return ws[cols]
 
 
 def _ln_bwd(dy, x, gamma, eps, dx, dxd, p, drop, dg, db, dbias, rows, cols):
@@ -106,9 +124,34 @@ def _ln_bwd(dy, x, gamma, eps, dx, dxd, p, drop, dg, db, dbias, rows, cols):
 
 
 # ---- dropout stream ------------------------------------------------------------------------------
+_BASE_SEED = 0x5A17C0DE
+
+
+def _rank_salt():
+    """Data-parallel replicas must not draw the same dropout masks: the stream seed mixes in the process rank
+    (torch.distributed, else the RANK variable torchrun sets) and the device index (nn.DataParallel threads)."""
+    rank = 0
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            rank = dist.get_rank()
+        else:
+            rank = int(os.environ.get("RANK", "0"))
+    except Exception:
+        rank = 0
+    return rank
+
+
 class _Rng(object):
-    def __init__(self):
-        self.seed = 0x5A17C0DE
+    def __init__(self, dev=0):
+        self.dev = int(dev)
+        self.reseed(_BASE_SEED)
+
+    def reseed(self, seed):
+        z = (int(seed) + 0x9E3779B97F4A7C15 * (1 + _rank_salt()) + 0xD1B54A32D192ED03 * self.dev) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        self.seed = z ^ (z >> 31)
         self.offset = 0
 
     def next(self):
@@ -116,12 +159,13 @@ class _Rng(object):
         return self.seed, self.offset
 
 
-_rng = _Rng()
+def _next_drop(dev=None):
+    return _state(dev).rng.next()
 
 
 def manual_seed(seed):
-    _rng.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-    _rng.offset = 0
+    """Re-seed the dropout stream of the current device (rank and device index are mixed in)."""
+    _state().rng.reseed(seed)
 
 
 # ---- operand preparation ---------------------------------------------------------------------------
@@ -129,12 +173,12 @@ def _ceil8(n):
     return (n + 7) // 8 * 8
 
 
-def cast_bf16(x2d):
-    """fp32 [rows, cols] (row stride arbitrary, unit column stride) -> bf16 [rows, ceil8(cols)] buffer."""
+def cast_16(x2d, dtype):
+    """fp32 [rows, cols] (row stride arbitrary, unit column stride) -> half / bf16 [rows, ceil8(cols)] buffer."""
     rows, cols = x2d.shape
     assert x2d.stride(1) == 1 and cols % 4 == 0
-    y = torch.empty(rows, _ceil8(cols), dtype=torch.bfloat16, device=x2d.device)
-    check(lib().samk_cast_bf16(ptr(x2d), x2d.stride(0), ptr(y), y.stride(0), rows, cols, stream_ptr()), "cast_bf16")
+    y = torch.empty(rows, _ceil8(cols), dtype=dtype, device=x2d.device)
+    check(lib().samk_cast_16(ptr(x2d), x2d.stride(0), ptr(y), y.stride(0), _DT[dtype], rows, cols, stream_ptr()), "cast_16")
     _count()
     return y
 
@@ -153,80 +197,162 @@ def _split3(x2d, order, along_rows):
 
 
 class Operand(object):
-    """A GEMM operand ready for the tensor-core kernel: bf16 storage, leading dimension, K multiplier."""
-    __slots__ = ("t", "ld", "kmul")
+    """A GEMM operand ready for the tensor-core kernel: 16-bit storage, its format, leading dimension, K multiplier."""
+    __slots__ = ("t", "ld", "kmul", "dt")
 
     def __init__(self, t, ld, kmul):
-        self.t, self.ld, self.kmul = t, ld, kmul
+        self.t, self.ld, self.kmul, self.dt = t, ld, kmul, _DT[t.dtype]
 
 
-# bf16 operand copies of fp32 activations made during the current forward pass, keyed on the fp32 tensor's
+class _State(object):
+    """Per-device, per-thread mutable state of the operators: dropout stream, operand caches, side stream, LayerNorm
+    workspace.  `nn.DataParallel` (the reference's multi-GPU path, train.py:111-112) runs replicas concurrently in
+    Python threads on different devices; nothing here is shared between them."""
+
+    def __init__(self, dev):
+        self.rng = _Rng(dev)
+        self.act_cache = {}
+        self.weight_cache = {}
+        self.ln_ws = {}
+        self.side_stream = None
+        self.side_open = False
+
+
+_tls = threading.local()
+
+
+def _state(dev=None):
+    if dev is None:
+        dev = torch.cuda.current_device()
+    elif isinstance(dev, torch.device):
+        dev = dev.index if dev.index is not None else torch.cuda.current_device()
+    table = getattr(_tls, "table", None)
+    if table is None:
+        table = _tls.table = {}
+    st = table.get(dev)
+    if st is None:
+        st = table[dev] = _State(dev)
+    return st
+
+
+# 16-bit operand copies of fp32 activations made during the current forward pass, keyed on the fp32 tensor's
 # storage.  The entry keeps the fp32 tensor alive (so the address cannot be recycled under the key) and is
 # dropped at the next forward (`begin_forward`).  Serves the backward pass (wgrad re-reads the layer input) and the
-# next layer (LayerNorm writes the bf16 copy of its output in the same pass, no separate cast kernel).
-_act_cache = {}
-
-
+# next layer (LayerNorm writes the half copy of its output in the same pass, no separate cast kernel).
 def begin_forward():
-    _act_cache.clear()
+    _state().act_cache.clear()
 
 
 def _act_key(x2d):
     return (x2d.data_ptr(), tuple(x2d.shape), x2d.stride(0), x2d._version)
 
 
-def remember_bf16(x2d, y_bf16):
-    if _PRECISION == "bf16":
-        _act_cache[_act_key(x2d)] = (x2d, y_bf16)
+def remember_act(x2d, *copies):
+    """register 16-bit copies (any formats) of the fp32 activation x2d made by the kernel that produced it"""
+    if _PRECISION == "f16":
+        cache = _state(x2d.device).act_cache
+        for y in copies:
+            if y is not None:
+                cache[(_act_key(x2d), y.dtype)] = (x2d, y)
 
 
-def operand(x2d, role, mn_major):
-    """x2d: logical [rows(MN), K] if not mn_major else stored [K, MN].  role 'a' or 'b'."""
+def cached_copy(x2d, dtype):
+    hit = _state(x2d.device).act_cache.get((_act_key(x2d), dtype))
+    return None if hit is None else hit[1]
+
+
+_FMT_DTYPE = {"f16": torch.float16, "bf16": torch.bfloat16}
+
+
+def operand(x2d, role, mn_major, fmt="f16", split=None):
+    """x2d: logical [rows(MN), K] if not mn_major else stored [K, MN].  role 'a' or 'b'.
+    fmt: 16-bit format an fp32 tensor is cast to in the product mode ("f16": forward values, "bf16": gradients and
+    the activation copies weight-gradient products read); a 16-bit tensor is used as it is.
+    split: force (True) / forbid (False) the 3-term bf16 split; None = by precision mode."""
     _cuda(x2d)
-    if x2d.dtype == torch.bfloat16:
-        if _PRECISION != "bf16":
-            raise _lib.SamkError("bf16 activation reached a bf16x3 contraction")
+    if split is None:
+        split = _PRECISION != "f16"
+    if x2d.dtype != torch.float32:
+        if split:
+            raise _lib.SamkError("16-bit activation reached a split (fp32-accurate) contraction")
         assert x2d.stride(1) == 1 and x2d.stride(0) % 8 == 0 and x2d.data_ptr() % 16 == 0
         return Operand(x2d, x2d.stride(0), 1)
-    if _PRECISION == "bf16":
-        hit = _act_cache.get(_act_key(x2d))
-        if hit is not None:
-            return Operand(hit[1], hit[1].stride(0), 1)
-        y = cast_bf16(x2d)
+    if split:
+        y = _split3(x2d, 0 if role == "a" else 1, 1 if mn_major else 0)
+        return Operand(y, y.stride(0), 3)
+    dtype = _FMT_DTYPE[fmt]
+    y = cached_copy(x2d, dtype)
+    if y is None:
+        y = cast_16(x2d, dtype)
         if x2d.shape[0] >= 1024 and x2d.shape[1] % 8 == 0:       # activations worth remembering (wgrad re-reads them)
-            _act_cache[_act_key(x2d)] = (x2d, y)
-        return Operand(y, y.stride(0), 1)
-    y = _split3(x2d, 0 if role == "a" else 1, 1 if mn_major else 0)
-    return Operand(y, y.stride(0), 3)
+            remember_act(x2d, y)
+    return Operand(y, y.stride(0), 1)
 
 
-_weight_cache = {}
+def scaled_f16(x2d):
+    """(Operand over half(x * S), device pointer to 1/S) for a gradient tensor x2d (bf16 or fp32, contiguous): S is the
+    power of two, found on the device, that puts max|x| into [2^11, 2^12).  The consumer passes the pointer as
+    `alpha_dev` of its GEMM.  Used where a gradient meets a big saved f16 activation in a weight-gradient product."""
+    _cuda(x2d)
+    assert x2d.is_contiguous() and x2d.numel() % 4 == 0
+    y = torch.empty(x2d.shape, dtype=torch.float16, device=x2d.device)
+    sc = torch.empty(4, dtype=torch.float32, device=x2d.device)
+    check(lib().samk_cast_scaled_f16(ptr(x2d), _dt(x2d), x2d.numel(), ptr(y), ptr(sc), stream_ptr()), "cast_scaled_f16")
+    _count(2)
+    return Operand(y, y.stride(0), 1), sc[1:2]
 
 
-def weight_operand(params, mn_major):
-    """Cached operand for one weight (or the row-concatenation of several, e.g. fused q|k|v).
+def weight_operand(params, mn_major, split=None, kdim=None, fmt="f16"):
+    """Cached operand for one weight (or the row-concatenation of several, e.g. fused q|k|v); kdim: use the first
+    kdim input columns only (the OCR projection drops its 50 always-zero columns, sa_m4c.py:240-242).
 
-    params: list of [n_i, K] fp32 parameters.  The cache is keyed on the parameters' storage and
-    version counters, so an optimizer step (in-place update) invalidates it."""
-    layout = bool(mn_major) and _PRECISION != "bf16"   # plain bf16 copies serve both majors
-    slot = (tuple(p.data_ptr() for p in params), tuple(tuple(p.shape) + tuple(p.stride()) for p in params), layout)
-    stamp = (tuple(p._version for p in params), _PRECISION)
-    hit = _weight_cache.get(slot)
+    params: list of [n_i, K] fp32 parameters.  The cache entry holds the parameters themselves (their storage cannot
+    be freed and re-allocated under the key) and is stamped with their version counters, so an optimizer step (in-place
+    update) invalidates it; updates that bypass the version counter (`p.data.copy_`, raw-pointer kernels such as
+    optim.FlatAdam) must call `clear_weight_cache()` / `bump_versions`.  Non-leaf tensors (e.g. `nn.DataParallel`
+    replicas, re-broadcast every step into recycled addresses with version 0) are never cached."""
+    if split is None:
+        split = _PRECISION != "f16"
+    cacheable = all(p.is_leaf for p in params)
+    layout = bool(mn_major) and split            # plain 16-bit copies serve both majors
+    slot = (tuple(id(p) for p in params), tuple(tuple(p.shape) + tuple(p.stride()) for p in params), layout, split, kdim,
+            None if split else fmt)
+    stamp = tuple((p._version, p.data_ptr()) for p in params)
+    cache = _state(params[0].device).weight_cache
+    hit = cache.get(slot) if cacheable else None
     if hit is not None and hit[0] == stamp:
         return hit[1]
     with torch.no_grad():
         w = params[0] if len(params) == 1 else torch.cat(list(params), dim=0)
-        op = operand(w.detach(), "b", mn_major)
-    _weight_cache[slot] = (stamp, op)
+        if kdim is not None and kdim != w.shape[1]:
+            w = w[:, :kdim]
+        op = operand(w.detach(), "b", mn_major, fmt=fmt, split=split)
+    if cacheable:
+        cache[slot] = (stamp, op, tuple(params))      # the parameters stay alive with the entry: ids cannot be reused
     return op
 
 
 def clear_weight_cache():
-    _weight_cache.clear()
+    table = getattr(_tls, "table", None)
+    if table:
+        for st in table.values():
+            st.weight_cache.clear()
 
 
 # ---- GEMM -------------------------------------------------------------------------------------------
-def _pick_split_k(M, N, K, sms=148):
+_SMS = {}
+
+
+def sm_count():
+    dev = torch.cuda.current_device()
+    if dev not in _SMS:
+        _SMS[dev] = max(1, int(lib().samk_sm_count()))
+    return _SMS[dev]
+
+
+def _pick_split_k(M, N, K, sms=None):
+    if sms is None:
+        sms = sm_count()
     tiles = ((M + 127) // 128) * ((N + 255) // 256)
     if tiles >= sms or K <= 1024:
         return 1
@@ -235,10 +361,11 @@ def _pick_split_k(M, N, K, sms=148):
 
 
 def gemm(a, a_mn, b, b_mn, M, N, K, out, bias=None, act=0, pre=None, aux=None, drop_p=0.0, drop=None,
-         residual=None, alpha=1.0, accumulate=False, split_k=None, out_parts=None):
-    """out[M,N] = epilogue(alpha * A.B^T).  a, b: Operand.  out: fp32/bf16 2-D view (unit column stride)."""
-    assert a.kmul == b.kmul
+         residual=None, alpha=1.0, accumulate=False, split_k=None, out_parts=None, alpha_dev=None):
+    """out[M,N] = epilogue(alpha * A.B^T).  a, b: Operand.  out: fp32 / half / bf16 2-D view (unit column stride)."""
+    assert a.kmul == b.kmul and a.dt == b.dt, "tcgen05 products need both operands in one format"
     ep = GemmEpilogue()
+    ep.alpha_dev = alpha_dev.data_ptr() if alpha_dev is not None else None
     ep.out = out.data_ptr()
     ep.ldo = out.stride(0)
     ep.out_dtype = _dt(out)
@@ -262,8 +389,8 @@ def gemm(a, a_mn, b, b_mn, M, N, K, out, bias=None, act=0, pre=None, aux=None, d
     if gemm_profile is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    check(lib().samk_gemm_bf16(ptr(a.t), 1 if a_mn else 0, a.ld, ptr(b.t), 1 if b_mn else 0, b.ld, M, N, Kk,
-                               ctypes.byref(ep), split_k, _GEMM_IMPL, stream_ptr()), "gemm")
+    check(lib().samk_gemm_16(ptr(a.t), a.dt, 1 if a_mn else 0, a.ld, ptr(b.t), b.dt, 1 if b_mn else 0, b.ld, M, N, Kk,
+                             ctypes.byref(ep), split_k, _GEMM_IMPL, stream_ptr()), "gemm")
     if gemm_profile is not None:
         ev1.record()
         gemm_profile.append((ev0, ev1, 2.0 * M * N * K, (int(M), int(N), int(K), bool(a_mn), bool(b_mn))))
@@ -282,42 +409,23 @@ def colsum_into(x2d, out):
 # issued on a second stream right behind the kernel that produced their input and joined before the gradients are
 # declared final, so they run beside the tensor-bound dgrad / wgrad GEMMs (a parallel branch of the captured graph;
 # colsum_kernel uses no shared memory so that its blocks fit on an SM whose shared memory a GEMM CTA owns).
-_SIDE_MODE = int(os.environ.get("SAMK_SIDE_BRANCH", "1"))      # 0 off, 1 side kernel enqueued first, 2 GEMM first
-_SIDE_BRANCH = _SIDE_MODE != 0
-_SIDE_DELTA = os.environ.get("SAMK_SIDE_DELTA", "0") != "0"
-_side_streams = {}
-_side_open = set()
-
-
-def fork_point():
-    """Mark the current position of the main stream: a later `side_branch(after=...)` depends on the work issued up to
-    here only, so the main stream's next kernel (a GEMM that wants every SM) is enqueued ahead of the side kernel."""
-    if _SIDE_MODE != 2:
-        return None
-    ev = torch.cuda.Event()
-    ev.record()
-    return ev
+_SIDE_BRANCH = os.environ.get("SAMK_SIDE_BRANCH", "1") != "0"
 
 
 class side_branch(object):
-    def __init__(self, after=None):
-        self._after = after
 
     def __enter__(self):
         self._cm = None
         if not _SIDE_BRANCH:
             return self
-        dev = torch.cuda.current_device()
-        side = _side_streams.get(dev)
-        if side is None:
-            side = _side_streams[dev] = torch.cuda.Stream(device=dev)
-        if self._after is not None:
-            side.wait_event(self._after)
-        else:
-            side.wait_stream(torch.cuda.current_stream())
+        st = _state()
+        if st.side_stream is None:
+            st.side_stream = torch.cuda.Stream(device=torch.cuda.current_device())
+        side = st.side_stream
+        side.wait_stream(torch.cuda.current_stream())
         self._cm = torch.cuda.stream(side)
         self._cm.__enter__()
-        _side_open.add(dev)
+        st.side_open = True
         return self
 
     def __exit__(self, *exc):
@@ -327,24 +435,26 @@ class side_branch(object):
 
 
 def join_side():
-    dev = torch.cuda.current_device()
-    if dev in _side_open:
-        _side_open.discard(dev)
-        torch.cuda.current_stream().wait_stream(_side_streams[dev])
+    st = _state()
+    if st.side_open:
+        st.side_open = False
+        torch.cuda.current_stream().wait_stream(st.side_stream)
 
 
 # ---- simple differentiable ops -----------------------------------------------------------------------
 class LinearFn(torch.autograd.Function):
-    """y = x W^T + b with fp32 output (input projections, pointer-net projections)."""
+    """y = x W^T + b with fp32 output (input projections, pointer-net projections).
+    strict: the forward product runs as the 3-term split in every precision mode (x must then be fp32)."""
 
     @staticmethod
-    def forward(ctx, x2d, weight, bias, kdim):
+    def forward(ctx, x2d, weight, bias, kdim, strict):
         _cuda(x2d, weight)
         M = x2d.shape[0]
         N = weight.shape[0]
         K = kdim
-        x_op = operand(x2d[:, :K] if x2d.shape[1] != K else x2d, "a", False)
-        w_op = weight_operand([weight[:, :K]] if weight.shape[1] != K else [weight], False)
+        split = True if strict else None
+        x_op = operand(x2d[:, :K] if x2d.shape[1] != K else x2d, "a", False, split=split)
+        w_op = weight_operand([weight], False, split=split, kdim=K)
         y = torch.empty(M, N, dtype=torch.float32, device=x2d.device)
         gemm(x_op, False, w_op, False, M, N, K, y, bias=bias)
         ctx.save_for_backward(x2d, weight)
@@ -362,25 +472,25 @@ class LinearFn(torch.autograd.Function):
         dW, db = _gbuf(weight), _gbuf(ctx_bias)
         with side_branch():
             colsum_into(dy, db[0])
-        dy_act = dy if _PRECISION != "bf16" else cast_bf16(dy)[:, :N]
-        dy_k = operand(dy_act, "a", False)          # [M, N] K-major for dgrad
-        dy_mn = operand(dy_act, "a", True)          # stored [tokens, N]: MN-major for wgrad
+        dy_act = dy if _PRECISION != "f16" else cast_16(dy, torch.bfloat16)[:, :N]
+        dy_k = operand(dy_act, "a", False, fmt="bf16")          # [M, N] K-major for dgrad
+        dy_mn = operand(dy_act, "a", True, fmt="bf16")          # stored [tokens, N]: MN-major for wgrad
         xs = x2d[:, :K] if x2d.shape[1] != K else x2d
-        x_mn = operand(xs, "b", True)
+        x_mn = operand(xs, "b", True, fmt="bf16")
         dx = None
         if ctx.x_needs_grad:
             dx = torch.zeros_like(x2d, dtype=torch.float32) if x2d.shape[1] != K else torch.empty(
                 M, K, dtype=torch.float32, device=dy.device)
-            w_op = weight_operand([weight[:, :K]] if weight.shape[1] != K else [weight], True)
+            w_op = weight_operand([weight], True, kdim=K, fmt="bf16")
             gemm(dy_k, False, w_op, True, M, K, N, dx[:, :K])
         gemm(dy_mn, True, x_mn, True, N, K, M, dW[0][:, :K], accumulate=True)
         join_side()
         _grads_done(weight, ctx_bias)
-        return dx, _ret(dW), _ret(db), None
+        return dx, _ret(dW), _ret(db), None, None
 
 
-def linear(x2d, weight, bias, kdim=None):
-    return LinearFn.apply(x2d, weight, bias, weight.shape[1] if kdim is None else kdim)
+def linear(x2d, weight, bias, kdim=None, strict=False):
+    return LinearFn.apply(x2d, weight, bias, weight.shape[1] if kdim is None else kdim, bool(strict))
 
 
 class LayerNormFn(torch.autograd.Function):
@@ -389,7 +499,7 @@ class LayerNormFn(torch.autograd.Function):
         _cuda(x2d, gamma, beta)
         x2d = x2d.contiguous()
         y = torch.empty_like(x2d)
-        check(lib().samk_layernorm_fwd(ptr(x2d), ptr(gamma), ptr(beta), eps, ptr(y), None, 0, x2d.shape[0],
+        check(lib().samk_layernorm_fwd(ptr(x2d), ptr(gamma), ptr(beta), eps, ptr(y), None, 0, None, 0, x2d.shape[0],
                                        x2d.shape[1], stream_ptr()), "layernorm_fwd")
         _count()
         ctx.save_for_backward(x2d, gamma)
@@ -422,7 +532,7 @@ class DropoutAddFn(torch.autograd.Function):
         b = b.contiguous()
         out = torch.empty_like(a)
         ctx.p = p
-        ctx.drop = _rng.next() if p > 0 else (0, 0)
+        ctx.drop = _next_drop() if p > 0 else (0, 0)
         rows, cols = a.numel() // a.shape[-1], a.shape[-1]
         check(lib().samk_dropout_add(ptr(a), ptr(b), ptr(out), None, 0, rows, cols, p, ctx.drop[0], ctx.drop[1],
                                      stream_ptr()), "dropout_add")
@@ -466,7 +576,7 @@ class BertEmbedFn(torch.autograd.Function):
         B, T = ids.shape
         d = word.shape[1]
         out = torch.empty(B * T, d, dtype=torch.float32, device=word.device)
-        ctx.drop = _rng.next() if p > 0 else (0, 0)
+        ctx.drop = _next_drop() if p > 0 else (0, 0)
         ctx.p, ctx.eps = p, eps
         check(lib().samk_bert_embed_fwd(ptr(ids), ptr(word), ptr(pos), ptr(type_), ptr(gamma), ptr(beta), eps,
                                         ptr(out), None, 0, B * T, T, d, p, ctx.drop[0], ctx.drop[1], stream_ptr()),
@@ -500,7 +610,7 @@ class PrevPredFn(torch.autograd.Function):
         V, d = cls_w.shape
         R = ocr_in.shape[1]
         out = torch.empty(B, D, d, dtype=torch.float32, device=cls_w.device)
-        ctx.drop = _rng.next() if p > 0 else (0, 0)
+        ctx.drop = _next_drop() if p > 0 else (0, 0)
         ctx.p, ctx.eps, ctx.dims = p, eps, (B, D, V, R, d)
         ln6 = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in (ag, ab, og, ob, eg, eb)])
         check(lib().samk_prevpred_fwd(ptr(prev), ptr(cls_w), ptr(ocr_in), ptr(pos), ptr(type_), ln6, eps, ptr(out),
@@ -529,14 +639,17 @@ class PrevPredFn(torch.autograd.Function):
 
 # ---- attention ------------------------------------------------------------------------------------------
 def _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, dctx=None, dqkv=None, delta=None,
-                 allow=None, dq_accum=None):
+                 allow=None, dq_accum=None, keep=None):
     B, L, H, T, A, D = dims
     ap = _lib.AttnParams()
     if qkv is not None:
         ap.qkv, ap.ctx, ap.lse = qkv.data_ptr(), ctx_t.data_ptr(), lse.data_ptr()
         ap.dtype = _dt(qkv)
+        ap.grad_dtype = DT_BF16 if qkv.dtype == torch.float16 else DT_F32
     if dctx is not None:
         ap.dctx, ap.dqkv, ap.delta = dctx.data_ptr(), dqkv.data_ptr(), delta.data_ptr()
+        ap.grad_dtype = _dt(dctx)
+    ap.keep_bits = keep.data_ptr() if keep is not None else None
     ap.B, ap.H, ap.head_dim = B, H, 64
     ap.T, ap.A, ap.D = T, A, D
     ap.key_valid = valid.data_ptr()
@@ -552,7 +665,26 @@ def _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop,
 
 
 def uses_tensor_core_attention(dtype):
-    return dtype == torch.bfloat16 and _ATTN_IMPL == 0
+    return dtype == torch.float16 and _ATTN_IMPL == 0
+
+
+def build_attn_keep(dims, p, drop, device):
+    """Dropout keep bits [B, H, L, ceil(L/32)] of one layer's attention probabilities (stream `drop`), shared by the
+    tensor-core forward and backward kernels."""
+    B, L, H, T, A, D = dims
+    keep = torch.empty(B * H * L * ((L + 31) // 32), dtype=torch.int32, device=device)
+    fill_attn_keep(keep, dims, p, drop)
+    return keep
+
+
+def fill_attn_keep(keep, dims, p, drop):
+    B, L, H, T, A, D = dims
+    ap = _lib.AttnParams()
+    ap.B, ap.H, ap.head_dim, ap.T, ap.A, ap.D = B, H, 64, T, A, D
+    ap.drop_p = p
+    ap.drop_seed, ap.drop_offset = drop
+    check(lib().samk_attn_build_keep(ctypes.byref(ap), ptr(keep), stream_ptr()), "attn_build_keep")
+    _count()
 
 
 def build_attn_mask(valid, rel, dims, spatial, quad_mask):
@@ -567,13 +699,16 @@ def build_attn_mask(valid, rel, dims, spatial, quad_mask):
     return allow
 
 
-def attention_fwd(qkv, valid, rel, dims, spatial, quad_mask, p, drop, allow=None, q_begin=0):
+def attention_fwd(qkv, valid, rel, dims, spatial, quad_mask, p, drop, allow=None, q_begin=0, keep=None):
     B, L, H, T, A, D = dims
-    if uses_tensor_core_attention(qkv.dtype) and allow is None:
-        allow = build_attn_mask(valid, rel, dims, spatial, quad_mask)
+    if uses_tensor_core_attention(qkv.dtype):
+        if allow is None:
+            allow = build_attn_mask(valid, rel, dims, spatial, quad_mask)
+        if p > 0 and keep is None:
+            keep = build_attn_keep(dims, p, drop, qkv.device)
     ctx_t = torch.empty(B * L, H * 64, dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty(B, H, L, dtype=torch.float32, device=qkv.device)
-    ap = _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, allow=allow)
+    ap = _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, allow=allow, keep=keep)
     ap.q_begin = int(q_begin)
     if attn_profile is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -581,47 +716,43 @@ def attention_fwd(qkv, valid, rel, dims, spatial, quad_mask, p, drop, allow=None
     check(lib().samk_attn_fwd(ctypes.byref(ap), _ATTN_IMPL, stream_ptr()), "attn_fwd")
     if attn_profile is not None:
         ev1.record()
-        # Q+K+V+O bf16, allow bits, LSE; dense-equivalent 4 L^2 d FLOP
-        mask_b = B * (H if spatial else 1) * L * ((L + 31) // 32) * 4
+        # Q+K+V+O 16-bit, allow bits (+ dropout keep bits), LSE; dense-equivalent 4 L^2 d FLOP
+        mask_b = B * ((H if spatial else 1) + (H if keep is not None else 0)) * L * ((L + 31) // 32) * 4
         attn_profile.append(("fwd", L, ev0, ev1, B * (4 * L * H * 64 * 2 + H * L * 4) + mask_b, 4.0 * B * L * L * H * 64))
     _count()
     return ctx_t, lse
 
 
-def attention_delta(dctx, ctx_t, dims, delta):
-    """delta[b,h,i] = dO_i . O_i for the tensor-core backward, as its own launch (so it can sit on the side branch);
-    `delta` [B, H, L] fp32 is allocated by the caller on the stream that consumes it."""
+def attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, allow=None, keep=None):
+    """dctx [B*L, H*64] (bf16 in the product mode) -> dq|dk|dv [B*L, 3*H*64] in the same dtype."""
     B, L, H, T, A, D = dims
-    check(lib().samk_attn_delta(ptr(dctx), ptr(ctx_t), ptr(delta), B, H, L, stream_ptr()), "attn_delta")
-    _count()
-    return delta
-
-
-def attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, allow=None, delta=None):
-    B, L, H, T, A, D = dims
-    dq_accum = None
-    if uses_tensor_core_attention(qkv.dtype):
+    dq_accum = do16 = inv_scale = None
+    tc = uses_tensor_core_attention(qkv.dtype)
+    if tc:
         if allow is None:
             allow = build_attn_mask(valid, rel, dims, spatial, quad_mask)
+        if p > 0 and keep is None:
+            keep = build_attn_keep(dims, p, drop, qkv.device)
         if L > 256:      # long sequences: key-tile CTAs reduce dQ through an fp32 buffer
             dq_accum = torch.empty(B * L, H * 64, dtype=torch.float32, device=qkv.device)
-    dqkv = torch.empty_like(qkv)
-    delta_ready = delta is not None
-    if delta is None:
-        delta = torch.empty_like(lse)
+        do16 = torch.empty(B * L, H * 64, dtype=torch.float16, device=qkv.device)     # dO in half, one scale per (b, h)
+        inv_scale = torch.empty(B * H, dtype=torch.float32, device=qkv.device)
+    dqkv = torch.empty(qkv.shape, dtype=dctx.dtype, device=qkv.device)
+    delta = torch.empty_like(lse)
     ap = _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, dctx, dqkv, delta,
-                      allow=allow, dq_accum=dq_accum)
-    ap.delta_ready = 1 if delta_ready else 0
+                      allow=allow, dq_accum=dq_accum, keep=keep)
+    if tc:
+        ap.do_f16, ap.do_inv_scale = do16.data_ptr(), inv_scale.data_ptr()
     if attn_profile is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
     check(lib().samk_attn_bwd(ctypes.byref(ap), _ATTN_IMPL, stream_ptr()), "attn_bwd")
     if attn_profile is not None:
         ev1.record()
-        # Q,K,V,O,dO read + dQ,dK,dV written (bf16), allow bits, LSE + delta; 10 L^2 d FLOP
-        mask_b = B * (H if spatial else 1) * L * ((L + 31) // 32) * 4
+        # Q,K,V,O,dO read + dQ,dK,dV written (16-bit), allow (+ keep) bits, LSE + delta; 10 L^2 d FLOP
+        mask_b = B * ((H if spatial else 1) + (H if keep is not None else 0)) * L * ((L + 31) // 32) * 4
         attn_profile.append(("bwd", L, ev0, ev1, B * (8 * L * H * 64 * 2 + 2 * H * L * 4) + mask_b, 10.0 * B * L * L * H * 64))
-    _count((4 if dq_accum is not None else 2) - (1 if delta_ready else 0))   # delta (+ memset) + main kernel (+ dq conversion)
+    _count(4 if dq_accum is not None else 2)   # prep (+ memset) + main kernel (+ dq conversion)
     return dqkv
 
 
@@ -643,13 +774,23 @@ class BertLayerFn(torch.autograd.Function):
         adt = act_dtype()
         M, d, F = B * L, x.shape[-1], iw.shape[0]
         x2 = x.contiguous().view(M, d)
-        drops = [_rng.next() if pp > 0 else (0, 0) for pp in (p_attn, p_hid, p_hid)]
+        drops = [_next_drop() if pp > 0 else (0, 0) for pp in (p_attn, p_hid, p_hid)]
+        want_bf = adt == torch.float16 and any(ctx.needs_input_grad)    # bf16 copies for the weight-gradient products
+        x_bf = cached_copy(x2, torch.bfloat16) if want_bf else None     # (written by the LayerNorm that produced x)
 
         x_op = operand(x2, "a", False)
         wqkv = weight_operand([qw, kw, vw], False)
-        bqkv = torch.cat([qb, kb, vb]).detach()
+        bqkv = _bias3(qb, kb, vb)
         qkv = torch.empty(M, 3 * d, dtype=adt, device=dev)
+        keep = None
+        if uses_tensor_core_attention(adt) and p_attn > 0:
+            # the dropout keep bits of this layer's attention are drawn beside the tensor-bound q|k|v projection
+            keep = torch.empty(B * H * L * ((L + 31) // 32), dtype=torch.int32, device=dev)
+            with side_branch():
+                fill_attn_keep(keep, dims, p_attn, drops[0])
         gemm(x_op, False, wqkv, False, M, 3 * d, d, qkv, bias=bqkv)
+        if keep is not None:
+            join_side()
         allow = None
         if uses_tensor_core_attention(adt):
             mkey = (bool(spatial), quad_mask if spatial else 0, rel.data_ptr() if (spatial and rel is not None) else 0, dims)
@@ -658,14 +799,15 @@ class BertLayerFn(torch.autograd.Function):
                 allow = build_attn_mask(valid, rel, dims, spatial, quad_mask)
                 if mask_cache is not None:
                     mask_cache[mkey] = allow
-        ctx_t, lse = attention_fwd(qkv, valid, rel, dims, spatial, quad_mask, p_attn, drops[0], allow)
+        ctx_t, lse = attention_fwd(qkv, valid, rel, dims, spatial, quad_mask, p_attn, drops[0], allow, keep=keep)
 
         y1 = torch.empty(M, d, dtype=torch.float32, device=dev)
         gemm(operand(ctx_t, "a", False), False, weight_operand([ow], False), False, M, d, d, y1, bias=ob,
              drop_p=p_hid, drop=drops[1], residual=x2)
         a = torch.empty(M, d, dtype=torch.float32, device=dev)
         a_act = torch.empty(M, d, dtype=adt, device=dev) if adt != torch.float32 else None
-        check(lib().samk_layernorm_fwd(ptr(y1), ptr(g1), ptr(b1), eps, ptr(a), ptr(a_act), DT_BF16, M, d,
+        a_bf = torch.empty(M, d, dtype=torch.bfloat16, device=dev) if want_bf else None
+        check(lib().samk_layernorm_fwd(ptr(y1), ptr(g1), ptr(b1), eps, ptr(a), ptr(a_act), _DT[adt], ptr(a_bf), DT_BF16, M, d,
                                        stream_ptr()), "ln1")
         _count()
         a_in = a_act if a_act is not None else a
@@ -677,95 +819,86 @@ class BertLayerFn(torch.autograd.Function):
              drop=drops[2], residual=a)
         out = torch.empty(M, d, dtype=torch.float32, device=dev)
         out_act = torch.empty(M, d, dtype=adt, device=dev) if adt != torch.float32 else None
-        check(lib().samk_layernorm_fwd(ptr(y2), ptr(g2), ptr(b2), eps, ptr(out), ptr(out_act), DT_BF16, M, d, stream_ptr()),
-              "ln2")
+        out_bf = torch.empty(M, d, dtype=torch.bfloat16, device=dev) if want_bf else None
+        check(lib().samk_layernorm_fwd(ptr(y2), ptr(g2), ptr(b2), eps, ptr(out), ptr(out_act), _DT[adt], ptr(out_bf), DT_BF16,
+                                       M, d, stream_ptr()), "ln2")
         _count()
         if out_act is not None:
-            remember_bf16(out, out_act)          # the next layer's q|k|v projection and its wgrad read this copy
+            remember_act(out, out_act, out_bf)   # the next layer's q|k|v projection (half) and its wgrad (bf16) read these
 
         ctx.cfg, ctx.drops = cfg[:6], drops
-        ctx.save_for_backward(x2, valid, rel, qkv, ctx_t, lse, y1, a_in, h, g, y2, allow, *P)
+        ctx.save_for_backward(x2, valid, rel, qkv, ctx_t, lse, y1, a_in, h, g, y2, allow, keep, x_bf, a_bf, *P)
         return out.view(B, L, d)
 
     @staticmethod
     def backward(ctx, dout):
         (dims, spatial, quad_mask, p_attn, p_hid, eps) = ctx.cfg
         B, L, H, T, A, D = dims
-        x2, valid, rel, qkv, ctx_t, lse, y1, a_in, h, g, y2, allow = ctx.saved_tensors[:12]
-        P = ctx.saved_tensors[12:]
+        x2, valid, rel, qkv, ctx_t, lse, y1, a_in, h, g, y2, allow, keep, x_bf, a_bf = ctx.saved_tensors[:15]
+        P = ctx.saved_tensors[15:]
         qw, qb, kw, kb, vw, vb, ow, ob, g1, b1, iw, ib, o2w, o2b, g2, b2 = P
         G = [_gbuf(p) for p in P]            # same order as P
         (Gqw, Gqb, Gkw, Gkb, Gvw, Gvb, Gow, Gob, Gg1, Gb1, Giw, Gib, Go2w, Go2b, Gg2, Gb2) = [x[0] for x in G]
         dev = dout.device
-        adt = act_dtype()
+        adt, gdt = act_dtype(), grad_dtype()
         M, d, F = B * L, x2.shape[1], iw.shape[0]
         dout = dout.contiguous().view(M, d)
 
+        # Product mode: dY tensors are bf16.  dgrad = bf16 dY x bf16 weight copy; wgrad = bf16 dY x bf16 activation copy
+        # (layer input, LN1 output: written by the LayerNorms) or, for the big saved activations that exist in half only
+        # (GELU output, attention context), half(dY * S) x half activation with alpha = 1/S from the device.
+        half = adt == torch.float16
+        wfmt = "bf16"
         # ---- LN2 backward (+ dropout mask of the FFN output, + b_2 gradient)
         dy2 = torch.empty(M, d, dtype=torch.float32, device=dev)      # grad wrt (dropout(dense)+a)
-        dY2 = torch.empty(M, d, dtype=adt, device=dev)                 # grad wrt dense output
+        dY2 = torch.empty(M, d, dtype=gdt, device=dev)                 # grad wrt dense output
         _ln_bwd(dout, y2, g2, eps, dy2, dY2, p_hid, ctx.drops[2], Gg2, Gb2, Go2b, M, d)
         # ---- FFN2: dgrad (fused with the stored GELU') and wgrad
-        dh = torch.empty(M, F, dtype=adt, device=dev)
-        gemm(operand(dY2, "a", False), False, weight_operand([o2w], True), True, M, F, d, dh, act=4, aux=h)
-        dh_ready = fork_point()
-        if dh_ready is None:
-            with side_branch():                   # b_1 gradient beside the GEMMs that follow
-                colsum_into(dh, Gib)
-        gemm(operand(dY2, "a", True), True, operand(g, "b", True), True, d, F, M, Go2w, accumulate=True)
-        if dh_ready is not None:
-            with side_branch(dh_ready):
-                colsum_into(dh, Gib)
+        dh = torch.empty(M, F, dtype=gdt, device=dev)
+        gemm(operand(dY2, "a", False, fmt=wfmt), False, weight_operand([o2w], True, fmt=wfmt), True, M, F, d, dh, act=4, aux=h)
+        with side_branch():                       # b_1 gradient beside the GEMMs that follow
+            colsum_into(dh, Gib)
+        if half:
+            dY2h, inv2 = scaled_f16(dY2)
+            gemm(dY2h, True, operand(g, "b", True), True, d, F, M, Go2w, accumulate=True, alpha_dev=inv2)
+        else:
+            gemm(operand(dY2, "a", True), True, operand(g, "b", True), True, d, F, M, Go2w, accumulate=True)
         # ---- FFN1
         da = torch.empty(M, d, dtype=torch.float32, device=dev)
-        gemm(operand(dh, "a", False), False, weight_operand([iw], True), True, M, d, F, da, residual=dy2)
-        gemm(operand(dh, "a", True), True, operand(a_in, "b", True), True, F, d, M, Giw, accumulate=True)
+        gemm(operand(dh, "a", False, fmt=wfmt), False, weight_operand([iw], True, fmt=wfmt), True, M, d, F, da, residual=dy2)
+        a_w = a_bf if half else a_in
+        gemm(operand(dh, "a", True, fmt=wfmt), True, operand(a_w, "b", True), True, F, d, M, Giw, accumulate=True)
         # ---- LN1 backward (+ dropout mask of the attention output dense, + b_o gradient)
         dy1 = torch.empty(M, d, dtype=torch.float32, device=dev)
-        dY1 = torch.empty(M, d, dtype=adt, device=dev)
+        dY1 = torch.empty(M, d, dtype=gdt, device=dev)
         _ln_bwd(da, y1, g1, eps, dy1, dY1, p_hid, ctx.drops[1], Gg1, Gb1, Gob, M, d)
         # ---- attention output dense
-        dctx = torch.empty(M, d, dtype=adt, device=dev)
-        gemm(operand(dY1, "a", False), False, weight_operand([ow], True), True, M, d, d, dctx)
-        delta = None
-        side_delta = _SIDE_BRANCH and _SIDE_DELTA and uses_tensor_core_attention(adt)
-        if side_delta:                            # dO . O row sums beside the out-projection wgrad
-            delta = torch.empty(B, H, L, dtype=torch.float32, device=dev)
-            dctx_ready = fork_point()
-            if dctx_ready is None:
-                with side_branch():
-                    attention_delta(dctx, ctx_t, dims, delta)
-        gemm(operand(dY1, "a", True), True, operand(ctx_t, "b", True), True, d, d, M, Gow, accumulate=True)
-        if side_delta:
-            if dctx_ready is not None:
-                with side_branch(dctx_ready):
-                    attention_delta(dctx, ctx_t, dims, delta)
-            join_side()
+        dctx = torch.empty(M, d, dtype=gdt, device=dev)
+        gemm(operand(dY1, "a", False, fmt=wfmt), False, weight_operand([ow], True, fmt=wfmt), True, M, d, d, dctx)
+        if half:
+            dY1h, inv1 = scaled_f16(dY1)
+            gemm(dY1h, True, operand(ctx_t, "b", True), True, d, d, M, Gow, accumulate=True, alpha_dev=inv1)
+        else:
+            gemm(operand(dY1, "a", True), True, operand(ctx_t, "b", True), True, d, d, M, Gow, accumulate=True)
         # ---- attention core
         dqkv = attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p_attn, ctx.drops[0], allow,
-                             delta=delta)
+                             keep=keep)
         # ---- fused q|k|v projection: one dgrad, three wgrads (separate parameter gradients)
-        def qkv_bias_grads():
+        with side_branch():                       # q, k, v bias gradients beside the dgrad / wgrad below
             check(lib().samk_colsum3(ptr(dqkv), _dt(dqkv), dqkv.stride(0), M, d, ptr(Gqb), ptr(Gkb), ptr(Gvb),
                                      stream_ptr()), "colsum3")
             _count()
-        dqkv_ready = fork_point()
-        if dqkv_ready is None:
-            with side_branch():                   # q, k, v bias gradients beside the dgrad / wgrad below
-                qkv_bias_grads()
         dx = torch.empty(M, d, dtype=torch.float32, device=dev)
-        gemm(operand(dqkv, "a", False), False, weight_operand([qw, kw, vw], True), True, M, d, 3 * d, dx, residual=dy1)
-        if dqkv_ready is not None:
-            with side_branch(dqkv_ready):
-                qkv_bias_grads()
-        x_mn = operand(x2, "b", True)
+        gemm(operand(dqkv, "a", False, fmt=wfmt), False, weight_operand([qw, kw, vw], True, fmt=wfmt), True, M, d, 3 * d, dx,
+             residual=dy1)
+        x_mn = operand(x_bf if x_bf is not None else x2, "b", True, fmt=wfmt)
         if Gqw.stride(0) == Gkw.stride(0) == Gvw.stride(0) and d % 32 == 0:
             # the three weight gradients in one launch: M = 3d output rows routed to three destinations
-            gemm(operand(dqkv, "a", True), True, x_mn, True, 3 * d, d, M, Gqw, accumulate=True, out_parts=(d, Gkw, Gvw))
+            gemm(operand(dqkv, "a", True, fmt=wfmt), True, x_mn, True, 3 * d, d, M, Gqw, accumulate=True, out_parts=(d, Gkw, Gvw))
         else:
             for part, Gw in enumerate((Gqw, Gkw, Gvw)):
                 sl = dqkv[:, part * d:(part + 1) * d]
-                gemm(operand(sl, "a", True), True, x_mn, True, d, d, M, Gw, accumulate=True)
+                gemm(operand(sl, "a", True, fmt=wfmt), True, x_mn, True, d, d, M, Gw, accumulate=True)
         join_side()
         _grads_done(*P)
         return (dx.view(B, L, d), None, None, None) + tuple(_ret(x) for x in G)
@@ -785,7 +918,7 @@ def bert_layer_infer(x2, valid, rel, dims, spatial, quad_mask, eps, P, allow, ca
     d, F = x2.shape[1], iw.shape[0]
     rows = x2.shape[0]
     wqkv = weight_operand([qw, kw, vw], False)
-    bqkv = torch.cat([qb, kb, vb]).detach()
+    bqkv = _bias3(qb, kb, vb)
     qkv_rows = torch.empty(rows, 3 * d, dtype=adt, device=dev)
     gemm(operand(x2, "a", False), False, wqkv, False, rows, 3 * d, d, qkv_rows, bias=bqkv)
     if cache is None:
@@ -802,7 +935,7 @@ def bert_layer_infer(x2, valid, rel, dims, spatial, quad_mask, eps, P, allow, ca
     gemm(operand(ctx_rows, "a", False), False, weight_operand([ow], False), False, rows, d, d, y1, bias=ob, residual=x2)
     a = torch.empty(rows, d, dtype=torch.float32, device=dev)
     a_act = torch.empty(rows, d, dtype=adt, device=dev) if adt != torch.float32 else None
-    check(lib().samk_layernorm_fwd(ptr(y1), ptr(g1), ptr(b1), eps, ptr(a), ptr(a_act), DT_BF16, rows, d,
+    check(lib().samk_layernorm_fwd(ptr(y1), ptr(g1), ptr(b1), eps, ptr(a), ptr(a_act), _DT[adt], None, 0, rows, d,
                                    stream_ptr()), "ln1")
     _count()
     g = torch.empty(rows, F, dtype=adt, device=dev)
@@ -811,7 +944,7 @@ def bert_layer_infer(x2, valid, rel, dims, spatial, quad_mask, eps, P, allow, ca
     y2 = torch.empty(rows, d, dtype=torch.float32, device=dev)
     gemm(operand(g, "a", False), False, weight_operand([o2w], False), False, rows, d, F, y2, bias=o2b, residual=a)
     out = torch.empty(rows, d, dtype=torch.float32, device=dev)
-    check(lib().samk_layernorm_fwd(ptr(y2), ptr(g2), ptr(b2), eps, ptr(out), None, 0, rows, d, stream_ptr()), "ln2")
+    check(lib().samk_layernorm_fwd(ptr(y2), ptr(g2), ptr(b2), eps, ptr(out), None, 0, None, 0, rows, d, stream_ptr()), "ln2")
     _count()
     return out, cache
 
@@ -830,14 +963,16 @@ class OutputFn(torch.autograd.Function):
         dev = dec.device
         dec2 = dec.contiguous().view(B * D, d)
         ocr2 = ocr.contiguous().view(B * R, d)
-        ocr_mask = ocr_mask.contiguous()
+        ocr_mask = ocr_mask.long().contiguous()      # any mask dtype (the reference multiplies it as a float, sa_m4c.py:879)
         scores = torch.empty(B * D, V + R, dtype=torch.float32, device=dev)
-        dec_op = operand(dec2, "a", False)
-        gemm(dec_op, False, weight_operand([cw], False), False, B * D, V, d, scores[:, :V], bias=cb)
+        # the vocabulary and pointer projections run as 3-term splits in every precision mode: they are 0.3 % of the
+        # FLOPs and their operand rounding is the largest single term of the logit error (DESIGN.md error budget)
+        dec_op = operand(dec2, "a", False, split=True)
+        gemm(dec_op, False, weight_operand([cw], False, split=True), False, B * D, V, d, scores[:, :V], bias=cb)
         q = torch.empty(B * D, dq, dtype=torch.float32, device=dev)
         k = torch.empty(B * R, dq, dtype=torch.float32, device=dev)
-        gemm(dec_op, False, weight_operand([qw], False), False, B * D, dq, d, q, bias=qb)
-        gemm(operand(ocr2, "a", False), False, weight_operand([kw], False), False, B * R, dq, d, k, bias=kb)
+        gemm(dec_op, False, weight_operand([qw], False, split=True), False, B * D, dq, d, q, bias=qb)
+        gemm(operand(ocr2, "a", False, split=True), False, weight_operand([kw], False, split=True), False, B * R, dq, d, k, bias=kb)
         check(lib().samk_ptr_scores_fwd(ptr(q), ptr(k), ptr(ocr_mask), ptr(scores), V + R, V, B, D, R, dq,
                                         stream_ptr()), "ptr_scores_fwd")
         _count()
@@ -861,25 +996,25 @@ class OutputFn(torch.autograd.Function):
                                         stream_ptr()), "ptr_scores_bwd")
         _count()
         dsv = ds[:, :V]
-        if _PRECISION == "bf16":
-            dsv = cast_bf16(dsv)[:, :V]
-            dq_a, dk_a = cast_bf16(dq_), cast_bf16(dk_)
+        if _PRECISION == "f16":
+            dsv = cast_16(dsv, torch.bfloat16)[:, :V]
+            dq_a, dk_a = cast_16(dq_, torch.bfloat16), cast_16(dk_, torch.bfloat16)
         else:
             dq_a, dk_a = dq_, dk_
-        dec_mn, ocr_mn = operand(dec2, "b", True), operand(ocr2, "b", True)
+        dec_mn, ocr_mn = operand(dec2, "b", True, fmt="bf16"), operand(ocr2, "b", True, fmt="bf16")
         # classifier
         ddec = torch.empty(B * D, d, dtype=torch.float32, device=dev)
-        gemm(operand(dsv, "a", False), False, weight_operand([cw], True), True, B * D, d, V, ddec)
-        gemm(operand(dsv, "a", True), True, dec_mn, True, V, d, B * D, Gcw, accumulate=True)
+        gemm(operand(dsv, "a", False, fmt="bf16"), False, weight_operand([cw], True, fmt="bf16"), True, B * D, d, V, ddec)
+        gemm(operand(dsv, "a", True, fmt="bf16"), True, dec_mn, True, V, d, B * D, Gcw, accumulate=True)
         colsum_into(ds[:, :V], Gcb)
         # pointer query / key projections
         ddec2 = torch.empty(B * D, d, dtype=torch.float32, device=dev)
-        gemm(operand(dq_a, "a", False), False, weight_operand([qw], True), True, B * D, d, dq, ddec2, residual=ddec)
-        gemm(operand(dq_a, "a", True), True, dec_mn, True, dq, d, B * D, Gqw, accumulate=True)
+        gemm(operand(dq_a, "a", False, fmt="bf16"), False, weight_operand([qw], True, fmt="bf16"), True, B * D, d, dq, ddec2, residual=ddec)
+        gemm(operand(dq_a, "a", True, fmt="bf16"), True, dec_mn, True, dq, d, B * D, Gqw, accumulate=True)
         colsum_into(dq_, Gqb)
         docr = torch.empty(B * R, d, dtype=torch.float32, device=dev)
-        gemm(operand(dk_a, "a", False), False, weight_operand([kw], True), True, B * R, d, dq, docr)
-        gemm(operand(dk_a, "a", True), True, ocr_mn, True, dq, d, B * R, Gkw, accumulate=True)
+        gemm(operand(dk_a, "a", False, fmt="bf16"), False, weight_operand([kw], True, fmt="bf16"), True, B * R, d, dq, docr)
+        gemm(operand(dk_a, "a", True, fmt="bf16"), True, ocr_mn, True, dq, d, B * R, Gkw, accumulate=True)
         colsum_into(dk_, Gkb)
         _grads_done(cw, cb, qw, qb, kw, kb)
         return (ddec2.view(B, D, d), docr.view(B, R, d), None) + tuple(_ret(x) for x in G)
@@ -891,8 +1026,8 @@ class BceLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, scores, targets, loss_mask):
         _cuda(scores, targets, loss_mask)
-        scores = scores.contiguous()
-        targets = targets.contiguous()
+        scores = scores.float().contiguous()
+        targets = targets.float().contiguous()
         loss_mask = loss_mask.contiguous().float()
         rows, ncls = scores.numel() // scores.shape[-1], scores.shape[-1]
         loss = torch.empty(2, dtype=torch.float32, device=scores.device)

@@ -530,8 +530,10 @@ class SAM4C(nn.Module):
     def _encode(self, feat_buf, bbox, lin_feat, lin_bbox, ln_feat, ln_bbox, kdim, drop_p):
         B, N = bbox.shape[0], bbox.shape[1]
         d = self.mmt_config.hidden_size
-        f = ops.layer_norm(ops.linear(feat_buf, lin_feat.weight, lin_feat.bias, kdim), ln_feat.weight, ln_feat.bias,
-                           ln_feat.variance_epsilon)
+        # strict: the 2048 / 2952-long feature projections run as 3-term splits in every precision mode (0.5 GFLOP per
+        # sample of 52; their operand rounding would otherwise be ~1.5e-4 of the 1e-3 logit budget)
+        f = ops.layer_norm(ops.linear(feat_buf, lin_feat.weight, lin_feat.bias, kdim, strict=True), ln_feat.weight,
+                           ln_feat.bias, ln_feat.variance_epsilon)
         bb = bbox.reshape(B * N, bbox.shape[-1])[:, :4]                    # remove bbox-area (sa_m4c.py:214,252)
         g = ops.layer_norm(ops.linear(bb, lin_bbox.weight, lin_bbox.bias, 4), ln_bbox.weight, ln_bbox.bias,
                            ln_bbox.variance_epsilon)
@@ -541,7 +543,7 @@ class SAM4C(nn.Module):
     def _forward_obj_encoding(self, batch_dict):
         feats = batch_dict["pad_obj_features"].float()
         B, O, dfeat = feats.shape
-        buf = torch.empty(B * O, dfeat, dtype=ops.act_dtype(), device=feats.device)
+        buf = torch.empty(B * O, dfeat, dtype=torch.float32, device=feats.device)
         ops.l2norm_into(feats, buf, 0, self.normalize)
         batch_dict["obj_mmt_in"] = self._encode(
             buf, batch_dict["pad_obj_bboxes"].float(), self.linear_obj_feat_to_mmt_in, self.linear_obj_bbox_to_mmt_in,
@@ -561,7 +563,7 @@ class SAM4C(nn.Module):
         if kdim + 50 != self.linear_ocr_feat_to_mmt_in.weight.shape[1]:
             raise RuntimeError("ocr_feature_size %d does not match the concatenated OCR features (%d + 50)"
                                % (self.linear_ocr_feat_to_mmt_in.weight.shape[1], kdim))
-        buf = torch.empty(B * R, kdim, dtype=ops.act_dtype(), device=fc6.device)
+        buf = torch.empty(B * R, kdim, dtype=torch.float32, device=fc6.device)
         off = 0
         for p in parts:
             ops.l2norm_into(p, buf, off, self.normalize)

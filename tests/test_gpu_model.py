@@ -1,6 +1,8 @@
 """GPU parity of the drop-in SAM4C against the goldens produced by the UNMODIFIED reference and
-against the CPU oracle on fresh inputs.  Tolerances: bf16x3 (parity mode) logits within 1e-3
-relative (north star), measured ~2e-5; bf16 (throughput mode) reported and bounded at 2e-2."""
+against the CPU oracle on fresh inputs.  Tolerance on the logits: 1e-3 relative with identical argmax (north star)
+in BOTH precision modes -- "f16" (the product / benchmarked mode: half forward operands, bf16 gradient operands;
+measured ~5e-4) and "bf16x3" (strict: fp32-accurate splits, measured ~2e-5).  Gradients: 1e-3 strict, 3e-2 in the
+product mode (bf16 rounding of the gradient operands)."""
 import numpy as np
 import pytest
 import torch
@@ -33,7 +35,7 @@ def golden():
     return g, mmt, tb, state, _model(mmt, tb, state)
 
 
-@pytest.mark.parametrize("precision,tol_logits,tol_grads", [("bf16x3", 1e-3, 1e-3), ("bf16", 2e-2, 5e-2)])
+@pytest.mark.parametrize("precision,tol_logits,tol_grads", [("bf16x3", 1e-3, 1e-3), ("f16", 1e-3, 3e-2)])
 def test_teacher_forced_logits_loss_grads_vs_reference_golden(golden, precision, tol_logits, tol_grads):
     from sam_textvqa_b200 import ops
     g, mmt, tb, state, model = golden
@@ -50,11 +52,11 @@ def test_teacher_forced_logits_loss_grads_vs_reference_golden(golden, precision,
         assert (scores.detach().cpu()[~live] < -9000).all()                 # padded OCR slots: raw - 10000
         assert torch.equal(scores.argmax(-1).cpu(), ref.argmax(-1))
         for key in ("obj_mmt_in", "ocr_mmt_in", "text_bert_emb", "mmt_seq_output"):
-            assert rel_err(batch[key].detach().cpu(), g["tf/" + key]) < tol_logits * 2, key
+            assert rel_err(batch[key].detach().cpu(), g["tf/" + key]) < 2e-3, key
         for key in ("mmt_txt_output", "mmt_ocr_output", "mmt_dec_output", "scores"):
             assert key in batch
         loss = ops.bce_with_mask_loss(scores, batch["targets"], batch["train_loss_mask"])
-        assert abs(loss.item() - float(g["tf/loss"])) < tol_logits * float(g["tf/loss"])
+        assert abs(loss.item() - float(g["tf/loss"])) < 1e-3 * float(g["tf/loss"])
         loss.backward()
         grads = dict((n, p.grad) for n, p in model.named_parameters())
         for k in g.files:
@@ -66,7 +68,7 @@ def test_teacher_forced_logits_loss_grads_vs_reference_golden(golden, precision,
         total = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in model.parameters())).item()
         assert abs(total - float(g["grad_norm_total"])) < tol_grads * float(g["grad_norm_total"])
     finally:
-        ops.set_precision("bf16")
+        ops.set_precision("f16")
 
 
 def test_greedy_decoding_tokens_identical_to_reference(golden):
@@ -85,7 +87,7 @@ def test_greedy_decoding_tokens_identical_to_reference(golden):
         assert rel_err(scores.cpu(), ref, ref > -5000) < 1e-3
         assert not torch.equal(batch["train_prev_inds"].cpu(), prev_in)      # eval overwrites train_prev_inds
     finally:
-        ops.set_precision("bf16")
+        ops.set_precision("f16")
 
 
 def test_full_c3_stack_vs_oracle_on_fresh_batch_with_cpu_resident_masks():
@@ -100,17 +102,22 @@ def test_full_c3_stack_vs_oracle_on_fresh_batch_with_cpu_resident_masks():
     batch = synth.make_batch(3, V=V, seed=5, contexts=(1, 3), graph_fn=graph_fn)
     ref_types = np.stack([graph_oracle.build_graph(b)["1"] for b in batch["boxes"].numpy()])
     assert np.array_equal(batch["spatial_types"].numpy(), ref_types)
-    ops.set_precision("bf16x3")
-    ops.clear_weight_cache()
+    ref, _, _ = sam4c_oracle.forward(state, batch, mmt, tb, train=True)
+    live = ref > -5000
+    gold = torch.from_numpy(load_golden("sam4c_c3.npz")["tf/scores"])     # the unmodified reference on this very batch
+    assert rel_err(ref, gold, live) < 5e-6
     try:
-        bd = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
-        scores = model(bd)["textvqa_scores"]
-        ref, _, _ = sam4c_oracle.forward(state, batch, mmt, tb, train=True)
-        live = ref > -5000
-        assert rel_err(scores.detach().cpu(), ref, live) < 1e-3
-        assert torch.equal(scores.argmax(-1).cpu(), ref.argmax(-1))
+        for prec in ("bf16x3", "f16"):
+            ops.set_precision(prec)
+            ops.clear_weight_cache()
+            bd = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+            scores = model(bd)["textvqa_scores"]
+            err = rel_err(scores.detach().cpu(), gold, live)
+            print("c3 stack [%s]: logits rel err vs reference golden %.3e" % (prec, err))
+            assert err < 1e-3, prec
+            assert torch.equal(scores.argmax(-1).cpu(), gold.argmax(-1)), prec
     finally:
-        ops.set_precision("bf16")
+        ops.set_precision("f16")
 
 
 def test_c5_dense_mask_stack_with_100_ocr_tokens_vs_oracle():
@@ -149,7 +156,7 @@ def test_c5_dense_mask_stack_with_100_ocr_tokens_vs_oracle():
             got = dict(model.named_parameters())[name].grad.detach().cpu()
             assert rel_err(got, P[name].grad) < 2e-3, name
     finally:
-        ops.set_precision("bf16")
+        ops.set_precision("f16")
 
 
 def test_context_biases_use_bias_true_vs_reference_golden():
@@ -178,13 +185,13 @@ def test_context_biases_use_bias_true_vs_reference_golden():
                     got = got.flatten()[:: max(1, got.numel() // 4096)]
                 assert rel_err(got, torch.from_numpy(g[k])) < 2e-3, k
     finally:
-        ops.set_precision("bf16")
+        ops.set_precision("f16")
 
 
 def test_two_updates_with_flat_adam_equal_torch_adam_with_clipping(golden):
     """train.py:139-143 on both sides: our fused clip + Adam on the flat buffers against clip_grad_norm_ +
     torch.optim.Adam on a second copy of the model; logits after two updates must agree (this also checks that the
-    cached bf16 weight operands are refreshed after an update that wrote through raw pointers)."""
+    cached 16-bit weight operands are refreshed after an update that wrote through raw pointers)."""
     from sam_textvqa_b200 import ops, optim
     g, mmt, tb, state, _ = golden
     batch = golden_batch(g)
@@ -214,7 +221,7 @@ def test_two_updates_with_flat_adam_equal_torch_adam_with_clipping(golden):
         first = torch.from_numpy(g["tf/scores"]).to(DEV)
         assert rel_err(a, first, live) > 1e-3          # the updates did change the model
     finally:
-        ops.set_precision("bf16")
+        ops.set_precision("f16")
 
 
 def test_dropout_training_step_runs_and_is_reproducible(golden):
@@ -263,7 +270,7 @@ def test_direct_accumulation_into_flat_grad_buffer_matches_autograd_grads(golden
         buf.zero()
         assert float(buf.flat.abs().max()) == 0.0
     finally:
-        ops.set_precision("bf16")
+        ops.set_precision("f16")
         for p in model.parameters():
             p.grad = None
 
@@ -277,7 +284,7 @@ def test_cached_greedy_decoder_equals_reference_style_loop(monkeypatch):
     model = _model(mmt, tb, state).eval()
     graph_fn = lambda boxes: spatial_utils.build_graph_batch(boxes, 0.5)[0]
     batch = synth.make_batch(3, V=V, seed=9, contexts=(1, 3), graph_fn=graph_fn)
-    for prec, tol in (("bf16x3", 1e-5), ("bf16", 1e-5)):
+    for prec, tol in (("bf16x3", 1e-5), ("f16", 1e-5)):
         ops.set_precision(prec)
         ops.clear_weight_cache()
         outs = {}
@@ -289,7 +296,7 @@ def test_cached_greedy_decoder_equals_reference_style_loop(monkeypatch):
                     scores = model(bd)["textvqa_scores"]
                 outs[mode] = (scores.cpu(), bd["train_prev_inds"].cpu(), bd["mmt_seq_output"].cpu())
         finally:
-            ops.set_precision("bf16")
+            ops.set_precision("f16")
         live = outs["reference"][0] > -5000
         assert torch.equal(outs["cached"][1], outs["reference"][1])
         assert rel_err(outs["cached"][0], outs["reference"][0], live) < tol
@@ -343,7 +350,7 @@ def test_on_device_batch_preparation_matches_dataset_prepared_masks(golden):
     from sam_textvqa_b200 import ops
     g, mmt, tb, state, model = golden
     model.eval()
-    ops.set_precision("bf16")
+    ops.set_precision("f16")
     ops.clear_weight_cache()
     with torch.no_grad():
         b1 = golden_batch(g)

@@ -24,7 +24,7 @@ if os.path.exists("MEASURED_PEAKS.json"):
 
 def run(B, T, O, R, D, spatial=True):
     A, L, H, d = O + R, T + O + R + D, 12, 768
-    qkv = torch.randn(B * L, 3 * d, device=dev).bfloat16()
+    qkv = torch.randn(B * L, 3 * d, device=dev).half()
     valid = torch.ones(B, L, dtype=torch.uint8, device=dev); valid[:, -D:] = 0
     rs = np.random.RandomState(0)
     bits = None
@@ -34,9 +34,10 @@ def run(B, T, O, R, D, spatial=True):
     dims = (B, L, H, T, A, D)
     allow = ops.build_attn_mask(valid, bits, dims, spatial, 0b11 if spatial else 0)
     w = torch.randn(B * L, d, device=dev).bfloat16()
-    f = lambda: ops.attention_fwd(qkv, valid, bits, dims, spatial, 0b11 if spatial else 0, args.p, (1, 1), allow)
+    keep = ops.build_attn_keep(dims, args.p, (1, 1), dev) if args.p > 0 else None
+    f = lambda: ops.attention_fwd(qkv, valid, bits, dims, spatial, 0b11 if spatial else 0, args.p, (1, 1), allow, keep=keep)
     ctx, lse = f()
-    g = lambda: ops.attention_bwd(w, qkv, ctx, lse, valid, bits, dims, spatial, 0b11 if spatial else 0, args.p, (1, 1), allow)
+    g = lambda: ops.attention_bwd(w, qkv, ctx, lse, valid, bits, dims, spatial, 0b11 if spatial else 0, args.p, (1, 1), allow, keep=keep)
     for _ in range(3): f(); g()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     ev[0].record()
@@ -45,7 +46,7 @@ def run(B, T, O, R, D, spatial=True):
     for _ in range(args.reps): g()
     ev[2].record(); torch.cuda.synchronize()
     tf, tb = ev[0].elapsed_time(ev[1]) / args.reps * 1e3, ev[1].elapsed_time(ev[2]) / args.reps * 1e3
-    mask_b = B * (H if spatial else 1) * L * ((L + 31) // 32) * 4
+    mask_b = B * ((H if spatial else 1) + (H if keep is not None else 0)) * L * ((L + 31) // 32) * 4
     bytes_f = B * (4 * L * d * 2 + H * L * 4) + mask_b
     bytes_b = B * (8 * L * d * 2 + 2 * H * L * 4) + mask_b
     fl_f, fl_b = B * 4 * L * L * d, B * 10 * L * L * d

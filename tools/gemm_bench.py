@@ -9,7 +9,8 @@ M = 23296
 only = sys.argv[1] if len(sys.argv) > 1 else None
 reps = int(os.environ.get("REPS", "20"))
 
-def bf(*s): return (0.1 * torch.randn(*s, device=dev)).bfloat16()
+def bf(*s): return (0.1 * torch.randn(*s, device=dev)).bfloat16()      # gradients
+def hf(*s): return (0.1 * torch.randn(*s, device=dev)).half()          # forward activations / weights
 def f32(*s): return 0.1 * torch.randn(*s, device=dev)
 
 def run(name, fn, flops):
@@ -22,11 +23,12 @@ def run(name, fn, flops):
     ms = s.elapsed_time(e) / reps
     print("%-14s %8.1f us  %7.1f TFLOP/s" % (name, ms * 1e3, flops / ms / 1e9), flush=True)
 
-x768, x3072, W_qkv, W_o, W_1, W_2 = bf(M, 768), bf(M, 3072), bf(2304, 768), bf(768, 768), bf(3072, 768), bf(768, 3072)
+x768, x3072, W_qkv, W_o, W_1, W_2 = hf(M, 768), hf(M, 3072), hf(2304, 768), hf(768, 768), hf(3072, 768), hf(768, 3072)
 dy768, dy3072, dy2304 = bf(M, 768), bf(M, 3072), bf(M, 2304)
 b768, b2304, b3072 = f32(768), f32(2304), f32(3072)
 res = f32(M, 768)
-o768f, o768b, o2304b, o3072b, pre3072 = torch.empty(M, 768, device=dev), bf(M, 768), bf(M, 2304), bf(M, 3072), bf(M, 3072)
+o768f, o768b, o2304b, o3072b, pre3072 = torch.empty(M, 768, device=dev), bf(M, 768), hf(M, 2304), hf(M, 3072), hf(M, 3072)
+o3072g = bf(M, 3072)
 O = lambda t: ops.Operand(t, t.stride(0), 1)
 g = ops.gemm
 run("plain_3072", lambda: g(O(x768), False, O(W_1), False, M, 3072, 768, o3072b), 2 * M * 3072 * 768)
@@ -37,10 +39,9 @@ run("o_f32", lambda: g(O(x768), False, O(W_o), False, M, 768, 768, o768f), 2 * M
 run("o_f32_bias", lambda: g(O(x768), False, O(W_o), False, M, 768, 768, o768f, bias=b768), 2 * M * 768 * 768)
 run("o_f32_res", lambda: g(O(x768), False, O(W_o), False, M, 768, 768, o768f, residual=res), 2 * M * 768 * 768)
 run("o_f32_drop", lambda: g(O(x768), False, O(W_o), False, M, 768, 768, o768f, drop_p=0.1, drop=(1, 2)), 2 * M * 768 * 768)
-run("o_bf16_drop", lambda: g(O(x768), False, O(W_o), False, M, 768, 768, o768b, drop_p=0.1, drop=(1, 2)), 2 * M * 768 * 768)
 run("ffn1_fwd", lambda: g(O(x768), False, O(W_1), False, M, 3072, 768, o3072b, bias=b3072, act=3, pre=pre3072), 2 * M * 3072 * 768)
 run("ffn2_fwd", lambda: g(O(x3072), False, O(W_2), False, M, 768, 3072, o768f, bias=b768, drop_p=0.1, drop=(1, 2), residual=res), 2 * M * 3072 * 768)
-run("ffn2_dgrad", lambda: g(O(dy768), False, O(W_2), True, M, 3072, 768, o3072b, act=4, aux=pre3072), 2 * M * 3072 * 768)
+run("ffn2_dgrad", lambda: g(O(dy768), False, O(W_2), True, M, 3072, 768, o3072g, act=4, aux=pre3072), 2 * M * 3072 * 768)
 run("ffn1_dgrad", lambda: g(O(dy3072), False, O(W_1), True, M, 768, 3072, o768f, residual=res), 2 * M * 3072 * 768)
 run("o_dgrad", lambda: g(O(dy768), False, O(W_o), True, M, 768, 768, o768b), 2 * M * 768 * 768)
 run("qkv_dgrad", lambda: g(O(dy2304), False, O(W_qkv), True, M, 768, 2304, o768f, residual=res), 2 * M * 2304 * 768)

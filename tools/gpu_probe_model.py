@@ -34,7 +34,7 @@ def t_layernorm():
 
 def t_linear():
     section("linear fwd/bwd (both precisions)")
-    for prec in ("bf16", "bf16x3"):
+    for prec in ("f16", "bf16x3"):
         ops.set_precision(prec)
         for (M, N, K) in ((472, 768, 768), (144, 768, 4), (200, 768, 2952)):
             x = torch.randn(M, K + (1 if K == 4 else 0), device=dev)[:, :K]
@@ -47,7 +47,7 @@ def t_linear():
             gx, gW, gb = torch.autograd.grad((y * w).sum(), (x, W, b))
             rx, rW, rb = torch.autograd.grad((ref * w).sum(), (x, W, b))
             print(prec, (M, N, K), "y %.2e dx %.2e dW %.2e db %.2e" % (rel_err(y, ref), rel_err(gx, rx), rel_err(gW, rW), rel_err(gb, rb)))
-    ops.set_precision("bf16")
+    ops.set_precision("f16")
 
 def t_attention():
     section("attention vs golden attn_unit (reference SpatialBertSelfAttention)")
@@ -103,7 +103,7 @@ def build_model(V=500):
 def t_model():
     g = load_golden("sam4c_cfg1.npz")
     model = build_model()
-    for prec in ("bf16x3", "bf16"):
+    for prec in ("bf16x3", "f16"):
         section("SAM4C cfg1 teacher-forced, precision " + prec)
         ops.set_precision(prec)
         ops.clear_weight_cache()
