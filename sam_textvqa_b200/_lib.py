@@ -115,10 +115,27 @@ def lib():
     return _LIB
 
 
+_DEBUG_CAPTURE = os.environ.get("SAMK_DEBUG_CAPTURE", "0") != "0"
+_cudart = None
+
+
+def _capture_status():
+    """cudaStreamCaptureStatus of torch's current stream (0 none, 1 active, 2 invalidated); debugging aid."""
+    global _cudart
+    import torch
+    if _cudart is None:
+        _cudart = ctypes.CDLL("libcudart.so.12")
+    st = ctypes.c_int(0)
+    _cudart.cudaStreamIsCapturing(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), ctypes.byref(st))
+    return st.value
+
+
 def check(rc, what=""):
     if rc != 0:
         msg = lib().samk_last_error()
         raise SamkError("%s failed (%d): %s" % (what or "samk call", rc, (msg or b"").decode()))
+    if _DEBUG_CAPTURE and _capture_status() == 2:
+        raise SamkError("stream capture was invalidated at or before %r" % what)
 
 
 def stream_ptr():

@@ -205,9 +205,10 @@ class Operand(object):
 
 
 class _State(object):
-    """Per-device, per-thread mutable state of the operators: dropout stream, operand caches, side stream, LayerNorm
-    workspace.  `nn.DataParallel` (the reference's multi-GPU path, train.py:111-112) runs replicas concurrently in
-    Python threads on different devices; nothing here is shared between them."""
+    """Per-device mutable state of the operators: dropout stream, operand caches, side stream, LayerNorm workspace.
+    `nn.DataParallel` (the reference's multi-GPU path, train.py:111-112) runs replicas concurrently in Python threads
+    on DIFFERENT devices, so nothing here is shared between them; the forward (caller's thread) and the backward
+    (autograd's device thread) of one replica share their device's state, which is what the operand caches need."""
 
     def __init__(self, dev):
         self.rng = _Rng(dev)
@@ -218,7 +219,8 @@ class _State(object):
         self.side_open = False
 
 
-_tls = threading.local()
+_states = {}
+_states_lock = threading.Lock()
 
 
 def _state(dev=None):
@@ -226,12 +228,12 @@ def _state(dev=None):
         dev = torch.cuda.current_device()
     elif isinstance(dev, torch.device):
         dev = dev.index if dev.index is not None else torch.cuda.current_device()
-    table = getattr(_tls, "table", None)
-    if table is None:
-        table = _tls.table = {}
-    st = table.get(dev)
+    st = _states.get(dev)
     if st is None:
-        st = table[dev] = _State(dev)
+        with _states_lock:
+            st = _states.get(dev)
+            if st is None:
+                st = _states[dev] = _State(dev)
     return st
 
 
@@ -333,10 +335,8 @@ def weight_operand(params, mn_major, split=None, kdim=None, fmt="f16"):
 
 
 def clear_weight_cache():
-    table = getattr(_tls, "table", None)
-    if table:
-        for st in table.values():
-            st.weight_cache.clear()
+    for st in list(_states.values()):
+        st.weight_cache.clear()
 
 
 # ---- GEMM -------------------------------------------------------------------------------------------
@@ -754,6 +754,15 @@ def attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p
         attn_profile.append(("bwd", L, ev0, ev1, B * (8 * L * H * 64 * 2 + 2 * H * L * 4) + mask_b, 10.0 * B * L * L * H * 64))
     _count(4 if dq_accum is not None else 2)   # prep (+ memset) + main kernel (+ dq conversion)
     return dqkv
+
+
+def _bias3(qb, kb, vb):
+    """q|k|v biases as one [3d] vector for the fused projection (concatenated by one of our kernels, not aten::cat)."""
+    d = qb.shape[0]
+    out = torch.empty(3 * d, dtype=torch.float32, device=qb.device)
+    check(lib().samk_concat3_f32(ptr(qb), ptr(kb), ptr(vb), ptr(out), d, stream_ptr()), "concat3")
+    _count()
+    return out
 
 
 # ---- one post-LN BERT block (plain or spatial) -------------------------------------------------------------
