@@ -123,9 +123,10 @@ int samk_gemm_16(const void* A, int a_dtype, int a_mn_major, long long lda, cons
 int samk_cast_bf16(const float* x, long long ldx, void* y, long long ldy, int rows, int cols, void* stream);
 int samk_cast_16(const float* x, long long ldx, void* y, long long ldy, int y_dtype, int rows, int cols, void* stream);
 /* y = half(x * S) with S = the power of two that puts max|x| into [2^11, 2^12) (computed on the device, two passes,
- * saturating conversion); x contiguous, n % 4 == 0, x_dtype F32 or BF16.  scale2: 3 floats of device workspace,
+ * saturating conversion); x contiguous, n % 4 == 0, x_dtype F32 or BF16.  amax: optional device float holding max|x|
+ * already (then one pass).  scale2: 3 floats of device workspace,
  * scale2[0] = S, scale2[1] = 1/S (pass as samk_gemm_epilogue.alpha_dev of the product that consumes y). */
-int samk_cast_scaled_f16(const void* x, int x_dtype, long long n, void* y, float* scale2, void* stream);
+int samk_cast_scaled_f16(const void* x, int x_dtype, long long n, const float* amax, void* y, float* scale2, void* stream);
 int samk_split3_bf16(const float* x, long long ldx, void* y, long long ldy, int rows, int cols, int order,
                      int along_rows, void* stream);
 /* F.normalize(x, dim=-1) of sa_m4c.py:208-209,224-238 (normalize=0: plain copy/cast) */
@@ -135,12 +136,13 @@ int samk_l2norm(const float* x, long long ldx, void* y, long long ldy, int y_dty
  * y2_dtype and/or y3 in y3_dtype (the f16 copy the next contraction reads and the bf16 copy its weight-gradient
  * product reads, written in the same pass).  Backward: dx fp32; optional dxd = dropout_mask(dx) in dxd_dtype (gradient of the dense
  * output under the dropout of BertSelfOutput/BertOutput); dgamma, dbeta, dbias (= colsum(dxd)) are
- * ACCUMULATED (+=) into fp32 [cols] buffers (each may be NULL). */
+ * ACCUMULATED (+=) into fp32 [cols] buffers (each may be NULL).  dxd_amax (optional, one float): receives max|dxd|,
+ * the input of samk_cast_scaled_f16 for the weight-gradient product that needs dxd in half. */
 int samk_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y, void* y2,
                        int y2_dtype, void* y3, int y3_dtype, int rows, int cols, void* stream);
 int samk_layernorm_bwd(const float* dy, const float* x, const float* gamma, float eps, float* dx, void* dxd,
                        int dxd_dtype, float drop_p, unsigned long long seed, unsigned long long offset, float* dgamma,
-                       float* dbeta, float* dbias, float* partials, int rows, int cols, void* stream);
+                       float* dbeta, float* dbias, float* partials, int rows, int cols, float* dxd_amax, void* stream);
 /* floats of scratch for `partials` (NULL = reduce with atomics instead of the 2-stage reduction) */
 long long samk_layernorm_bwd_partials(int cols);
 /* out = dropout(a + b) (b may be NULL); also the dropout backward with a = dout */

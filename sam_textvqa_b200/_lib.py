@@ -56,13 +56,13 @@ SIGNATURES = {
                              ctypes.POINTER(GemmEpilogue), c_int, c_int, c_void_p]),
     "samk_cast_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p]),
     "samk_cast_16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
-    "samk_cast_scaled_f16": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p]),
+    "samk_cast_scaled_f16": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
     "samk_split3_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
     "samk_l2norm": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
     "samk_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                    c_int, c_void_p]),
     "samk_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_float, c_ull,
-                                   c_ull, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+                                   c_ull, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "samk_layernorm_bwd_partials": (c_ll, [c_int]),
     "samk_dropout_add": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_ull, c_ull, c_void_p]),
     "samk_colsum": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p]),

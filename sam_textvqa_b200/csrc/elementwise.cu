@@ -31,6 +31,17 @@ __device__ __forceinline__ float4 load_act(const void* base, int bf16, size_t id
   return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
 }
 
+template <int DT>
+__device__ __forceinline__ float4 load_act_t(const void* base, size_t idx) {
+  if constexpr (DT == SAMK_DT_F32) {
+    return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+  } else {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(base) + idx);
+    const float2 a = unpack_16<DT == SAMK_DT_F16>(u.x), b = unpack_16<DT == SAMK_DT_F16>(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+}
+
 __device__ __forceinline__ float4 drop4(float4 v, uint32_t thresh, float scale, uint64_t seed, uint64_t off,
                                         uint64_t ctr) {
   if (!thresh) return v;
@@ -166,8 +177,9 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
                      float eps, float* __restrict__ dx, void* __restrict__ dxd, int dxd_bf16, uint32_t thresh,
                      float scale, unsigned long long seed, unsigned long long off, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, float* __restrict__ dbias, float* __restrict__ partials, int rows,
-                     int cols) {
+                     int cols, unsigned int* __restrict__ dxd_amax) {
   extern __shared__ float4 acc4[];   // [warps][3][cols/4]
+  float amax = 0.f;                  // max |dxd| seen by this lane (for the exactly scaled half copy, samk_cast_scaled_f16)
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warp = blockIdx.x * kLnBwdWarps + wib;
   const int nwarps = gridDim.x * kLnBwdWarps;
@@ -239,9 +251,14 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
       if (want_d) {
         float4 od = drop4(o, thresh, scale, seed, off, (uint64_t)r * row_groups + (uint64_t)c4);
         if (dxd) store_act(dxd, dxd_bf16, (size_t)r * cols + c, od);
+        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(od.x), fabsf(od.y)), fmaxf(fabsf(od.z), fabsf(od.w))));
         if (dbias) { float4 t = sd[c4]; t.x += od.x; t.y += od.y; t.z += od.z; t.w += od.w; sd[c4] = t; }
       }
     }
+  }
+  if (dxd_amax) {
+    amax = warp_max(amax);
+    if (lane == 0 && amax > 0.f) atomicMax(dxd_amax, __float_as_uint(amax));
   }
   __syncthreads();
   // reduce the per-warp slices and publish the block partials
@@ -309,7 +326,8 @@ __global__ void dropout_add_kernel(const float* __restrict__ a, const float* __r
 // out[c] += sum_r x[r, c]
 // part_cols > 0: the columns are n consecutive groups of part_cols with separate destinations out, out1, out2
 // (bias gradients of the fused q|k|v projection are three separate parameters)
-__global__ void __launch_bounds__(1024) colsum_kernel(const void* __restrict__ x, int x_bf16, long long ld, int rows, int cols,
+template <int DT>
+__global__ void __launch_bounds__(1024) colsum_kernel(const void* __restrict__ x, long long ld, int rows, int cols,
                               float* __restrict__ out, float* __restrict__ out1, float* __restrict__ out2, int part_cols) {
   // block = 1024 threads = 64 column-quads x 16 row lanes; a warp holds 16 quads (128 contiguous bytes of a bf16 row)
   // x 2 row lanes, reduced with one shuffle.  No shared memory and about one block per SM: on the side branch of the
@@ -324,15 +342,15 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const void* __restrict__ x
     const int stride = gridDim.y * nrl;
     int r = blockIdx.y * nrl + rl;
     for (; r + 3 * stride < rows; r += 4 * stride) {   // 4 independent loads in flight per thread
-      float4 v0 = load_act(x, x_bf16, (size_t)r * ld + cq * 4);
-      float4 v1 = load_act(x, x_bf16, (size_t)(r + stride) * ld + cq * 4);
-      float4 v2 = load_act(x, x_bf16, (size_t)(r + 2 * stride) * ld + cq * 4);
-      float4 v3 = load_act(x, x_bf16, (size_t)(r + 3 * stride) * ld + cq * 4);
+      float4 v0 = load_act_t<DT>(x, (size_t)r * ld + cq * 4);
+      float4 v1 = load_act_t<DT>(x, (size_t)(r + stride) * ld + cq * 4);
+      float4 v2 = load_act_t<DT>(x, (size_t)(r + 2 * stride) * ld + cq * 4);
+      float4 v3 = load_act_t<DT>(x, (size_t)(r + 3 * stride) * ld + cq * 4);
       acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
       acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
     }
     for (; r < rows; r += stride) {
-      float4 v = load_act(x, x_bf16, (size_t)r * ld + cq * 4);
+      float4 v = load_act_t<DT>(x, (size_t)r * ld + cq * 4);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
   }
@@ -936,9 +954,13 @@ int samk_layernorm_fwd(const float* x, const float* gamma, const float* beta, fl
 
 int samk_layernorm_bwd(const float* dy, const float* x, const float* gamma, float eps, float* dx, void* dxd,
                        int dxd_dtype, float drop_p, unsigned long long seed, unsigned long long offset, float* dgamma,
-                       float* dbeta, float* dbias, float* partials, int rows, int cols, void* stream) {
+                       float* dbeta, float* dbias, float* partials, int rows, int cols, float* dxd_amax, void* stream) {
   SAMK_REQUIRE(dy && x && gamma && rows >= 0, "bad argument");
   SAMK_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 1024, "cols must be a multiple of 4, <= 1024");
+  if (dxd_amax && cudaMemsetAsync(dxd_amax, 0, sizeof(float), (cudaStream_t)stream) != cudaSuccess) {
+    set_error("%s: memset failed", __func__);
+    return SAMK_ERR_CUDA;
+  }
   if (!rows) return SAMK_OK;
   int grid = grid_for(rows, kLnBwdWarps * 4);
   if (grid > 592) grid = 592;   // partials workspace is sized for 592 blocks (samk_layernorm_bwd_partials)
@@ -946,7 +968,7 @@ int samk_layernorm_bwd(const float* dy, const float* x, const float* gamma, floa
   launch_maybe_pdl(layernorm_bwd_kernel, dim3(grid), dim3(kLnBwdWarps * 32), (size_t)smem, (cudaStream_t)stream,
                    pdl_level() >= 2, dy, x, gamma, eps, dx, dxd, dxd_dtype,
                    drop_p > 0.f ? drop_threshold(drop_p) : 0u, drop_keep_scale(drop_p), seed, offset, dgamma, dbeta,
-                   dbias, partials, rows, cols);
+                   dbias, partials, rows, cols, reinterpret_cast<unsigned int*>(dxd_amax));
   int rc = check_launch(__func__);
   if (rc || !partials) return rc;
   ln_bwd_finalize_kernel<<<dim3((cols + 31) / 32, 3), 1024, 0, (cudaStream_t)stream>>>(partials, grid, cols, dgamma, dbeta, dbias);
@@ -975,6 +997,13 @@ static int colsum_threads() {
   return t;
 }
 
+static void launch_colsum(int dt, dim3 grid, int threads, cudaStream_t st, const void* x, long long ld, int rows, int cols,
+                          float* o0, float* o1, float* o2, int part_cols) {
+  if (dt == SAMK_DT_F32) colsum_kernel<SAMK_DT_F32><<<grid, threads, 0, st>>>(x, ld, rows, cols, o0, o1, o2, part_cols);
+  else if (dt == SAMK_DT_F16) colsum_kernel<SAMK_DT_F16><<<grid, threads, 0, st>>>(x, ld, rows, cols, o0, o1, o2, part_cols);
+  else colsum_kernel<SAMK_DT_BF16><<<grid, threads, 0, st>>>(x, ld, rows, cols, o0, o1, o2, part_cols);
+}
+
 int samk_colsum(const void* x, int x_dtype, long long ld, int rows, int cols, float* out, void* stream) {
   SAMK_REQUIRE(x && out && rows >= 0 && cols >= 0, "bad argument");
   if (!rows || !cols) return SAMK_OK;
@@ -989,7 +1018,7 @@ int samk_colsum(const void* x, int x_dtype, long long ld, int rows, int cols, fl
   if (gy > (rows + nrl - 1) / nrl) gy = (rows + nrl - 1) / nrl;
   if (gy < 1) gy = 1;
   dim3 grid(gx, gy);
-  colsum_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(x, x_dtype, ld, rows, cols, out, nullptr, nullptr, 0);
+  launch_colsum(x_dtype, grid, threads, (cudaStream_t)stream, x, ld, rows, cols, out, nullptr, nullptr, 0);
   return check_launch(__func__);
 }
 
@@ -1006,7 +1035,7 @@ int samk_colsum3(const void* x, int x_dtype, long long ld, int rows, int part_co
   if (gy > (rows + nrl - 1) / nrl) gy = (rows + nrl - 1) / nrl;
   if (gy < 1) gy = 1;
   dim3 grid(gx, gy);
-  colsum_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(x, x_dtype, ld, rows, cols, out0, out1, out2, part_cols);
+  launch_colsum(x_dtype, grid, threads, (cudaStream_t)stream, x, ld, rows, cols, out0, out1, out2, part_cols);
   return check_launch(__func__);
 }
 
@@ -1127,12 +1156,17 @@ int samk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
   return check_launch(__func__);
 }
 
-int samk_cast_scaled_f16(const void* x, int x_dtype, long long n, void* y, float* scale2, void* stream) {
+int samk_cast_scaled_f16(const void* x, int x_dtype, long long n, const float* amax, void* y, float* scale2, void* stream) {
   SAMK_REQUIRE(x && y && scale2 && n >= 0, "bad argument");
   SAMK_REQUIRE(n % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 7) == 0, "n must be a multiple of 4, aligned buffers");
   cudaStream_t st = (cudaStream_t)stream;
   // scale2[0] doubles as the amax accumulator of pass 1 (bit pattern), overwritten with S by pass 2 ... no: a reader
   // of pass 2 in another block could see S instead of amax, so the accumulator is the third float of the workspace
+  const int grid_c = grid_for(n / 4, 2048) > 1184 ? 1184 : grid_for(n / 4, 2048);
+  if (amax) {      // max|x| already known (e.g. accumulated by samk_layernorm_bwd while it wrote x): one pass
+    cast_scaled_f16_kernel<<<n ? grid_c : 1, n ? 256 : 32, 0, st>>>(x, x_dtype, n / 4, reinterpret_cast<const unsigned int*>(amax), (__half*)y, scale2);
+    return check_launch(__func__);
+  }
   if (cudaMemsetAsync(scale2 + 2, 0, sizeof(float), st) != cudaSuccess) { set_error("%s: memset failed", __func__); return SAMK_ERR_CUDA; }
   if (!n) { cast_scaled_f16_kernel<<<1, 32, 0, st>>>(x, x_dtype, 0, reinterpret_cast<unsigned int*>(scale2 + 2), (__half*)y, scale2); return check_launch(__func__); }
   const int grid = grid_for(n / 4, 2048) > 1184 ? 1184 : grid_for(n / 4, 2048);

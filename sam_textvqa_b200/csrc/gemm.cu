@@ -722,12 +722,12 @@ static int gemm_2cta() {
 // (forward activations are stored as IEEE half, gradients as bfloat16: see ops.py "Precision modes")
 constexpr int M_QKV = F_OUT_BF16 | F_OUT_F16 | F_BIAS | F_VEC;                            // fused q|k|v projection
 constexpr int M_OUTPROJ = F_BIAS | F_DROP | F_RES | F_VEC;                                // W_o / FFN2 forward (train)
-constexpr int M_FFN1 = F_OUT_BF16 | F_OUT_F16 | F_BIAS | F_GELU_PAIR | F_PRE_BF16 | F_PRE_F16 | F_VEC;   // FFN1 forward (train)
+constexpr int M_FFN1 = F_OUT_BF16 | F_OUT_F16 | F_BIAS | F_GELU_PAIR | F_PRE_BF16 | F_VEC;   // FFN1 forward (train): gelu half, gelu' bf16
 constexpr int M_BF16 = F_OUT_BF16 | F_VEC;                                                // W_o dgrad
 constexpr int M_F32_BIAS = F_BIAS | F_VEC;                                                // input projections, heads
 constexpr int M_F32_BIAS_RES = F_BIAS | F_RES | F_VEC;                                    // inference W_o / FFN2
 constexpr int M_GELU = F_OUT_BF16 | F_OUT_F16 | F_BIAS | F_GELU | F_VEC;                  // inference FFN1
-constexpr int M_MULAUX = F_OUT_BF16 | F_MULAUX | F_AUX_BF16 | F_AUX_F16 | F_VEC;          // FFN2 dgrad * gelu'
+constexpr int M_MULAUX = F_OUT_BF16 | F_MULAUX | F_AUX_BF16 | F_VEC;                      // FFN2 dgrad * gelu' (bf16: unpacked by a shift)
 constexpr int M_F32_RES = F_RES | F_VEC;                                                  // FFN1 / qkv dgrad + skip grad
 constexpr int M_F32 = F_VEC;
 constexpr int M_ATOMIC = F_ATOMIC | F_ALPHA | F_VEC;                                      // wgrad accumulation (alpha: 1 / gradient scale)

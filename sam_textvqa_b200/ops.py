@@ -115,10 +115,10 @@ def _ln_partials(dev, cols):
     return ws[cols]
 
 
-def _ln_bwd(dy, x, gamma, eps, dx, dxd, p, drop, dg, db, dbias, rows, cols):
+def _ln_bwd(dy, x, gamma, eps, dx, dxd, p, drop, dg, db, dbias, rows, cols, amax=None):
     check(lib().samk_layernorm_bwd(ptr(dy), ptr(x), ptr(gamma), eps, ptr(dx), ptr(dxd),
                                    _dt(dxd) if dxd is not None else 0, p, drop[0], drop[1], ptr(dg), ptr(db),
-                                   ptr(dbias), ptr(_ln_partials(dy.device, cols)), rows, cols, stream_ptr()),
+                                   ptr(dbias), ptr(_ln_partials(dy.device, cols)), rows, cols, ptr(amax), stream_ptr()),
           "layernorm_bwd")
     _count(2)
 
@@ -291,16 +291,18 @@ def operand(x2d, role, mn_major, fmt="f16", split=None):
     return Operand(y, y.stride(0), 1)
 
 
-def scaled_f16(x2d):
+def scaled_f16(x2d, amax=None):
     """(Operand over half(x * S), device pointer to 1/S) for a gradient tensor x2d (bf16 or fp32, contiguous): S is the
     power of two, found on the device, that puts max|x| into [2^11, 2^12).  The consumer passes the pointer as
-    `alpha_dev` of its GEMM.  Used where a gradient meets a big saved f16 activation in a weight-gradient product."""
+    `alpha_dev` of its GEMM.  Used where a gradient meets a big saved f16 activation in a weight-gradient product.
+    amax: device float already holding max|x| (written by the kernel that produced x), saves the reduction pass."""
     _cuda(x2d)
     assert x2d.is_contiguous() and x2d.numel() % 4 == 0
     y = torch.empty(x2d.shape, dtype=torch.float16, device=x2d.device)
     sc = torch.empty(4, dtype=torch.float32, device=x2d.device)
-    check(lib().samk_cast_scaled_f16(ptr(x2d), _dt(x2d), x2d.numel(), ptr(y), ptr(sc), stream_ptr()), "cast_scaled_f16")
-    _count(2)
+    check(lib().samk_cast_scaled_f16(ptr(x2d), _dt(x2d), x2d.numel(), ptr(amax), ptr(y), ptr(sc), stream_ptr()),
+          "cast_scaled_f16")
+    _count(1 if amax is not None else 2)
     return Operand(y, y.stride(0), 1), sc[1:2]
 
 
@@ -820,9 +822,9 @@ class BertLayerFn(torch.autograd.Function):
                                        stream_ptr()), "ln1")
         _count()
         a_in = a_act if a_act is not None else a
-        h = torch.empty(M, F, dtype=adt, device=dev)
+        h = torch.empty(M, F, dtype=grad_dtype(), device=dev)     # gelu'(pre-activation): read by the FFN2 dgrad epilogue only
         g = torch.empty(M, F, dtype=adt, device=dev)
-        gemm(operand(a_in, "a", False), False, weight_operand([iw], False), False, M, F, d, g, bias=ib, act=3, pre=h)  # h := gelu'(pre-activation)
+        gemm(operand(a_in, "a", False), False, weight_operand([iw], False), False, M, F, d, g, bias=ib, act=3, pre=h)
         y2 = torch.empty(M, d, dtype=torch.float32, device=dev)
         gemm(operand(g, "a", False), False, weight_operand([o2w], False), False, M, d, F, y2, bias=o2b, drop_p=p_hid,
              drop=drops[2], residual=a)
@@ -861,14 +863,15 @@ class BertLayerFn(torch.autograd.Function):
         # ---- LN2 backward (+ dropout mask of the FFN output, + b_2 gradient)
         dy2 = torch.empty(M, d, dtype=torch.float32, device=dev)      # grad wrt (dropout(dense)+a)
         dY2 = torch.empty(M, d, dtype=gdt, device=dev)                 # grad wrt dense output
-        _ln_bwd(dout, y2, g2, eps, dy2, dY2, p_hid, ctx.drops[2], Gg2, Gb2, Go2b, M, d)
+        amax2 = torch.empty(2, dtype=torch.float32, device=dev) if half else None     # max|dY2|, max|dY1|
+        _ln_bwd(dout, y2, g2, eps, dy2, dY2, p_hid, ctx.drops[2], Gg2, Gb2, Go2b, M, d, amax=amax2)
         # ---- FFN2: dgrad (fused with the stored GELU') and wgrad
         dh = torch.empty(M, F, dtype=gdt, device=dev)
         gemm(operand(dY2, "a", False, fmt=wfmt), False, weight_operand([o2w], True, fmt=wfmt), True, M, F, d, dh, act=4, aux=h)
         with side_branch():                       # b_1 gradient beside the GEMMs that follow
             colsum_into(dh, Gib)
         if half:
-            dY2h, inv2 = scaled_f16(dY2)
+            dY2h, inv2 = scaled_f16(dY2, amax2)
             gemm(dY2h, True, operand(g, "b", True), True, d, F, M, Go2w, accumulate=True, alpha_dev=inv2)
         else:
             gemm(operand(dY2, "a", True), True, operand(g, "b", True), True, d, F, M, Go2w, accumulate=True)
@@ -880,12 +883,12 @@ class BertLayerFn(torch.autograd.Function):
         # ---- LN1 backward (+ dropout mask of the attention output dense, + b_o gradient)
         dy1 = torch.empty(M, d, dtype=torch.float32, device=dev)
         dY1 = torch.empty(M, d, dtype=gdt, device=dev)
-        _ln_bwd(da, y1, g1, eps, dy1, dY1, p_hid, ctx.drops[1], Gg1, Gb1, Gob, M, d)
+        _ln_bwd(da, y1, g1, eps, dy1, dY1, p_hid, ctx.drops[1], Gg1, Gb1, Gob, M, d, amax=amax2[1:] if half else None)
         # ---- attention output dense
         dctx = torch.empty(M, d, dtype=gdt, device=dev)
         gemm(operand(dY1, "a", False, fmt=wfmt), False, weight_operand([ow], True, fmt=wfmt), True, M, d, d, dctx)
         if half:
-            dY1h, inv1 = scaled_f16(dY1)
+            dY1h, inv1 = scaled_f16(dY1, amax2[1:])
             gemm(dY1h, True, operand(ctx_t, "b", True), True, d, d, M, Gow, accumulate=True, alpha_dev=inv1)
         else:
             gemm(operand(dY1, "a", True), True, operand(ctx_t, "b", True), True, d, d, M, Gow, accumulate=True)

@@ -1,2 +1,5 @@
 cd /root/repo
-SAMK_DEBUG_CAPTURE=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | grep -v "^{" | tail -30
+OUT=gpurun_out; TAG=r02d
+timeout 600 ncu --clock-control none --metrics gpu__time_duration.sum -c 6000 --csv --log-file $OUT/${TAG}_launches.csv python bench.py --profile-only > $OUT/${TAG}_launches.out 2>&1
+python tools/summarize_launches.py $OUT/${TAG}_launches.csv 1 > $OUT/${TAG}_launches_summary.txt 2>&1
+head -60 $OUT/${TAG}_launches_summary.txt; gzip -f $OUT/${TAG}_launches.csv
