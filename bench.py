@@ -10,9 +10,21 @@ N > 1) -> zero_grad.  Workload at every N: BASELINE config[1], the shipped c3 ex
 (layers n,n,s,s,s,s; 20 text + 100 obj + 50 OCR + 12 dec tokens; d=768; V=5000), 128 samples per GPU
 (weak scaling).  `value` is timed with the inputs resident in HBM; `e2e` runs the same step from
 pinned host buffers with the host->device copies and a device->host read of the loss inside the
-timed region.  `--impl reference` times the CPU restatement of the reference algorithm
-(oracle/sam4c_oracle.py, the reference's own torch CPU ops and mask algebra; the reference tree
-itself does not exist on the GPU box) on the host cores, on a bounded sample of the same workload.
+timed region.
+
+The line also carries
+  parity    the precision mode that was TIMED, checked on this box against the reference-generated golden of the
+            shipped c3 stack (tests/golden/sam4c_c3.npz): logits rel err and argmax identity, plus the other mode;
+  extras    (N = 1) throughput of the other precision mode, a full optimizer step, greedy decoding, BASELINE
+            configs 0 / 2, the spatial-graph kernel (pairs/s, GB/s);
+  roofline  all tcgen05 GEMM launches of one step against the sustained bf16 peak, per-shape detail with the DRAM
+            bytes ncu measured (profiles/ncu_traffic.json, written by tools/ncu_summary.py from `ncu --set full`).
+
+`--impl reference` times the UNMODIFIED reference (oracle/_ref: a verbatim, git-ignored copy of /root/reference/sam
+made by `python -m oracle.build_ref`, run through the oracle/shim stand-ins for its two un-vendored dependencies) on the
+host cores: same model, same batch recipe with the relation graph from the reference's own builder, train mode, the
+reference's own loss; every step processes a bounded sample (--ref-batch rows of the 128-row batch).  Without the copy
+it falls back to the oracle port and says so (`kind`).
 """
 import argparse
 import json
@@ -30,6 +42,14 @@ METRIC = "SA-M4C fwd+bwd samples/sec"
 UNIT = "samples/s"
 CFG = dict(T=20, O=100, R=50, D=12, V=5000)
 WORKLOAD = "c3 yml SA-M4C (n,n,s,s,s,s), 20+100+50+12 tokens, d=768, V=5000, train fwd+bwd, dropout 0.1"   # both arms
+
+
+def config_dict(world, B, launch=None):
+    cfg = {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": world * B, "parallelism": "dp%d" % world}
+    if launch:
+        cfg["launch"] = launch
+        cfg["l2"] = "per-step working set (~6 GB of activations) >> 126 MB L2; no explicit flush"
+    return cfg
 
 
 def peaks():
@@ -88,11 +108,71 @@ class ClockSampler(object):
 
 
 # ---------------------------------------------------------------------------------------------------
-def cpu_port_step_fn(B, seed, threads):
-    """Returns (step, description): one fwd+loss+bwd+zero_grad of the oracle port on `B` samples."""
+# CPU arm: the unmodified reference (oracle/_ref) or, without it, the oracle port
+# ---------------------------------------------------------------------------------------------------
+def _ref_graph_one(args):
+    """(worker) relation types of one sample from the reference's own builder, sam/spatial_utils.py:92-218"""
+    root, shim, boxes = args
+    import warnings
+    warnings.filterwarnings("ignore")
+    for p in (root, shim):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import sam.spatial_utils as S
+    return S.build_graph_using_normalized_boxes(boxes)["1"]
+
+
+def cpu_reference_step_fn(B, seed, threads):
+    """Returns (step, kind, description): one zero_grad + fwd + loss + bwd of the reference on `B` samples."""
     import numpy as np
     import torch
-    from oracle import graph_oracle, sam4c_oracle
+    from oracle import ref_loader
+    from sam_textvqa_b200 import synth
+    from sam_textvqa_b200.config import c3_config
+    torch.set_num_threads(threads)
+    mmt, tb = c3_config()
+    if not ref_loader.reference_available():
+        return cpu_port_step_fn(B, seed, threads)
+    import warnings
+    warnings.filterwarnings("ignore")
+    M, S, registry = ref_loader.load_reference(CFG["V"])
+
+    def graph_fn(boxes):            # the dataset side of the reference builds these in a process pool as well
+        import multiprocessing as mp
+        jobs = [(ref_loader.REF_ROOT, ref_loader.SHIM_DIR, b) for b in np.asarray(boxes)]
+        with mp.get_context("fork").Pool(max(1, min(threads, len(jobs)))) as pool:
+            return np.stack(pool.map(_ref_graph_one, jobs))
+
+    batch = synth.make_batch(B, seed=seed, contexts=(1, 3), graph_fn=graph_fn, **CFG)
+    torch.manual_seed(0)
+    model = M.SAM4C(M.BertConfig.from_dict(mmt), M.BertConfig.from_dict(tb)).train()
+    try:
+        from sam.task_utils import M4CDecodingBCEWithMaskLoss       # sam/task_utils.py:19-30, unmodified
+        loss_fn, loss_src = M4CDecodingBCEWithMaskLoss(), "sam.task_utils.M4CDecodingBCEWithMaskLoss"
+    except Exception as exc:                                          # a dataset-side import missing on this host
+        from oracle import sam4c_oracle
+        loss_fn, loss_src = sam4c_oracle.bce_with_mask_loss, "oracle restatement of the loss (%s)" % type(exc).__name__
+    keys = [k for k, v in batch.items() if torch.is_tensor(v) and k not in ("boxes", "spatial_types")]
+
+    def step():
+        model.zero_grad()
+        bd = {k: batch[k] for k in keys}
+        bd["spatial_adj_matrices"] = dict(batch["spatial_adj_matrices"])
+        scores = model(bd)["textvqa_scores"]
+        loss = loss_fn(scores, batch["targets"], batch["train_loss_mask"])
+        loss.backward()
+        return float(loss.detach())
+
+    desc = ("unmodified reference SAM4C (%s via oracle/shim), torch CPU fp32, train mode, %s, relation graph from the "
+            "reference builder, %d of the 128 samples of the batch per step" % (ref_loader.REF_ROOT, loss_src, B))
+    return step, "reference", desc
+
+
+def cpu_port_step_fn(B, seed, threads):
+    """Fallback when oracle/_ref is absent: the oracle port (same op sequence as the reference)."""
+    import numpy as np
+    import torch
+    from oracle import sam4c_oracle
     from sam_textvqa_b200 import synth
     from sam_textvqa_b200.config import c3_config
     from tests._util import sam4c_state_shapes
@@ -115,7 +195,8 @@ def cpu_port_step_fn(B, seed, threads):
             v.grad = None
         return float(loss.detach())
 
-    return step, "oracle port (torch CPU fp32, reference op sequence incl. dense masks, unique-check, dropout), B=%d" % B
+    return step, "port", ("oracle port (oracle/_ref missing): torch CPU fp32, reference op sequence incl. dense masks, "
+                          "unique-check, dropout; random relation types; B=%d" % B)
 
 
 def run_reference(args):
@@ -124,26 +205,74 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     B = args.ref_batch
-    step, desc = cpu_port_step_fn(B, 0, threads)
-    for _ in range(args.warmup if args.warmup < 2 else 1):
+    step, kind, desc = cpu_reference_step_fn(B, 0, threads)
+    for _ in range(args.warmup):
         step()
     t0 = time.time()
     for _ in range(args.steps):
         step()
-    dt = (time.time() - t0) / args.steps
+    dt = (time.time() - t0) / max(args.steps, 1)
     val = B / dt
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "sample_batch": B},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args.gpus, args.batch),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------
+def parity_check(dev):
+    """Logits of the shipped c3 stack against the golden the UNMODIFIED reference produced for this very model and
+    batch (tests/golden/sam4c_c3.npz; generator oracle/make_golden.py), in the current precision mode."""
+    import numpy as np
+    import torch
+    from sam_textvqa_b200 import ops, spatial_utils, synth
+    from sam_textvqa_b200.config import c3_config
+    from sam_textvqa_b200.registry import registry
+    from sam_textvqa_b200.sa_m4c import SAM4C, BertConfig
+    from tests._util import rel_err, sam4c_state_shapes
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "sam4c_c3.npz"))
+    V = 500
+    saved = registry.get("answer_vocab")
+    registry.answer_vocab = ["w%d" % i for i in range(V)]
+    try:
+        mmt, tb = c3_config(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, obj_drop=0.0, ocr_drop=0.0)
+        tb = dict(tb, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+        model = SAM4C(BertConfig.from_dict(mmt), BertConfig.from_dict(tb))
+        model.load_state_dict(synth.seeded_state(sam4c_state_shapes(mmt, tb, V), 1), strict=True)
+        model = model.to(dev).train()
+        graph_fn = lambda boxes: spatial_utils.build_graph_batch(boxes, 0.5)[0]
+        batch = synth.make_batch(3, V=V, seed=5, contexts=(1, 3), graph_fn=graph_fn)
+        types_ok = bool(np.array_equal(batch["spatial_types"].numpy(), gold["types"]))    # CUDA graph kernel == reference builder
+        ref = torch.from_numpy(gold["tf/scores"])
+        live = ref > -5000
+        out = {}
+        cur = ops.get_precision()
+        for mode in (cur, "bf16x3" if cur != "bf16x3" else "f16"):
+            ops.set_precision(mode)
+            ops.clear_weight_cache()
+            bd = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+            bd["spatial_adj_matrices"] = {k: v.to(dev) for k, v in batch["spatial_adj_matrices"].items()}
+            with torch.no_grad():
+                scores = model(bd)["textvqa_scores"].float().cpu()
+            out[mode] = {"logits_rel_err": rel_err(scores, ref, live),
+                         "argmax_match": bool(torch.equal(scores.argmax(-1), ref.argmax(-1)))}
+        ops.set_precision(cur)
+        ops.clear_weight_cache()
+        del model
+        res = {"mode": cur, "logits_rel_err": out[cur]["logits_rel_err"], "argmax_match": out[cur]["argmax_match"],
+               "tolerance": 1e-3, "golden": "tests/golden/sam4c_c3.npz (unmodified reference, c3 stack, L=182, B=3)",
+               "graph_types_bit_exact": types_ok}
+        other = [m for m in out if m != cur][0]
+        res["other_mode"] = dict(out[other], mode=other)
+        return res
+    finally:
+        registry.answer_vocab = saved
+
+
 def run_samk(args):
     import torch
     import torch.distributed as dist
@@ -157,26 +286,25 @@ def run_samk(args):
 
     from sam_textvqa_b200 import build as samk_build
     samk_build.build()
-    from sam_textvqa_b200 import dp, ops, spatial_utils, synth
+    from sam_textvqa_b200 import dp, ops, optim, spatial_utils, synth
     from sam_textvqa_b200.config import c3_config
     from sam_textvqa_b200.registry import registry
     from sam_textvqa_b200.sa_m4c import SAM4C, BertConfig
 
     ops.set_precision(args.precision)
+    parity = parity_check(dev) if rank == 0 and not args.profile_only else None
     registry.answer_vocab = ["w%d" % i for i in range(CFG["V"])]
     registry.BOS_IDX = 1
     mmt, tb = c3_config()
     torch.manual_seed(0)
     model = SAM4C(BertConfig.from_dict(mmt), BertConfig.from_dict(tb)).to(dev).train()
-    grads = dp.FlatGradBuffer(model.parameters())
-    # SAMK_DP_OVERLAP=1: bucketed NCCL all-reduce on a side stream under the backward pass.  Measured at N=2 it does
-    # not pay (13.97 vs 13.85 ms/step): NCCL's CTAs displace CTAs of the persistent 148-CTA GEMMs, which then run a
-    # second partial wave.  Default: one all-reduce of the flat buffer after backward (~0.9 ms exposed).
-    overlap = world > 1 and os.environ.get("SAMK_DP_OVERLAP", "0") == "1"
-    if overlap:
-        # one early bucket: everything that is final when the MMT stack's backward ends (~half of the bytes) goes
-        # out while the TextBERT backward runs (its GEMMs have fewer tiles than SMs, so NCCL's CTAs cost nothing)
-        grads.enable_overlap(bucket_bytes=int(os.environ.get("SAMK_DP_BUCKET_MB", "160")) << 20)
+    # gradients and parameters in flat buffers laid out by learning-rate group (get_optimizer_parameters,
+    # sa_m4c.py:349-371); the fused clip + Adam of the `extras` leg works on them (built before the graph capture:
+    # it moves the parameters)
+    groups = model.get_optimizer_parameters(1e-4)
+    grads = optim.flat_grad_buffer_for(groups)
+    opt = optim.FlatAdam(groups, grads, lr=1e-4, max_grad_norm=0.25)
+    exchange = dp.GradExchange(grads, world) if world > 1 else None
     B = args.batch
 
     def graph_fn(boxes):
@@ -191,28 +319,25 @@ def run_samk(args):
     h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values()) + pinned_adj.numel()
     resident = {k: v.to(dev) for k, v in pinned.items()}
     resident_adj = pinned_adj.to(dev)
+    # Data-parallel loss normalisation: the reference divides by the GLOBAL number of valid steps (DataParallel gathers
+    # the scores, task_utils.py:118-129).  Every rank scales its loss by local_count / global_count and the exchange
+    # SUMS the gradients: no divide pass over the 387 MB buffer.
+    loss_scale = dp.global_loss_scale(resident["train_loss_mask"]) if world > 1 else None
 
-    def step(inputs, adj_dev):
+    def loss_of(scores, b):
+        loss = ops.bce_with_mask_loss(scores, b["targets"], b["train_loss_mask"])
+        return loss * loss_scale if loss_scale is not None else loss
+
+    def fwd_bwd(inputs, adj_dev):
         grads.zero()
-        if overlap:
-            grads.begin_step()
         bd = dict(inputs)
         bd["spatial_adj_matrices"] = {"3": adj_dev}
-        scores = model(bd)["textvqa_scores"]
-        loss = ops.bce_with_mask_loss(scores, inputs["targets"], inputs["train_loss_mask"])
+        loss = loss_of(model(bd)["textvqa_scores"], inputs)
         loss.backward()
-        if overlap:
-            grads.finish_step()
-        elif world > 1:
-            grads.all_reduce()
         return loss
 
-    def upload():
-        up = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
-        return up, pinned_adj.to(dev, non_blocking=True)
-
     # The step as a user runs it: captured once into a CUDA graph (sam_textvqa_b200/graph_step.py) and replayed --
-    # ~310 launches through ctypes + autograd cost the host about as long as the GPU needs for the step.
+    # ~340 launches through ctypes + autograd cost the host about as long as the GPU needs for the step.
     # SAMK_BENCH_EAGER=1 keeps the eager loop.
     graphed = None
     if os.environ.get("SAMK_BENCH_EAGER", "0") != "1":
@@ -220,21 +345,21 @@ def run_samk(args):
             from sam_textvqa_b200.graph_step import GraphedTrainStep
             ex = dict(resident)
             ex["spatial_adj_matrices"] = {"3": resident_adj}
-            graphed = GraphedTrainStep(model, grads, ex, allreduce="overlap" if overlap else None)
+            graphed = GraphedTrainStep(model, grads, ex, loss_fn=loss_of)
         except Exception as exc:                      # fall back loudly, never silently
             print("bench: CUDA-graph capture failed (%r); running the eager step" % (exc,), file=sys.stderr, flush=True)
             graphed = None
-    eager_step = step
 
-    def step(inputs, adj_dev):                       # noqa: F811  (same contract as the eager step above)
+    def step(inputs, adj_dev, do_exchange=True):
         if graphed is None:
-            return eager_step(inputs, adj_dev)
-        if inputs is not resident:                    # fresh upload: device-to-device copy into the graph's input buffers
-            graphed.load(inputs)
-            graphed.load({"spatial_adj_matrices": {"3": adj_dev}})
-        loss = graphed.run()
-        if world > 1 and not overlap:
-            grads.all_reduce()
+            loss = fwd_bwd(inputs, adj_dev)
+        else:
+            if inputs is not resident:                # fresh upload: device-to-device copy into the graph's input buffers
+                graphed.load(inputs)
+                graphed.load({"spatial_adj_matrices": {"3": adj_dev}})
+            loss = graphed.run()
+        if exchange is not None and do_exchange:
+            exchange.all_reduce()
         return loss
 
     def barrier():
@@ -260,21 +385,20 @@ def run_samk(args):
             step(resident, resident_adj)
         torch.cuda.synchronize()
         return
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step(resident, resident_adj)
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = ops.launch_count
     ms = timed(lambda: step(resident, resident_adj), args.steps)
     launches = ops.launch_count - l0
     if graphed is not None:                    # replays do not pass through the Python counters
-        launches = graphed.kernels_per_replay * args.steps
+        launches = (graphed.kernels_per_replay + (exchange.kernels_per_call if exchange else 0)) * args.steps
 
     # ---- end to end: every step's inputs come from pinned host memory; the copy of step i+1 runs on a
     # side stream while step i computes (double-buffered device staging), and every step's loss is read
     # back to the host.  All K uploads and K loss reads are inside the timed region.
     copy_stream = torch.cuda.Stream()
-    # two persistent device staging sets; `consumed[slot]` (compute stream) says the step that read slot has taken its
-    # inputs, `ready[slot]` (copy stream) says the next upload into slot has landed
     staged = [({k: torch.empty_like(v) for k, v in resident.items()}, torch.empty_like(resident_adj)) for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
@@ -290,16 +414,11 @@ def run_samk(args):
             abuf.copy_(pinned_adj, non_blocking=True)
             ready[slot].record(copy_stream)
 
-    diag = os.environ.get("SAMK_E2E_DIAG", "")
     host_loss = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_done = [torch.cuda.Event(), torch.cuda.Event()]
     loss_values = []
 
     def e2e_run(steps):
-        if diag == "noupload":
-            for i in range(steps):
-                step(resident, resident_adj).item()
-            return
         stage(0)
         for i in range(steps):
             torch.cuda.current_stream().wait_event(ready[i % 2])
@@ -311,22 +430,19 @@ def run_samk(args):
                 graphed.load({"spatial_adj_matrices": {"3": a}})
                 consumed[i % 2].record()
                 loss = graphed.run()
-                if world > 1 and not overlap:
-                    grads.all_reduce()
             else:
-                loss = eager_step(up, a)
+                loss = fwd_bwd(up, a)
                 consumed[i % 2].record()
+            if exchange is not None:
+                exchange.all_reduce()
             # device->host read of EVERY step's loss: an async copy into pinned memory plus an event right behind the
             # step; the host reads step i-1's value after it has enqueued step i, waiting on that event only
-            # (`.item()` would synchronise the whole stream, i.e. also wait for the step just enqueued, and the GPU
-            # would then idle while the host prepares the next one)
-            if diag != "noitem":
-                host_loss[i % 2].copy_(loss.detach().reshape(1), non_blocking=True)
-                loss_done[i % 2].record()
-                if i >= 1:
-                    loss_done[(i - 1) % 2].synchronize()
-                    loss_values.append(float(host_loss[(i - 1) % 2][0]))
-        if diag != "noitem" and steps >= 1:
+            host_loss[i % 2].copy_(loss.detach().reshape(1), non_blocking=True)
+            loss_done[i % 2].record()
+            if i >= 1:
+                loss_done[(i - 1) % 2].synchronize()
+                loss_values.append(float(host_loss[(i - 1) % 2][0]))
+        if steps >= 1:
             loss_done[(steps - 1) % 2].synchronize()
             loss_values.append(float(host_loss[(steps - 1) % 2][0]))
 
@@ -343,6 +459,12 @@ def run_samk(args):
     ms_e2e = ms_t.item() / args.steps
     clocks = sampler.stop() if sampler else None
 
+    # exposed part of the gradient exchange: the same K steps without it (after the headline measurements)
+    allreduce_exposed_ms = None
+    if exchange is not None:
+        ms_noex = timed(lambda: step(resident, resident_adj, do_exchange=False), args.steps)
+        allreduce_exposed_ms = ms - ms_noex
+
     # ---- roofline of the dominant kernel family (tcgen05 GEMM), instrumented extra steps ----
     ops.gemm_profile = []
     ops.attn_profile = []
@@ -354,7 +476,7 @@ def run_samk(args):
             torch.cuda._sleep(int(4e7))        # ~20 ms at 1.9 GHz; the host needs ~10-15 ms to enqueue a step
         except Exception:                      # private torch API: without it the figures are only more pessimistic
             pass
-        eager_step(resident, resident_adj)
+        fwd_bwd(resident, resident_adj)
         torch.cuda.synchronize()
     prof, ops.gemm_profile = ops.gemm_profile, None
     aprof, ops.attn_profile = ops.attn_profile, None
@@ -363,33 +485,37 @@ def run_samk(args):
     n_gemm = len(prof) // 2
     peak_tf, peak_gbs, peak_src = peaks()
     achieved = g_flop / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
-    # the same live events per GEMM shape: the five shapes that take the most time in a step, each with its algorithmic
-    # operand bytes (bf16 A and B read once, output written once) and, where profiles/ holds an `ncu --set full`
-    # capture of that shape, the measured DRAM bytes per launch
-    ncu_dram = {   # (M, N, K, a_mn, b_mn) -> (read MB, write MB, file)  -- profiles/r01j_ncu_summary.txt
-        (768, 3072, 23296, True, True): (342.2, 10.0, "r01j_ncu_gemm_ffn2_wgrad_raw.csv"),
-        (23296, 3072, 768, False, False): (40.6, 234.0, "r01j_ncu_gemm_ffn1_fwd_raw.csv"),
-        (23296, 3072, 768, False, True): (183.7, 110.0, "r01j_ncu_gemm_ffn2_dgrad_raw.csv"),
-        (23296, 2304, 768, False, False): (39.4, 54.9, "r01j_ncu_gemm_qkv_fwd_raw.csv"),
-    }
+    # DRAM bytes per launch measured by `ncu --set full` for the big shapes (tools/ncu_summary.py --json)
+    ncu_traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            ncu_traffic = json.load(open(tpath))
+        except Exception:
+            ncu_traffic = {}
     groups = {}
     for s_, e_, f_, shape in prof:
         g = groups.setdefault(shape, [0.0, 0, f_])
         g[0] += s_.elapsed_time(e_)
         g[1] += 1
     by_shape = []
-    for shape, (tot_ms, cnt, f_) in sorted(groups.items(), key=lambda kv: -kv[1][0])[:5]:
+    tr_sum, tr_launches, tr_ms = 0.0, 0, 0.0
+    for shape, (tot_ms, cnt, f_) in sorted(groups.items(), key=lambda kv: -kv[1][0]):
         us = tot_ms / cnt * 1e3
         tf = f_ / (us * 1e-6) / 1e12
         Mg, Ng, Kg, amn, bmn = shape
         item = {"M": Mg, "N": Ng, "K": Kg, "a_mn": amn, "b_mn": bmn, "launches_per_step": cnt // 2,
                 "us_per_launch": us, "achieved": tf, "frac": tf / peak_tf, "share_of_step": tot_ms / 2 / ms if ms > 0 else None,
                 "operand_MB": (Mg * Kg + Ng * Kg) * 2 / 1e6}
-        if shape in ncu_dram and B == 128:
-            rd, wr, src = ncu_dram[shape]
-            item["traffic"] = (rd + wr) * 1e6
-            item["traffic_src"] = "profiles/" + src
-        by_shape.append(item)
+        key = "gemm_%dx%dx%d_%d%d" % (Mg, Ng, Kg, int(amn), int(bmn))
+        if key in ncu_traffic and B == 128:
+            item["traffic"] = ncu_traffic[key]["dram_bytes"]
+            item["traffic_src"] = ncu_traffic[key].get("src")
+            tr_sum += item["traffic"] * (cnt // 2)
+            tr_launches += cnt // 2
+            tr_ms += tot_ms / 2
+        if len(by_shape) < 6:
+            by_shape.append(item)
     # the north-star kernel: fused masked attention of the MMT layers (L = 182), HBM-bound at this length
     Lm = CFG["T"] + CFG["O"] + CFG["R"] + CFG["D"]
     attention = {}
@@ -401,54 +527,155 @@ def run_samk(args):
                                "algorithmic_MB": rows[0][1] / 1e6, "achieved_GBs": rows[0][1] / (ms_k * 1e-3) / 1e9,
                                "hbm_frac": rows[0][1] / (ms_k * 1e-3) / 1e9 / peak_gbs,
                                "dense_equiv_TFLOPs": rows[0][2] / (ms_k * 1e-3) / 1e12}
+            key = "attn_%s_L%d" % (kind, Lm)
+            if key in ncu_traffic and B == 128:
+                attention[kind]["traffic"] = ncu_traffic[key]["dram_bytes"]
+                attention[kind]["tensor_pipe_pct"] = ncu_traffic[key].get("tensor_pipe_pct")
+                attention[kind]["traffic_src"] = ncu_traffic[key].get("src")
     attention["peak_GBs"] = peak_gbs
-    attention["ncu"] = ("profiles/r01j_ncu_summary.txt: fwd (attn_fwd3) 80.6 us, DRAM 185+29 MB per launch, tensor pipe "
-                        "12.1 %, issue slots 50 %; bwd (attn_bwd2) 190 us, DRAM 153+73 MB, tensor pipe 14.4 % "
-                        "(L=182 is HBM/ALU-bound, SURVEY 8d)")
+    attention["note"] = "L=182 is HBM/ALU-bound (SURVEY 8d); the bwd launch includes the dO preparation kernel"
 
     if rank != 0:
         if world > 1:
+            del graphed
+            torch.cuda.synchronize()
             dist.destroy_process_group()
         return
     value = world * B / (ms * 1e-3)
     e2e_val = world * B / (ms_e2e * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f16" if args.precision == "f16" else "bf16x3", "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "batch_per_gpu": B, "global_batch": world * B, "parallelism": "dp%d" % world,
-                   "launch": "cuda-graph replay of the captured step" if graphed is not None else "eager",
-                   "l2": "per-step working set (~6 GB of activations) >> 126 MB L2; no explicit flush"},
+        "config": config_dict(world, B, "cuda-graph replay of the captured step" if graphed is not None else "eager"),
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d_bytes),
                 "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
+        "parity": parity,
         "roofline": {"bound": "tensor", "kernel": "samk::gemm_tc_kernel (all %d GEMM launches of one step)" % n_gemm,
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                     "traffic": None, "peak_source": peak_src + " (sustained bf16)",
+                     "traffic": (tr_sum / tr_launches) if tr_launches else None,
+                     "traffic_note": ("mean DRAM bytes per launch over the %d launches (%.0f %% of the GEMM time) whose shape has "
+                                      "an ncu --set full capture in profiles/ncu_traffic.json" % (tr_launches, 100 * tr_ms / g_ms))
+                     if tr_launches else "no profiles/ncu_traffic.json",
+                     "peak_source": peak_src + " (sustained bf16)",
                      "gemm_ms_per_step": g_ms, "gemm_share_of_step": g_ms / ms if ms > 0 else None,
                      "step_flop_frac_of_peak": value / world * FLOP_PER_SAMPLE / (peak_tf * 1e12),
-                     "by_shape": by_shape,
-                     "traffic_note": "aggregate over all GEMM shapes of the step, so no single per-launch figure; per-shape "
-                                     "DRAM bytes from ncu --set full are in profiles/r01i_ncu_summary.txt "
-                                     "(e.g. FFN2 wgrad 342+9 MB vs 322 MB algorithmic)"},
+                     "by_shape": by_shape},
         "attention": attention,
     }
+    if exchange is not None:
+        line["allreduce_exposed_ms"] = allreduce_exposed_ms
+        line["exchange"] = exchange.describe()
+    if world == 1 and not args.no_extras:
+        line["extras"] = run_extras(args, dev, model, grads, opt, graphed, resident, resident_adj, B)
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        cstep, desc = cpu_port_step_fn(args.ref_batch, 0, threads)
+        cstep, kind, desc = cpu_reference_step_fn(args.ref_batch, 0, threads)
         cstep()
         t0 = time.time()
         n = 2
         for _ in range(n):
             cstep()
         dt = (time.time() - t0) / n
-        line["cpu_baseline"] = {"value": args.ref_batch / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": desc + ", 1 warm-up + %d timed iterations" % n}
+        line["cpu_baseline"] = {"value": args.ref_batch / dt, "unit": UNIT, "cores": threads, "kind": kind,
+                                "sample": desc + "; 1 warm-up + %d timed steps" % n}
     print(json.dumps(line), flush=True)
     if world > 1:
+        del graphed
+        torch.cuda.synchronize()
         dist.destroy_process_group()
+
+
+def run_extras(args, dev, model, grads, opt, graphed, resident, resident_adj, B):
+    """Secondary measurements on the same box (N = 1): short, each reported with its own timing."""
+    import numpy as np
+    import torch
+    from sam_textvqa_b200 import dp, ops, spatial_utils, synth
+    from sam_textvqa_b200.config import c3_config
+    from sam_textvqa_b200.sa_m4c import SAM4C, BertConfig
+    out = {}
+
+    def timeit(fn, steps, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / steps
+
+    def fwd_bwd(mdl, gr, res, adjd):
+        gr.zero()
+        bd = dict(res)
+        bd["spatial_adj_matrices"] = adjd
+        ops.bce_with_mask_loss(mdl(bd)["textvqa_scores"], res["targets"], res["train_loss_mask"]).backward()
+
+    try:
+        # 1. the same step in the other precision mode (strict: 3-term splits, exact fp32 attention), eager
+        cur = ops.get_precision()
+        other = "bf16x3" if cur == "f16" else "f16"
+        ops.set_precision(other)
+        ops.clear_weight_cache()
+        ms_o = timeit(lambda: fwd_bwd(model, grads, resident, {"3": resident_adj}), 3, 1)
+        out["other_precision_mode"] = {"mode": other, "ms_per_step": ms_o, "samples_per_s": B / ms_o * 1e3, "launch": "eager"}
+        ops.set_precision(cur)
+        ops.clear_weight_cache()
+        # 2. full training step: graph-replayed fwd+bwd + fused clip + Adam on the flat buffers (train.py:139-143)
+        if graphed is not None:
+            try:
+                def train_step():
+                    graphed.run()
+                    opt.step()
+                ms_t = timeit(train_step, 5, 2)
+                out["train_step_with_clip_adam"] = {"ms_per_step": ms_t, "samples_per_s": B / ms_t * 1e3}
+            except Exception as exc:
+                out["train_step_with_clip_adam"] = {"error": repr(exc)[:200]}
+        # 3. greedy 12-step decoding (eval), KV-cached
+        model.eval()
+
+        def decode():
+            bd = dict(resident)
+            bd["spatial_adj_matrices"] = {"3": resident_adj}
+            with torch.no_grad():
+                model(bd)
+        ms_d = timeit(decode, 3, 1)
+        out["greedy_decode_12_steps"] = {"ms_per_batch": ms_d, "samples_per_s": B / ms_d * 1e3}
+        model.train()
+        # 4. spatial-graph kernel (BASELINE: the reference builds 19-56 k pairs/s per core in Python)
+        N = CFG["O"] + CFG["R"]
+        boxes = torch.from_numpy(synth.make_boxes(np.random.RandomState(0), 1024, N)[..., :4].astype("float32")).to(dev)
+        ms_g = timeit(lambda: spatial_utils.build_graph_batch(boxes, 0.5, context=3), 10, 2)
+        pairs = 1024 * N * N
+        gbytes = 1024 * (16 * N + N * N + 2 * N * N)            # float4 boxes in, int8 types + uint16 head bits out
+        out["graph_kernel"] = {"B": 1024, "N": N, "us_per_launch": ms_g * 1e3, "pairs_per_s": pairs / (ms_g * 1e-3),
+                               "algorithmic_GBs": gbytes / (ms_g * 1e-3) / 1e9,
+                               "bound": "latency / fp64 classification (24.9 KB in+out per sample)"}
+        # 5. BASELINE configs 0 and 2 (fwd+bwd, eager)
+        graph_fn = lambda b: spatial_utils.build_graph_batch(b.astype("float32"), 0.5)[0]
+        for name, over, Bc, O, R, ctx in (("cfg0: 1 spatial layer, 20+36+50 tokens, B=4", dict(layer_type_list=["s"], mix_list=["share3"]), 4, 36, 50, 3),
+                                          ("cfg2: c5, 100 obj + 100 OCR tokens, B=256",
+                                           dict(mix_list=["none", "none", "share5", "share5", "share5", "share5"]), 256, 100, 100, 5)):
+            mmt, tb = c3_config(**over)
+            torch.manual_seed(0)
+            m2 = SAM4C(BertConfig.from_dict(mmt), BertConfig.from_dict(tb)).to(dev).train()
+            g2 = dp.FlatGradBuffer(m2.parameters())
+            b2 = synth.make_batch(Bc, O=O, R=R, V=CFG["V"], seed=0, contexts=(ctx,), graph_fn=graph_fn)
+            adjd = {str(ctx): b2.pop("spatial_adj_matrices")[str(ctx)].to(dev)}
+            if ctx != 1:
+                adjd["1"] = adjd[str(ctx)]
+            r2 = {k: v.to(dev) for k, v in b2.items() if torch.is_tensor(v)}
+            ms_c = timeit(lambda: fwd_bwd(m2, g2, r2, adjd), 3 if Bc > 8 else 10, 2)
+            out[name] = {"ms_per_step": ms_c, "samples_per_s": Bc / ms_c * 1e3, "launch": "eager"}
+            del m2, g2, r2, adjd
+            torch.cuda.empty_cache()
+    except Exception as exc:      # extras never take the headline down
+        out["error"] = repr(exc)[:300]
+    return out
 
 
 def main():
@@ -458,9 +685,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="samk", choices=["samk", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="samples per GPU")
-    ap.add_argument("--ref-batch", type=int, default=16, help="bounded CPU sample size")
+    ap.add_argument("--ref-batch", type=int, default=32, help="bounded CPU sample: rows of the batch per reference step")
     ap.add_argument("--precision", default="f16", choices=["f16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="run 3 bare steps and exit (for ncu launch lists)")
     args = ap.parse_args()
     if args.impl == "reference":

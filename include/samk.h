@@ -122,6 +122,9 @@ int samk_gemm_16(const void* A, int a_dtype, int a_mn_major, long long lda, cons
  * GEMM over the 3x longer K reproduces fp32 products to ~2^-16 ("bf16x3" parity mode). */
 int samk_cast_bf16(const float* x, long long ldx, void* y, long long ldy, int rows, int cols, void* stream);
 int samk_cast_16(const float* x, long long ldx, void* y, long long ldy, int y_dtype, int rows, int cols, void* stream);
+/* contiguous copy between fp32 and a 16-bit format (either direction; e.g. the bf16 wire format of the gradient
+ * all-reduce that replaces nn.DataParallel's reduction, train.py:111-112) */
+int samk_cast_flat(const void* x, int x_dtype, void* y, int y_dtype, long long n, void* stream);
 /* y = half(x * S) with S = the power of two that puts max|x| into [2^11, 2^12) (computed on the device, two passes,
  * saturating conversion); x contiguous, n % 4 == 0, x_dtype F32 or BF16.  amax: optional device float holding max|x|
  * already (then one pass).  scale2: 3 floats of device workspace,

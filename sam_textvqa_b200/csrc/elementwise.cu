@@ -897,6 +897,18 @@ __global__ void cast_scaled_f16_kernel(const void* __restrict__ x, int dt, long 
   }
 }
 
+// flat copy between fp32 and a 16-bit format (either direction), 4 elements per thread + scalar tail
+__global__ void cast_flat_kernel(const void* __restrict__ x, int xdt, void* __restrict__ y, int ydt, long long n) {
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+    store_act(y, ydt, (size_t)i * 4, load_act(x, xdt, (size_t)i * 4));
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = n4 * 4 + threadIdx.x;
+    const float v = xdt ? ld_16(reinterpret_cast<const uint16_t*>(x) + i, xdt == SAMK_DT_F16) : reinterpret_cast<const float*>(x)[i];
+    if (ydt) st_16(reinterpret_cast<uint16_t*>(y) + i, v, ydt == SAMK_DT_F16); else reinterpret_cast<float*>(y)[i] = v;
+  }
+}
+
 // out[0:n] = a, out[n:2n] = b, out[2n:3n] = c (the three biases of the fused q|k|v projection)
 __global__ void concat3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
                                float* __restrict__ out, int n) {
@@ -1172,6 +1184,14 @@ int samk_cast_scaled_f16(const void* x, int x_dtype, long long n, const float* a
   const int grid = grid_for(n / 4, 2048) > 1184 ? 1184 : grid_for(n / 4, 2048);
   amax_kernel<<<grid, 256, 0, st>>>(x, x_dtype, n / 4, reinterpret_cast<unsigned int*>(scale2 + 2));
   cast_scaled_f16_kernel<<<grid, 256, 0, st>>>(x, x_dtype, n / 4, reinterpret_cast<const unsigned int*>(scale2 + 2), (__half*)y, scale2);
+  return check_launch(__func__);
+}
+
+int samk_cast_flat(const void* x, int x_dtype, void* y, int y_dtype, long long n, void* stream) {
+  SAMK_REQUIRE(x && y && n >= 0, "bad argument");
+  SAMK_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "buffers must be 16-byte aligned");
+  if (!n) return SAMK_OK;
+  cast_flat_kernel<<<grid_for(n / 4 + 1, 1024), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, y, y_dtype, n);
   return check_launch(__func__);
 }
 

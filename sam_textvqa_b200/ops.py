@@ -183,6 +183,15 @@ def cast_16(x2d, dtype):
     return y
 
 
+def cast_flat(src, dst):
+    """contiguous fp32 <-> 16-bit copy of a flat buffer (gradient wire format of dp.GradExchange)"""
+    _cuda(src, dst)
+    n = src.numel()
+    assert dst.numel() == n and src.is_contiguous() and dst.is_contiguous()
+    check(lib().samk_cast_flat(ptr(src), _dt(src), ptr(dst), _dt(dst), n, stream_ptr()), "cast_flat")
+    _count()
+
+
 def _split3(x2d, order, along_rows):
     rows, cols = x2d.shape
     assert x2d.stride(1) == 1 and cols % 4 == 0

@@ -461,8 +461,23 @@ class SAM4C(nn.Module):
                     "downloads them (sa_m4c.py:74-77). Offline: export them once with torch.save(state_dict) "
                     "and set SAMK_BERT_BASE_STATE=<file>, or set text_bert_init_from_bert_base: false.")
             sd = torch.load(path, map_location="cpu")
-            sd = {k[len("bert."):] if k.startswith("bert.") else k: v for k, v in sd.items()}
-            self.text_bert.load_state_dict(sd, strict=False)
+            # what pytorch_transformers' from_pretrained does to a bert-base-uncased checkpoint (sa_m4c.py:74-77): strip
+            # the "bert." prefix, rename the TF-style LayerNorm gamma / beta, keep the first num_hidden_layers layers
+            ren = {}
+            for k, v in sd.items():
+                k = k[len("bert."):] if k.startswith("bert.") else k
+                if k.endswith(".gamma"):
+                    k = k[:-len("gamma")] + "weight"
+                elif k.endswith(".beta"):
+                    k = k[:-len("beta")] + "bias"
+                ren[k] = v
+            res = self.text_bert.load_state_dict(ren, strict=False)
+            if res.missing_keys:           # every TextBert parameter must come from the checkpoint
+                raise RuntimeError("SAMK_BERT_BASE_STATE=%s lacks TextBert parameters: %s" % (path, res.missing_keys[:8]))
+            extra = [k for k in res.unexpected_keys if not (k.startswith("encoder.layer.") or k.startswith("pooler.")
+                                                           or k.startswith("cls."))]
+            if extra:
+                logger.warning("bert-base state: %d unexpected keys ignored, e.g. %s", len(extra), extra[:4])
             self.finetune_modules.append({"module": self.text_bert,
                                           "lr_scale": self.text_bert_config.lr_scale_text_bert})
         if self.mmt_config.hidden_size != TEXT_BERT_HIDDEN_SIZE:
