@@ -281,6 +281,17 @@ def run_samk(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # SAMK_DP_OVERLAP=1: the gradient exchange runs bucket by bucket under the backward pass (captured in the graph).
+    # NCCL is capped at a few CTAs and the persistent kernels leave that many SMs out of their grids.
+    # Measured at N=2 (profiles/r02_dp_experiments.txt): 13.23 ms/step against 12.64 ms for the plain exchange after the
+    # step -- the 8 reserved SMs cost 0.25 ms and the last bucket (TextBERT + its 94 MB embedding table, final only when
+    # the backward pass ends) stays exposed at the capped NCCL bandwidth -- so it is opt-in.
+    overlap = world > 1 and os.environ.get("SAMK_DP_OVERLAP", "0") == "1"
+    if world > 1:
+        os.environ.setdefault("SAMK_DP_WIRE", "bf16")     # 193 MB on the wire instead of 387 MB (SAMK_DP_WIRE=f32: exact sum)
+    reserve = int(os.environ.get("SAMK_DP_RESERVE_SMS", "8"))
+    if overlap:
+        os.environ.setdefault("NCCL_MAX_CTAS", str(reserve))
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -304,7 +315,11 @@ def run_samk(args):
     groups = model.get_optimizer_parameters(1e-4)
     grads = optim.flat_grad_buffer_for(groups)
     opt = optim.FlatAdam(groups, grads, lr=1e-4, max_grad_norm=0.25)
-    exchange = dp.GradExchange(grads, world) if world > 1 else None
+    if overlap:
+        grads.enable_overlap(average=False, bucket_bytes=int(os.environ.get("SAMK_DP_BUCKET_MB", "32")) << 20)
+        from sam_textvqa_b200._lib import lib as _samk_lib
+        _samk_lib().samk_reserve_sms(reserve)
+    exchange = dp.GradExchange(grads, world, overlapped=overlap) if world > 1 else None
     B = args.batch
 
     def graph_fn(boxes):
@@ -328,12 +343,16 @@ def run_samk(args):
         loss = ops.bce_with_mask_loss(scores, b["targets"], b["train_loss_mask"])
         return loss * loss_scale if loss_scale is not None else loss
 
-    def fwd_bwd(inputs, adj_dev):
+    def fwd_bwd(inputs, adj_dev, exchange_inside=True):
         grads.zero()
+        if overlap and exchange_inside:
+            grads.begin_step()
         bd = dict(inputs)
         bd["spatial_adj_matrices"] = {"3": adj_dev}
         loss = loss_of(model(bd)["textvqa_scores"], inputs)
         loss.backward()
+        if overlap and exchange_inside:
+            grads.finish_step()
         return loss
 
     # The step as a user runs it: captured once into a CUDA graph (sam_textvqa_b200/graph_step.py) and replayed --
@@ -345,7 +364,7 @@ def run_samk(args):
             from sam_textvqa_b200.graph_step import GraphedTrainStep
             ex = dict(resident)
             ex["spatial_adj_matrices"] = {"3": resident_adj}
-            graphed = GraphedTrainStep(model, grads, ex, loss_fn=loss_of)
+            graphed = GraphedTrainStep(model, grads, ex, loss_fn=loss_of, allreduce="overlap" if overlap else None)
         except Exception as exc:                      # fall back loudly, never silently
             print("bench: CUDA-graph capture failed (%r); running the eager step" % (exc,), file=sys.stderr, flush=True)
             graphed = None
@@ -461,13 +480,24 @@ def run_samk(args):
 
     # exposed part of the gradient exchange: the same K steps without it (after the headline measurements)
     allreduce_exposed_ms = None
-    if exchange is not None:
-        ms_noex = timed(lambda: step(resident, resident_adj, do_exchange=False), args.steps)
+    if exchange is not None and graphed is not None:
+        if overlap:          # the exchange is part of the captured step: capture the step once more without it
+            from sam_textvqa_b200 import ops as _ops
+            hook, _ops.grad_ready_hook = _ops.grad_ready_hook, None
+            plain = GraphedTrainStep(model, grads, ex, loss_fn=loss_of, allreduce=None)
+            for _ in range(3):
+                plain.run()
+            ms_noex = timed(plain.run, args.steps)
+            _ops.grad_ready_hook = hook
+            del plain
+        else:
+            ms_noex = timed(lambda: step(resident, resident_adj, do_exchange=False), args.steps)
         allreduce_exposed_ms = ms - ms_noex
 
     # ---- roofline of the dominant kernel family (tcgen05 GEMM), instrumented extra steps ----
     ops.gemm_profile = []
     ops.attn_profile = []
+    saved_hook, ops.grad_ready_hook = ops.grad_ready_hook, None      # no exchange in the instrumented eager steps
     for _ in range(2):
         # per-launch events cannot be recorded inside a graph replay, and the eager loop is launch-bound: an event pair
         # around a kernel the GPU is waiting for also times the host's launch latency.  A spin kernel in front keeps the
@@ -476,8 +506,9 @@ def run_samk(args):
             torch.cuda._sleep(int(4e7))        # ~20 ms at 1.9 GHz; the host needs ~10-15 ms to enqueue a step
         except Exception:                      # private torch API: without it the figures are only more pessimistic
             pass
-        fwd_bwd(resident, resident_adj)
+        fwd_bwd(resident, resident_adj, exchange_inside=False)
         torch.cuda.synchronize()
+    ops.grad_ready_hook = saved_hook
     prof, ops.gemm_profile = ops.gemm_profile, None
     aprof, ops.attn_profile = ops.attn_profile, None
     g_ms = sum(s.elapsed_time(e) for s, e, _, _ in prof) / 2

@@ -34,6 +34,10 @@ int samk_version(void);
 const char* samk_last_error(void);
 /* number of SMs of the current device (grid sizing); <0 on error */
 int samk_sm_count(void);
+/* Leave n SMs out of the grids of the persistent kernels (GEMM, attention) launched from now on, for a collective
+ * that runs concurrently (the overlapped gradient all-reduce: NCCL capped at <= n CTAs).  Returns the number of SMs
+ * the persistent kernels will use (>= 2, even), or a negative error code.  n = 0 restores the default. */
+int samk_reserve_sms(int n);
 /* XORed into the key of every dropout stream of every kernel launched afterwards on this device (default 0).  Kernels
  * replayed from a CUDA graph keep the (seed, offset) they were captured with; setting a new salt before each replay
  * (stream-ordered, not itself captured) gives every replay fresh masks, identical in its forward and backward. */

@@ -42,6 +42,7 @@ SIGNATURES = {
     "samk_version": (c_int, []),
     "samk_last_error": (ctypes.c_char_p, []),
     "samk_sm_count": (c_int, []),
+    "samk_reserve_sms": (c_int, [c_int]),
     "samk_set_dropout_salt": (c_int, [c_ull, c_void_p]),
     "samk_advance_dropout_salt": (c_int, [c_void_p]),
     "samk_build_graph_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_int, c_void_p, c_void_p]),

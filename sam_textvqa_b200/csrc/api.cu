@@ -27,6 +27,8 @@ int check_launch(const char* what) {
 }
 
 int sm_count();
+int sm_count_physical();
+void set_sm_reserved(int n);
 int set_drop_salt_gemm(unsigned long long salt, cudaStream_t stream);
 int set_drop_salt_attn_tc(unsigned long long salt, cudaStream_t stream);
 int set_drop_salt_attn_simt(unsigned long long salt, cudaStream_t stream);
@@ -50,7 +52,12 @@ __global__ void advance_salt_kernel() {
 extern "C" {
 int samk_version(void) { return 100; }
 const char* samk_last_error(void) { return samk::g_err; }
-int samk_sm_count(void) { return samk::sm_count(); }
+int samk_sm_count(void) { return samk::sm_count_physical(); }
+int samk_reserve_sms(int n) {
+  if (n < 0) { samk::set_error("samk_reserve_sms: negative count"); return SAMK_ERR_ARG; }
+  samk::set_sm_reserved(n);
+  return samk::sm_count();
+}
 int samk_advance_dropout_salt(void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   unsigned long long* state = nullptr;

@@ -1614,7 +1614,7 @@ int attn_tc_bwd(const samk_attn_params* p, cudaStream_t stream) {
   dim3 grid((a.L + 127) / 128, a.H, a.B);
   attn_bwd_tc_kernel<<<grid, 256, smem, stream>>>(tqkv, tdo, a);
   if ((rc = check_launch("samk_attn_bwd(tc)"))) return rc;
-  attn_dq_store_kernel<<<148 * 8, 256, 0, stream>>>(p->dq_accum, (__nv_bfloat16*)p->dqkv, (size_t)rows, hd);
+  attn_dq_store_kernel<<<(sm_count() > 0 ? sm_count() : 148) * 8, 256, 0, stream>>>(p->dq_accum, (__nv_bfloat16*)p->dqkv, (size_t)rows, hd);
   return check_launch("samk_attn_bwd(dq store)");
 }
 

@@ -658,7 +658,8 @@ int make_tmap_bf16_2d(CUtensorMap* m, const void* base, long long rows, long lon
 }
 
 static int g_sm_count = 0;
-int sm_count() {
+static int g_sm_reserved = 0;
+int sm_count_physical() {
   if (!g_sm_count) {
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
@@ -667,6 +668,19 @@ int sm_count() {
   }
   return g_sm_count;
 }
+// SMs the persistent kernels (GEMM, attention) size their grids for: the device's SMs minus the ones reserved for a
+// concurrently running collective (samk_reserve_sms).  A persistent kernel has a STATIC tile schedule and one CTA per
+// SM: a CTA that cannot become resident because an NCCL CTA holds its SM starts only when a whole wave has finished
+// and doubles the kernel's duration; leaving those SMs out of the grid costs reserved/148 instead.
+int sm_count() {
+  const int n = sm_count_physical();
+  if (n <= 0) return n;
+  int r = g_sm_reserved;
+  if (r < 0) r = 0;
+  if (r > n - 2) r = n - 2;
+  return (n - r) & ~1;        // CTA pairs: keep it even
+}
+void set_sm_reserved(int n) { g_sm_reserved = n; }
 
 template <int BN, int A_MN, int B_MN, int CL, int EPI, bool STAGED>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiArgs& ep, int M, int N, int K, int split_k,

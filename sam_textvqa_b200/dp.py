@@ -47,7 +47,7 @@ class FlatGradBuffer(object):
     # PrevPredEmbeddings) is ready after its last report; the number of reports per parameter is learned in
     # the first step.  Maximal runs of ready, not yet reduced parameters are all-reduced on a side stream as
     # soon as they reach `bucket_bytes`, so the NVLink exchange runs under the rest of the backward pass.
-    def enable_overlap(self, group=None, average=True, bucket_bytes=48 << 20):
+    def enable_overlap(self, group=None, average=False, bucket_bytes=48 << 20):
         from . import ops
         self._ov = {"group": group, "average": average, "bucket": int(bucket_bytes), "expected": None,
                     "seen": {}, "stream": None, "works": []}
@@ -142,8 +142,9 @@ class FlatGradBuffer(object):
         if ov["stream"] is not None:
             torch.cuda.current_stream().wait_stream(ov["stream"])
 
-    def all_reduce(self, group=None, average=True, async_op=False):
-        """Sum (or average) gradients over the data-parallel group with one collective."""
+    def all_reduce(self, group=None, average=False, async_op=False):
+        """Sum (or average) gradients over the data-parallel group with one collective.  Prefer the sum with
+        `global_loss_scale` on the loss: averaging costs a pass over the buffer."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
         if average:
@@ -160,9 +161,10 @@ class GradExchange(object):
     wire_dtype torch.bfloat16 (SAMK_DP_WIRE=bf16): the buffer is packed to bf16 (one pass), all-reduced (193 MB) and
     unpacked; the sum then carries bf16 rounding (2^-9 relative per addend) -- off by default."""
 
-    def __init__(self, grads, world, group=None, wire_dtype=None):
+    def __init__(self, grads, world, group=None, wire_dtype=None, overlapped=False):
         import os
         self.grads, self.world, self.group = grads, world, group
+        self.overlapped = overlapped      # the bucketed exchange runs inside the step (FlatGradBuffer.enable_overlap)
         if wire_dtype is None:
             wire_dtype = torch.bfloat16 if os.environ.get("SAMK_DP_WIRE", "f32") == "bf16" else torch.float32
         self.wire_dtype = wire_dtype
@@ -170,7 +172,7 @@ class GradExchange(object):
         self.kernels_per_call = 0 if self.wire is None else 2
 
     def all_reduce(self):
-        if self.world <= 1 or not (dist.is_available() and dist.is_initialized()):
+        if self.overlapped or self.world <= 1 or not (dist.is_available() and dist.is_initialized()):
             return
         flat = self.grads.flat
         if self.wire is None:
@@ -182,7 +184,15 @@ class GradExchange(object):
         ops.cast_flat(self.wire, flat)
 
     def describe(self):
+        import os
         n = self.grads.flat.numel()
+        if self.overlapped:
+            ov = self.grads._ov
+            return {"collective": "bucketed ncclAllReduce(sum) on a side stream under the backward pass (captured in the step's "
+                                  "CUDA graph), buckets >= %d MB of finished gradients, NCCL_MAX_CTAS=%s, %s SMs left out of "
+                                  "the persistent kernels' grids" % (ov["bucket"] >> 20, os.environ.get("NCCL_MAX_CTAS", "default"),
+                                                                     os.environ.get("SAMK_DP_RESERVE_SMS", "8")),
+                    "wire_dtype": "float32", "bytes": n * 4, "average": "folded into the loss scale (no pass over the buffer)"}
         return {"collective": "ncclAllReduce(sum) over the flat gradient buffer, after the step",
                 "wire_dtype": str(self.wire_dtype).replace("torch.", ""),
                 "bytes": n * (4 if self.wire is None else 2), "average": "folded into the loss scale (no pass over the buffer)"}

@@ -103,9 +103,15 @@ def _ret(buf_direct):
     return None if buf_direct[1] else buf_direct[0]
 
 
+# parameters that also receive a gradient contribution from autograd AFTER the op that owns them has finished (the
+# out-projection weight and the context biases of a `use_bias` spatial layer: the folded bias W_o b + b_o is formed by a
+# torch op outside BertLayerFn); they are never reported early, the final flush of the exchange sends them
+late_grad_param_ids = set()
+
+
 def _grads_done(*params):
     if grad_ready_hook is not None:
-        grad_ready_hook([p for p in params if p is not None and p.is_leaf])
+        grad_ready_hook([p for p in params if p is not None and p.is_leaf and id(p) not in late_grad_param_ids])
 
 
 def _ln_partials(dev, cols):

@@ -156,6 +156,7 @@ class BertLayer(nn.Module):
             # W_o (ctx + b) + b_o = W_o ctx + (W_o b + b_o): the context bias of sa_m4c.py:600-603 (added to every row,
             # dead ones included) folds into the out-projection bias; autograd carries its gradient to b and W_o
             out_bias = out_bias + torch.nn.functional.linear(s.biases.weight, a.output.dense.weight)[0]
+            ops.late_grad_param_ids.update((id(a.output.dense.weight), id(s.biases.weight), id(a.output.dense.bias)))
         return (s.query.weight, s.query.bias, s.key.weight, s.key.bias, s.value.weight, s.value.bias,
                 a.output.dense.weight, out_bias, a.output.LayerNorm.weight, a.output.LayerNorm.bias,
                 self.intermediate.dense.weight, self.intermediate.dense.bias,
