@@ -400,9 +400,14 @@ def run_samk(args):
         return ms.item() / steps
 
     if args.profile_only:      # for `ncu` launch lists: 1 warm-up + 2 steps, nothing else
-        for _ in range(3):
+        log_path = os.environ.get("SAMK_LAUNCH_LOG")
+        for i in range(3):
+            if log_path and graphed is None and i == 2:      # eager run: shapes of the last step's launches, in order
+                ops.launch_log = []
             step(resident, resident_adj)
         torch.cuda.synchronize()
+        if log_path and ops.launch_log is not None:
+            json.dump(ops.launch_log, open(log_path, "w"))
         return
     warm = max(args.warmup, 3)
     for _ in range(warm):

@@ -191,6 +191,27 @@ int samk_ptr_scores_bwd(const float* dscores, long long ldds, int col_off, const
 int samk_bce_loss(const float* scores, const float* targets, const float* loss_mask, float* dscores, float* loss_out,
                   float* scratch, int rows, int ncls, void* stream);
 int samk_scale_inplace(float* x, long long n, const float* scale_dev, void* stream);
+/* Row segments of a joint [B, L, d] fp32 tensor <-> separate contiguous [B, rows_k, d] tensors (n_seg <= 4; segs /
+ * rows / offs are HOST arrays).  to_joint = 1 builds the MMT input [txt ; obj ; ocr ; dec] (sa_m4c.py:790) or scatters
+ * gradients of row slices into a joint buffer; to_joint = 0 is the inverse (the backward of the concatenation; the
+ * decoder / OCR rows the output heads read, sa_m4c.py:852-862). */
+int samk_row_segments_f32(float* joint, float* const* segs, const int* rows, const int* offs, int n_seg, int B, int L, int d,
+                          int to_joint, void* stream);
+/* key-valid bytes [B, T+O+R+D] of MMT.forward (sa_m4c.py:793-795): masks != 0, decoder part zero */
+int samk_key_valid(const long long* q_mask, const long long* obj_mask, const long long* ocr_mask, uint8_t* out, int B, int T,
+                   int O, int R, int D, void* stream);
+/* stream-ordered zero fill (gradient buffers) */
+int samk_memset0(void* p, long long bytes, void* stream);
+/* Greedy prediction without moving the logits: idx_out[r] = argmax_c x[r, c] (first maximum; sa_m4c.py:299-301,
+ * sam/datasets/metrics.py:26); hit_out[r] (optional) = targets[r, idx] (token-level hit against the soft targets). */
+int samk_argmax_rows(const float* x, long long ld, long long rows, int ncls, const float* targets, long long ldt, long long* idx_out,
+                     float* hit_out, void* stream);
+/* One step of beam search (sam/beam_search.py:88-130; the decoder the reference ships disabled, train.py:222): per sample
+ * the K best of K x ncls candidates log sigmoid(scores[b K + k, c]) + beam_scores[b K + k], completed beams continue
+ * with EOS only, at the first step only beam 0 counts.  scores points at step t of [B K, D, ncls] (row_stride = D ncls).
+ * Outputs [B K]: source beam row, chosen class, accumulated score (descending per sample). */
+int samk_beam_step(const float* scores, long long row_stride, int ncls, const float* beam_scores, const uint8_t* completed,
+                   int eos, int first_step, int B, int K, long long* prev_pos, long long* new_pos, float* new_scores, void* stream);
 /* out = [a ; b ; c], n floats each: the three nn.Linear biases of the fused q|k|v projection (sa_m4c.py:429-431) */
 int samk_concat3_f32(const float* a, const float* b, const float* c, float* out, int n, void* stream);
 

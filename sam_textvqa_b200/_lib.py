@@ -8,7 +8,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsamk.so")
+LIB_PATH = os.environ.get("SAMK_LIB") or os.path.join(HERE, "libsamk.so")     # SAMK_LIB: an instrumented developer build
 
 c_void_p, c_int, c_ll, c_float, c_double, c_ull = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong,
                                                    ctypes.c_float, ctypes.c_double, ctypes.c_ulonglong)
@@ -83,6 +83,12 @@ SIGNATURES = {
                                     c_int, c_void_p]),
     "samk_bce_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "samk_scale_inplace": (c_int, [c_void_p, c_ll, c_void_p, c_void_p]),
+    "samk_row_segments_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "samk_key_valid": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "samk_memset0": (c_int, [c_void_p, c_ll, c_void_p]),
+    "samk_argmax_rows": (c_int, [c_void_p, c_ll, c_ll, c_int, c_void_p, c_ll, c_void_p, c_void_p, c_void_p]),
+    "samk_beam_step": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                               c_void_p, c_void_p]),
     "samk_concat3_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "samk_sumsq": (c_int, [c_void_p, c_ll, c_void_p, c_void_p]),
     "samk_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_double, c_double, c_double, c_double, c_int,

@@ -12,8 +12,8 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libsamk.so")
-OBJ = os.path.join(HERE, "build")
+OUT = os.environ.get("SAMK_LIB") or os.path.join(HERE, "libsamk.so")
+OBJ = os.environ.get("SAMK_OBJ_DIR") or os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("SAMK_NVCC_EXTRA", "").split()

@@ -909,6 +909,142 @@ __global__ void cast_flat_kernel(const void* __restrict__ x, int xdt, void* __re
   }
 }
 
+// Up to 4 row segments of a [B, L, d] fp32 tensor <-> separate contiguous [B, rows_k, d] tensors, one launch.
+//   to_joint = 1: joint[b, off_k + i, :] = seg_k[b, i, :]     (MMT input: [txt ; obj ; ocr ; dec], sa_m4c.py:790)
+//   to_joint = 0: seg_k[b, i, :] = joint[b, off_k + i, :]     (its backward; decoder / OCR rows for the output heads)
+struct RowSegments { float* ptr[4]; int rows[4]; int off[4]; int n; };
+__global__ void row_segments_kernel(float* __restrict__ joint, RowSegments sg, int B, int L, int d4, int to_joint) {
+  int total = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) total += k < sg.n ? sg.rows[k] : 0;
+  const long long n = (long long)B * total * d4;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % d4);
+    long long r = e / d4;
+    const int b = (int)(r / total);
+    int i = (int)(r - (long long)b * total);
+    int k = 0;
+    while (k + 1 < sg.n && i >= sg.rows[k]) { i -= sg.rows[k]; ++k; }
+    float4* sp = reinterpret_cast<float4*>(sg.ptr[k]) + ((size_t)b * sg.rows[k] + i) * d4 + c;
+    float4* jp = reinterpret_cast<float4*>(joint) + ((size_t)b * L + sg.off[k] + i) * d4 + c;
+    if (to_joint) *jp = *sp; else *sp = *jp;
+  }
+}
+
+// key_valid[b, :] = [question_mask ; obj_mask ; ocr_mask ; zeros(D)] != 0 as bytes (sa_m4c.py:793-795: the decoder
+// part of the joint attention mask is zeros, causality is handled by the kernels)
+__global__ void key_valid_kernel(const long long* __restrict__ q, const long long* __restrict__ o, const long long* __restrict__ r,
+                                 uint8_t* __restrict__ out, int B, int T, int O, int R, int D) {
+  const int L = T + O + R + D;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B * L) return;
+  const int b = e / L, j = e - b * L;
+  long long v = 0;
+  if (j < T) v = q[(size_t)b * T + j];
+  else if (j < T + O) v = o[(size_t)b * O + (j - T)];
+  else if (j < T + O + R) v = r[(size_t)b * R + (j - T - O)];
+  out[e] = v != 0 ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Beam-search step (sam/beam_search.py:88-130): for every sample, the K best of the K x ncls candidates
+//   score(k, c) = log sigmoid(scores[b K + k, t, c]) + beam_score[b K + k]
+// with the reference's rules: a completed beam may only continue with EOS at no cost (:92-96); at t = 0 only beam 0
+// of every sample counts (:101-108).  One block per sample: every thread keeps its K best in registers, then K
+// rounds of a block-wide arg-max pop the winners in descending order (ties: lowest candidate index).
+// ---------------------------------------------------------------------------------------------
+constexpr int kBeamMax = 16;
+__global__ void __launch_bounds__(256)
+beam_step_kernel(const float* __restrict__ scores, long long row_stride, int ncls, const float* __restrict__ beam_scores,
+                 const uint8_t* __restrict__ completed, int eos, int first_step, int K, long long* __restrict__ prev_pos,
+                 long long* __restrict__ new_pos, float* __restrict__ new_scores) {
+  __shared__ float s_val[8];
+  __shared__ int s_idx[8];
+  __shared__ int s_win;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  float best[kBeamMax];
+  int bidx[kBeamMax];
+#pragma unroll
+  for (int i = 0; i < kBeamMax; ++i) { best[i] = -INFINITY; bidx[i] = 0x7fffffff; }
+  const int total = K * ncls;
+  for (int e = tid; e < total; e += blockDim.x) {
+    const int k = e / ncls, c = e - k * ncls;
+    const int row = b * K + k;
+    float v;
+    if (first_step && k > 0) v = -INFINITY;
+    else if (completed && completed[row]) v = (c == eos) ? beam_scores[row] : -INFINITY;
+    else {
+      const float x = scores[(size_t)row * row_stride + c];
+      v = fminf(x, 0.f) - log1pf(__expf(-fabsf(x))) + beam_scores[row];
+    }
+    if (v > best[K - 1] || (v == best[K - 1] && e < bidx[K - 1])) {      // insert into the sorted local list
+      int j = K - 1;
+      while (j > 0 && (v > best[j - 1] || (v == best[j - 1] && e < bidx[j - 1]))) { best[j] = best[j - 1]; bidx[j] = bidx[j - 1]; --j; }
+      best[j] = v; bidx[j] = e;
+    }
+  }
+  int head = 0;                       // next unpopped entry of this thread's list
+  for (int r = 0; r < K; ++r) {
+    float v = head < K ? best[head] : -INFINITY;
+    int ix = head < K ? bidx[head] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, ix, o);
+      if (ov > v || (ov == v && oi < ix)) { v = ov; ix = oi; }
+    }
+    if ((tid & 31) == 0) { s_val[tid >> 5] = v; s_idx[tid >> 5] = ix; }
+    __syncthreads();
+    if (tid == 0) {
+      float bv = s_val[0]; int bi = s_idx[0];
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+        if (s_val[w] > bv || (s_val[w] == bv && s_idx[w] < bi)) { bv = s_val[w]; bi = s_idx[w]; }
+      s_win = bi;
+      const int out = b * K + r;
+      const int k = bi == 0x7fffffff ? 0 : bi / ncls;
+      prev_pos[out] = (long long)b * K + k;
+      new_pos[out] = bi == 0x7fffffff ? eos : bi - k * ncls;
+      new_scores[out] = bv;
+    }
+    __syncthreads();
+    if (head < K && bidx[head] == s_win) ++head;
+    __syncthreads();
+  }
+}
+
+// row-wise arg-max of a [rows, ncls] fp32 matrix (first maximum), and whether the target at that index is set:
+// the prediction step of the greedy decoder (sa_m4c.py:299-301) and a token-level hit count without moving the
+// [B, D, V+R] logits to the host (sam/datasets/metrics.py:26 reads only the arg-max)
+__global__ void __launch_bounds__(256)
+argmax_rows_kernel(const float* __restrict__ x, long long ld, int ncls, const float* __restrict__ targets, long long ldt,
+                   long long* __restrict__ idx_out, float* __restrict__ hit_out) {
+  __shared__ float s_val[8];
+  __shared__ int s_idx[8];
+  const long long row = blockIdx.x;
+  const float* xr = x + row * ld;
+  float v = -INFINITY;
+  int ix = 0x7fffffff;
+  for (int c = threadIdx.x; c < ncls; c += blockDim.x) {
+    const float u = xr[c];
+    if (ix == 0x7fffffff || u > v) { v = u; ix = c; }        // c ascends per thread: the first maximum stays
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, ix, o);
+    if (oi != 0x7fffffff && (ix == 0x7fffffff || ov > v || (ov == v && oi < ix))) { v = ov; ix = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { s_val[threadIdx.x >> 5] = v; s_idx[threadIdx.x >> 5] = ix; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (s_idx[w] != 0x7fffffff && (ix == 0x7fffffff || s_val[w] > v || (s_val[w] == v && s_idx[w] < ix))) { v = s_val[w]; ix = s_idx[w]; }
+    if (ix == 0x7fffffff) ix = 0;
+    idx_out[row] = ix;
+    if (hit_out) hit_out[row] = targets ? targets[row * ldt + ix] : 0.f;
+  }
+}
+
 // out[0:n] = a, out[n:2n] = b, out[2n:3n] = c (the three biases of the fused q|k|v projection)
 __global__ void concat3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
                                float* __restrict__ out, int n) {
@@ -1192,6 +1328,64 @@ int samk_cast_flat(const void* x, int x_dtype, void* y, int y_dtype, long long n
   SAMK_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "buffers must be 16-byte aligned");
   if (!n) return SAMK_OK;
   cast_flat_kernel<<<grid_for(n / 4 + 1, 1024), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, y, y_dtype, n);
+  return check_launch(__func__);
+}
+
+int samk_row_segments_f32(float* joint, float* const* segs, const int* rows, const int* offs, int n_seg, int B, int L, int d,
+                          int to_joint, void* stream) {
+  SAMK_REQUIRE(joint && segs && rows && offs && n_seg >= 1 && n_seg <= 4 && B >= 0 && L >= 0, "bad argument");
+  SAMK_REQUIRE(d > 0 && d % 4 == 0 && al16(joint), "d must be a multiple of 4, 16-byte aligned buffers");
+  RowSegments sg;
+  long long total = 0;
+  for (int k = 0; k < 4; ++k) {
+    sg.ptr[k] = k < n_seg ? segs[k] : nullptr; sg.rows[k] = k < n_seg ? rows[k] : 0; sg.off[k] = k < n_seg ? offs[k] : 0;
+    if (k < n_seg) {
+      SAMK_REQUIRE(rows[k] >= 0 && offs[k] >= 0 && offs[k] + rows[k] <= L && (rows[k] == 0 || (segs[k] && al16(segs[k]))), "bad segment");
+      total += rows[k];
+    }
+  }
+  sg.n = n_seg;
+  if (!B || !total) return SAMK_OK;
+  row_segments_kernel<<<grid_for((long long)B * total * (d / 4), 1024), 256, 0, (cudaStream_t)stream>>>(joint, sg, B, L, d / 4, to_joint);
+  return check_launch(__func__);
+}
+
+int samk_key_valid(const long long* q_mask, const long long* obj_mask, const long long* ocr_mask, uint8_t* out, int B, int T,
+                   int O, int R, int D, void* stream) {
+  SAMK_REQUIRE(out && B >= 0 && T >= 0 && O >= 0 && R >= 0 && D >= 0, "bad argument");
+  SAMK_REQUIRE((T == 0 || q_mask) && (O == 0 || obj_mask) && (R == 0 || ocr_mask), "null mask");
+  const long long n = (long long)B * (T + O + R + D);
+  if (!n) return SAMK_OK;
+  key_valid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(q_mask, obj_mask, ocr_mask, out, B, T, O, R, D);
+  return check_launch(__func__);
+}
+
+int samk_memset0(void* p, long long bytes, void* stream) {
+  SAMK_REQUIRE(p && bytes >= 0, "bad argument");
+  if (!bytes) return SAMK_OK;
+  if (cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)stream) != cudaSuccess) {
+    set_error("%s: %s", __func__, cudaGetErrorString(cudaGetLastError()));
+    return SAMK_ERR_CUDA;
+  }
+  return SAMK_OK;
+}
+
+int samk_beam_step(const float* scores, long long row_stride, int ncls, const float* beam_scores, const uint8_t* completed,
+                   int eos, int first_step, int B, int K, long long* prev_pos, long long* new_pos, float* new_scores, void* stream) {
+  SAMK_REQUIRE(scores && beam_scores && prev_pos && new_pos && new_scores && B >= 0 && ncls > 0, "bad argument");
+  SAMK_REQUIRE(K >= 1 && K <= kBeamMax, "beam size must be in 1..16");
+  SAMK_REQUIRE((long long)K * ncls < 0x7fffffffLL, "too many candidates per sample");
+  if (!B) return SAMK_OK;
+  beam_step_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(scores, row_stride, ncls, beam_scores, completed, eos, first_step, K,
+                                                       prev_pos, new_pos, new_scores);
+  return check_launch(__func__);
+}
+
+int samk_argmax_rows(const float* x, long long ld, long long rows, int ncls, const float* targets, long long ldt, long long* idx_out,
+                     float* hit_out, void* stream) {
+  SAMK_REQUIRE(x && idx_out && rows >= 0 && ncls > 0 && rows < 0x7fffffffLL, "bad argument");
+  if (!rows) return SAMK_OK;
+  argmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, ld, ncls, targets, ldt, idx_out, hit_out);
   return check_launch(__func__);
 }
 

@@ -30,7 +30,11 @@ class FlatGradBuffer(object):
             off += n
 
     def zero(self):
-        self.flat.zero_()
+        if self.flat.is_cuda:
+            from . import ops
+            ops.zero_(self.flat)          # stream-ordered memset (a memset node in a captured step)
+        else:
+            self.flat.zero_()
         # autograd accumulates in place into existing .grad tensors; re-attach in case a caller
         # replaced them (e.g. optimizer.zero_grad(set_to_none=True)).
         off = 0

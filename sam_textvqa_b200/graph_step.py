@@ -33,6 +33,7 @@ class GraphedTrainStep(object):
         self.static = self._clone(example_batch)
         self.replays = 0
         self.graph = None
+        self._zero_stream = None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -64,7 +65,14 @@ class GraphedTrainStep(object):
     def _eager_step(self):
         # first node of the captured step: new dropout salt for this replay, computed and installed on the device
         check(lib().samk_advance_dropout_salt(stream_ptr()), "advance salt")
-        self.grads.zero()
+        # the 387 MB gradient buffer is cleared on its own stream beside the forward pass (a parallel branch of the
+        # captured graph) and joined before the backward pass starts accumulating into it
+        main = torch.cuda.current_stream()
+        if self._zero_stream is None:
+            self._zero_stream = torch.cuda.Stream()
+        self._zero_stream.wait_stream(main)
+        with torch.cuda.stream(self._zero_stream):
+            self.grads.zero()
         if self.allreduce == "overlap":
             self.grads.begin_step()
         bd = dict(self.static)
@@ -72,6 +80,7 @@ class GraphedTrainStep(object):
             bd["spatial_adj_matrices"] = dict(bd["spatial_adj_matrices"])
         scores = self.model(bd)["textvqa_scores"]
         loss = self.loss_fn(scores, bd)
+        main.wait_stream(self._zero_stream)
         loss.backward()
         if self.allreduce == "overlap":
             self.grads.finish_step()

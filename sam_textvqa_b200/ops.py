@@ -39,6 +39,7 @@ _ATTN_IMPL = int(os.environ.get("SAMK_ATTN_IMPL", "0"))
 launch_count = 0  # kernels launched through this module (bench.py reports it)
 gemm_profile = None  # bench.py: list collecting (start_event, end_event, algorithmic_flops, (M, N, K, a_mn, b_mn)) per GEMM launch
 grad_ready_hook = None  # dp.FlatGradBuffer.enable_overlap: called with the parameters a backward op has just finished
+launch_log = None    # bench.py --profile-only: list collecting ("gemm", M, N, K, a_mn, b_mn) / ("attn_fwd" | "attn_bwd", L) in launch order
 attn_profile = None  # bench.py: list collecting (kind, L, start_event, end_event, algorithmic_bytes, dense_flops) per launch
 
 
@@ -96,7 +97,7 @@ def _gbuf(p):
     if (direct_grad_accumulation and g is not None and g.dtype == torch.float32 and g.is_contiguous()
             and g.shape == p.shape and g.device == p.device):
         return g, True
-    return torch.zeros_like(p, dtype=torch.float32), False
+    return zeros(p.shape, torch.float32, p.device), False
 
 
 def _ret(buf_direct):
@@ -403,6 +404,8 @@ def gemm(a, a_mn, b, b_mn, M, N, K, out, bias=None, act=0, pre=None, aux=None, d
     ep.atomic_add = 1 if (accumulate or split_k > 1) else 0
     if out_parts is not None:       # (rows per part, out1, out2): M = 3 * rows, destinations out / out1 / out2
         ep.part_rows, ep.out_part1, ep.out_part2 = out_parts[0], out_parts[1].data_ptr(), out_parts[2].data_ptr()
+    if launch_log is not None:
+        launch_log.append(("gemm", int(M), int(N), int(K), bool(a_mn), bool(b_mn)))
     if gemm_profile is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -641,7 +644,7 @@ class PrevPredFn(torch.autograd.Function):
         prev, cls_w, ocr_in, pos, type_, ag, ab, og, ob, eg, eb = ctx.saved_tensors
         B, D, V, R, d = ctx.dims
         dout = dout.contiguous()
-        gs = [_gbuf(t) if t.is_leaf else (torch.zeros_like(t), False)
+        gs = [_gbuf(t) if t.is_leaf else (zeros(t.shape, torch.float32, t.device), False)
               for t in (cls_w, ocr_in, pos, type_, ag, ab, og, ob, eg, eb)]
         grads = [g[0] for g in gs]
         ln6 = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in (ag, ab, og, ob, eg, eb)])
@@ -730,6 +733,8 @@ def attention_fwd(qkv, valid, rel, dims, spatial, quad_mask, p, drop, allow=None
     if attn_profile is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+    if launch_log is not None:
+        launch_log.append(("attn_fwd", int(L)))
     check(lib().samk_attn_fwd(ctypes.byref(ap), _ATTN_IMPL, stream_ptr()), "attn_fwd")
     if attn_profile is not None:
         ev1.record()
@@ -763,6 +768,8 @@ def attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p
     if attn_profile is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+    if launch_log is not None:
+        launch_log.append(("attn_bwd", int(L)))
     check(lib().samk_attn_bwd(ctypes.byref(ap), _ATTN_IMPL, stream_ptr()), "attn_bwd")
     if attn_profile is not None:
         ev1.record()
@@ -771,6 +778,77 @@ def attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p
         attn_profile.append(("bwd", L, ev0, ev1, B * (8 * L * H * 64 * 2 + 2 * H * L * 4) + mask_b, 10.0 * B * L * L * H * 64))
     _count(4 if dq_accum is not None else 2)   # prep (+ memset) + main kernel (+ dq conversion)
     return dqkv
+
+
+def zeros(shape, dtype, device):
+    """zero-filled tensor through a stream-ordered memset (a memset node in a captured step, not an aten fill kernel)"""
+    t = torch.empty(shape, dtype=dtype, device=device)
+    check(lib().samk_memset0(ptr(t), t.numel() * t.element_size(), stream_ptr()), "memset0")
+    return t
+
+
+def zero_(t):
+    assert t.is_contiguous()
+    check(lib().samk_memset0(ptr(t), t.numel() * t.element_size(), stream_ptr()), "memset0")
+    return t
+
+
+def _row_segments(joint, segs, offs, to_joint):
+    """segs: contiguous fp32 [B, rows_k, d] tensors; offs: first row of each inside joint [B, L, d]"""
+    B, L, d = joint.shape
+    n = len(segs)
+    ptrs = (ctypes.c_void_p * 4)(*([t.data_ptr() for t in segs] + [None] * (4 - n)))
+    rows = (ctypes.c_int * 4)(*([t.shape[1] for t in segs] + [0] * (4 - n)))
+    offa = (ctypes.c_int * 4)(*(list(offs) + [0] * (4 - n)))
+    check(lib().samk_row_segments_f32(ptr(joint), ptrs, rows, offa, n, B, L, d, 1 if to_joint else 0, stream_ptr()), "row_segments")
+    _count()
+
+
+class JoinFn(torch.autograd.Function):
+    """[txt ; obj ; ocr ; dec] along the token axis (MMT.forward, sa_m4c.py:790) in one launch; the backward hands every
+    segment its contiguous gradient in one launch (instead of four strided slice copies)."""
+
+    @staticmethod
+    def forward(ctx, *segs):
+        _cuda(*segs)
+        segs = [t.float().contiguous() for t in segs]
+        B, d = segs[0].shape[0], segs[0].shape[2]
+        offs, L = [], 0
+        for t in segs:
+            offs.append(L)
+            L += t.shape[1]
+        out = torch.empty(B, L, d, dtype=torch.float32, device=segs[0].device)
+        _row_segments(out, segs, offs, True)
+        ctx.meta = ([t.shape[1] for t in segs], offs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        rows, offs = ctx.meta
+        dout = dout.contiguous()
+        B, L, d = dout.shape
+        outs = [torch.empty(B, r, d, dtype=torch.float32, device=dout.device) for r in rows]
+        _row_segments(dout, outs, offs, False)
+        return tuple(outs)
+
+
+def join_segments(*segs):
+    return JoinFn.apply(*segs)
+
+
+def key_valid_bytes(q_mask, obj_mask, ocr_mask, D):
+    """uint8 [B, T+O+R+D] key-valid map of MMT.forward (sa_m4c.py:793-795) from the int64 masks of the batch"""
+    def m(t):
+        return None if t is None else t.long().contiguous()
+    q_mask, obj_mask, ocr_mask = m(q_mask), m(obj_mask), m(ocr_mask)
+    _cuda(q_mask, obj_mask, ocr_mask)
+    B, T = q_mask.shape
+    O = obj_mask.shape[1] if obj_mask is not None else 0
+    R = ocr_mask.shape[1] if ocr_mask is not None else 0
+    out = torch.empty(B, T + O + R + D, dtype=torch.uint8, device=q_mask.device)
+    check(lib().samk_key_valid(ptr(q_mask), ptr(obj_mask), ptr(ocr_mask), ptr(out), B, T, O, R, D, stream_ptr()), "key_valid")
+    _count()
+    return out
 
 
 def _bias3(qb, kb, vb):
@@ -979,17 +1057,22 @@ def bert_layer_infer(x2, valid, rel, dims, spatial, quad_mask, eps, P, allow, ca
 # ---- output heads + loss -------------------------------------------------------------------------------------
 class OutputFn(torch.autograd.Function):
     """scores = cat[classifier(dec), OcrPtrNet(dec, ocr, mask)] written into one [B,D,V+R] buffer
-    (sa_m4c.py:270-278, 878-897)."""
+    (sa_m4c.py:270-278, 878-897).  Takes the whole MMT output [B,L,d] and the row ranges of its OCR / decoder
+    segments (sa_m4c.py:852-862): the rows are gathered, and their gradients scattered into the gradient of the whole
+    sequence, by one launch each (no strided slice copies, no gradient adds on the autograd side)."""
 
     @staticmethod
-    def forward(ctx, dec, ocr, ocr_mask, cw, cb, qw, qb, kw, kb):
-        _cuda(dec, ocr, cw)
-        B, D, d = dec.shape
-        R = ocr.shape[1]
+    def forward(ctx, seq, ocr_off, R, D, ocr_mask, cw, cb, qw, qb, kw, kb):
+        _cuda(seq, cw)
+        seq = seq.float().contiguous()
+        B, L, d = seq.shape
         V, dq = cw.shape[0], qw.shape[0]
-        dev = dec.device
-        dec2 = dec.contiguous().view(B * D, d)
-        ocr2 = ocr.contiguous().view(B * R, d)
+        dev = seq.device
+        ocr = torch.empty(B, R, d, dtype=torch.float32, device=dev)
+        dec = torch.empty(B, D, d, dtype=torch.float32, device=dev)
+        _row_segments(seq, [ocr, dec], [ocr_off, L - D], False)
+        dec2 = dec.view(B * D, d)
+        ocr2 = ocr.view(B * R, d)
         ocr_mask = ocr_mask.long().contiguous()      # any mask dtype (the reference multiplies it as a float, sa_m4c.py:879)
         scores = torch.empty(B * D, V + R, dtype=torch.float32, device=dev)
         # the vocabulary and pointer projections run as 3-term splits in every precision mode: they are 0.3 % of the
@@ -1004,6 +1087,7 @@ class OutputFn(torch.autograd.Function):
                                         stream_ptr()), "ptr_scores_fwd")
         _count()
         ctx.dims = (B, D, R, V, d, dq)
+        ctx.seq_meta = (L, ocr_off)
         ctx.bias_refs = (cb, qb, kb)
         ctx.save_for_backward(dec2, ocr2, q, k, cw, qw, kw)
         return scores.view(B, D, V + R)
@@ -1044,7 +1128,10 @@ class OutputFn(torch.autograd.Function):
         gemm(operand(dk_a, "a", True, fmt="bf16"), True, ocr_mn, True, dq, d, B * R, Gkw, accumulate=True)
         colsum_into(dk_, Gkb)
         _grads_done(cw, cb, qw, qb, kw, kb)
-        return (ddec2.view(B, D, d), docr.view(B, R, d), None) + tuple(_ret(x) for x in G)
+        L, ocr_off = ctx.seq_meta
+        dseq = zeros((B, L, d), torch.float32, dev)
+        _row_segments(dseq, [docr.view(B, R, d), ddec2.view(B, D, d)], [ocr_off, L - D], True)
+        return (dseq, None, None, None, None) + tuple(_ret(x) for x in G)
 
 
 class BceLossFn(torch.autograd.Function):
@@ -1072,6 +1159,38 @@ class BceLossFn(torch.autograd.Function):
         check(lib().samk_scale_inplace(ptr(ds), ds.numel(), ptr(g), stream_ptr()), "scale")
         _count()
         return ds, None, None
+
+
+def argmax_rows(scores, targets=None):
+    """Greedy tokens on the device: scores [..., ncls] fp32 -> int64 [...] (first maximum, like torch.argmax on distinct
+    values); with `targets` also returns hit[...] = targets[..., argmax] (a token-level accuracy count that never moves
+    the [B, D, V+R] logits to the host)."""
+    _cuda(scores, targets)
+    scores = scores.float().contiguous()
+    ncls = scores.shape[-1]
+    rows = scores.numel() // ncls
+    idx = torch.empty(scores.shape[:-1], dtype=torch.long, device=scores.device)
+    hit = None
+    if targets is not None:
+        targets = targets.float().contiguous()
+        hit = torch.empty(scores.shape[:-1], dtype=torch.float32, device=scores.device)
+    check(lib().samk_argmax_rows(ptr(scores), ncls, rows, ncls, ptr(targets), ncls, ptr(idx), ptr(hit), stream_ptr()), "argmax_rows")
+    _count()
+    return idx if targets is None else (idx, hit)
+
+
+def beam_step(scores_t, row_stride, beam_scores, completed, eos, first_step, B, K):
+    """One beam-search step (samk_beam_step); scores_t = scores[:, t, :] view of the contiguous [B K, D, ncls] logits."""
+    _cuda(scores_t, beam_scores)
+    ncls = scores_t.shape[-1]
+    dev = scores_t.device
+    prev_pos = torch.empty(B * K, dtype=torch.long, device=dev)
+    new_pos = torch.empty(B * K, dtype=torch.long, device=dev)
+    new_scores = torch.empty(B * K, dtype=torch.float32, device=dev)
+    check(lib().samk_beam_step(ptr(scores_t), row_stride, ncls, ptr(beam_scores), ptr(completed), int(eos), 1 if first_step else 0,
+                               B, K, ptr(prev_pos), ptr(new_pos), ptr(new_scores), stream_ptr()), "beam_step")
+    _count()
+    return prev_pos, new_pos, new_scores
 
 
 def bce_with_mask_loss(scores, targets, loss_mask):

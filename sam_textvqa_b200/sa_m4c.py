@@ -236,7 +236,7 @@ class TextBert(nn.Module):
     def forward(self, batch_dict):
         ids = batch_dict["question_indices"]
         x = self.embeddings(ids)
-        valid = batch_dict["question_mask"].to(torch.uint8).contiguous()
+        valid = ops.key_valid_bytes(batch_dict["question_mask"], None, None, 0)
         T = ids.shape[1]
         cache = {}
         for layer in self.encoder.layer:
@@ -333,11 +333,10 @@ class MMT(nn.Module):
     def forward(self, batch_dict, fixed_ans_emb):
         dec_emb = self.prev_pred_embeddings(fixed_ans_emb, batch_dict["ocr_mmt_in"], batch_dict["train_prev_inds"])
         txt, obj, ocr = batch_dict["text_bert_emb"], batch_dict["obj_mmt_in"], batch_dict["ocr_mmt_in"]
-        x = torch.cat([txt, obj, ocr, dec_emb], dim=1)
+        x = ops.join_segments(txt, obj, ocr, dec_emb)
         T, O, R, D = txt.size(1), obj.size(1), ocr.size(1), dec_emb.size(1)
         dev = x.device
-        key_valid = torch.cat([batch_dict["question_mask"], batch_dict["pad_obj_mask"], batch_dict["pad_ocr_mask"],
-                               torch.zeros(x.size(0), D, dtype=torch.long, device=dev)], dim=1).to(torch.uint8).contiguous()
+        key_valid = ops.key_valid_bytes(batch_dict["question_mask"], batch_dict["pad_obj_mask"], batch_dict["pad_ocr_mask"], D)
         rel_cache = batch_dict.setdefault("_samk_rel_bits", {})
 
         def rel_lookup(key):
@@ -534,14 +533,17 @@ class SAM4C(nn.Module):
                 batch_dict[k] = v.to(dev, non_blocking=True)
 
     def forward(self, batch_dict, use_beam_search=False):
-        if use_beam_search:
-            raise NotImplementedError("beam search is disabled in the reference (train.py:222, README.md:68-69)")
+        if use_beam_search and (self.training or torch.is_grad_enabled()):
+            raise RuntimeError("beam search is an inference path: call model.eval() and run under torch.no_grad()")
         self._to_device(batch_dict)
         ops.begin_forward()
         batch_dict.pop("_samk_rel_bits", None)
         self._forward_obj_encoding(batch_dict)
         self._forward_ocr_encoding(batch_dict)
-        self._forward_mmt_and_output(batch_dict)
+        if use_beam_search:
+            self._forward_beam_search(batch_dict)
+        else:
+            self._forward_mmt_and_output(batch_dict)
         if self.use_aux_heads:
             self._forward_aux(batch_dict)
         return {"textvqa_scores": batch_dict["scores"]}
@@ -603,8 +605,11 @@ class SAM4C(nn.Module):
 
     def _forward_output(self, batch_dict):
         p = self.ocr_ptr_net
+        seq = batch_dict["mmt_seq_output"]
+        R, D = batch_dict["mmt_ocr_output"].size(1), batch_dict["mmt_dec_output"].size(1)
+        ocr_off = seq.size(1) - D - R                          # [txt ; obj ; ocr ; dec] (sa_m4c.py:852-862)
         batch_dict["scores"] = ops.OutputFn.apply(
-            batch_dict["mmt_dec_output"], batch_dict["mmt_ocr_output"], batch_dict["pad_ocr_mask"],
+            seq, ocr_off, R, D, batch_dict["pad_ocr_mask"],
             self.classifier.weight, self.classifier.bias, p.query.weight, p.query.bias, p.key.weight, p.key.bias)
 
     def _forward_mmt_and_output(self, batch_dict):
@@ -621,7 +626,7 @@ class SAM4C(nn.Module):
         for _ in range(dec_step_num):
             self._forward_mmt(batch_dict)
             self._forward_output(batch_dict)
-            argmax_inds = batch_dict["scores"].argmax(dim=-1)
+            argmax_inds = ops.argmax_rows(batch_dict["scores"].detach())
             batch_dict["train_prev_inds"][:, 1:] = argmax_inds[:, :-1]
 
     def _greedy_decode_cached(self, batch_dict):
@@ -646,8 +651,7 @@ class SAM4C(nn.Module):
         T, O, R = txt.size(1), obj.size(1), ocr.size(1)
         L, d = T + O + R + D, txt.size(2)
         dev = txt.device
-        key_valid = torch.cat([batch_dict["question_mask"], batch_dict["pad_obj_mask"], batch_dict["pad_ocr_mask"],
-                               torch.zeros(B, D, dtype=torch.long, device=dev)], dim=1).to(torch.uint8).contiguous()
+        key_valid = ops.key_valid_bytes(batch_dict["question_mask"], batch_dict["pad_obj_mask"], batch_dict["pad_ocr_mask"], D)
         rel_cache = batch_dict.setdefault("_samk_rel_bits", {})
 
         def rel_lookup(key):
@@ -660,7 +664,7 @@ class SAM4C(nn.Module):
         for step in range(D):
             dec_emb = mmt.prev_pred_embeddings(self.classifier.weight, ocr, prev)
             if step == 0:
-                x = torch.cat([txt, obj, ocr, dec_emb], dim=1).reshape(B * L, d).contiguous()
+                x = ops.join_segments(txt, obj, ocr, dec_emb).view(B * L, d)
                 out, caches = _encoder_infer(mmt.encoder, x, key_valid, rel_lookup, dims, mask_cache)
                 seq = out.view(B, L, d)
             else:
@@ -670,7 +674,75 @@ class SAM4C(nn.Module):
             batch_dict.update({"mmt_seq_output": seq, "mmt_txt_output": seq[:, :T],
                                "mmt_ocr_output": seq[:, T + O:T + O + R], "mmt_dec_output": seq[:, L - D:]})
             self._forward_output(batch_dict)
-            prev[:, 1:] = batch_dict["scores"].argmax(dim=-1)[:, :-1]
+            prev[:, 1:] = ops.argmax_rows(batch_dict["scores"])[:, :-1]
+
+    def _forward_beam_search(self, batch_dict):
+        """Beam-search decoding (sa_m4c.py:304-314 + sam/beam_search.py), on the cached decoder: the rows of the question /
+        object / OCR segments do not depend on the decoded prefix, so they are encoded once (step 0), not once per
+        step; every beam's decoder rows are recomputed from its current prefix each step, and since the encoder rows
+        of a sample's beams are identical, re-ordering the beams only permutes the prefixes (the caches stay put).  Selection per step is samk_beam_step (log sigmoid + accumulated beam score, completed
+        beams continue with EOS only, step 0 looks at one beam per sample).
+        Outputs as the reference's evaluator reads them (evaluator.py:137-160): `complete_seqs` [B*K, D] (BOS-first
+        token sequences), `topkscores` [B*K, 1], `train_prev_inds` = the sequences, `scores` of the last pass.
+        Two defects of the reference's disabled decoder are not reproduced: `indices / vocab_size` is an integer
+        division here (beam_search.py:109 yields fractional beam indices on torch >= 1.5) and a beam's score is the
+        accumulated log-probability once (beam_search.py:124 adds the parent's score a second time)."""
+        mmt = self.mmt
+        K = int(getattr(self, "beam_size", 1) or 1)
+        eos = int(getattr(registry, "EOS_IDX", 2))
+        B, D = batch_dict["train_prev_inds"].shape
+
+        def rep(v):
+            return v.repeat_interleave(K, dim=0) if torch.is_tensor(v) else v
+        prev = batch_dict["train_prev_inds"].new_zeros((B * K, D))
+        prev[:, 0] = registry.BOS_IDX
+        text_bert_out = self.text_bert(batch_dict)
+        if not isinstance(self.text_bert_out_linear, nn.Identity):
+            lin = self.text_bert_out_linear
+            text_bert_out = ops.linear(text_bert_out.reshape(-1, text_bert_out.shape[-1]), lin.weight, lin.bias).view(B, -1, lin.weight.shape[0])
+        batch_dict["text_bert_emb"] = text_bert_out
+        txt, obj, ocr = rep(text_bert_out), rep(batch_dict["obj_mmt_in"]), rep(batch_dict["ocr_mmt_in"])
+        T, O, R = txt.size(1), obj.size(1), ocr.size(1)
+        L, d = T + O + R + D, txt.size(2)
+        dev = txt.device
+        key_valid = ops.key_valid_bytes(rep(batch_dict["question_mask"]), rep(batch_dict["pad_obj_mask"]),
+                                        rep(batch_dict["pad_ocr_mask"]), D)
+        ocr_mask = rep(batch_dict["pad_ocr_mask"])
+        rel_cache = {}
+
+        def rel_lookup(key):
+            if key not in rel_cache:
+                rel_cache[key] = _relation_bits(batch_dict, key, dev).repeat_interleave(K, dim=0).contiguous()
+            return rel_cache[key]
+
+        dims = (B * K, L, T, O + R, D)
+        beam_scores = torch.zeros(B * K, dtype=torch.float32, device=dev)
+        completed = None
+        mask_cache, caches, seq = {}, None, None
+        p = self.ocr_ptr_net
+        for t in range(D):
+            dec_emb = mmt.prev_pred_embeddings(self.classifier.weight, ocr, prev)
+            if t == 0:
+                x = ops.join_segments(txt, obj, ocr, dec_emb).view(B * K * L, d)
+                out, caches = _encoder_infer(mmt.encoder, x, key_valid, rel_lookup, dims, mask_cache)
+                seq = out.view(B * K, L, d)
+            else:
+                out, caches = _encoder_infer(mmt.encoder, dec_emb.reshape(B * K * D, d).contiguous(), key_valid, rel_lookup,
+                                             dims, mask_cache, caches)
+                seq[:, L - D:, :] = out.view(B * K, D, d)
+            scores = ops.OutputFn.apply(seq, T + O, R, D, ocr_mask, self.classifier.weight, self.classifier.bias,
+                                        p.query.weight, p.query.bias, p.key.weight, p.key.bias)
+            ncls = scores.shape[-1]
+            prev_pos, new_pos, beam_scores = ops.beam_step(scores[:, t, :], D * ncls, beam_scores, completed, eos, t == 0, B, K)
+            prev = prev[prev_pos]
+            if t + 1 < D:
+                prev[:, t + 1] = new_pos
+                completed = (prev[:, t + 1] == eos).to(torch.uint8).contiguous()
+                if bool(completed.all()):
+                    break
+        batch_dict.update({"mmt_seq_output": seq, "mmt_txt_output": seq[:, :T], "mmt_ocr_output": seq[:, T + O:T + O + R],
+                           "mmt_dec_output": seq[:, L - D:], "scores": scores, "train_prev_inds": prev,
+                           "complete_seqs": prev, "topkscores": beam_scores.view(-1, 1)})
 
     def _forward_aux(self, batch_dict):
         T = batch_dict["question_mask"].size(-1)

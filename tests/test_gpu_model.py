@@ -362,3 +362,75 @@ def test_on_device_batch_preparation_matches_dataset_prepared_masks(golden):
     assert torch.equal(s1, s2)
     assert torch.equal(b1["train_prev_inds"], b2["train_prev_inds"])      # greedy tokens
     model.train()
+
+
+def test_beam_search_decoder_on_the_cached_decoder(golden):
+    """SURVEY 8f rank 4 (sa_m4c.py:304-314, sam/beam_search.py).  The reference ships its decoder disabled (train.py:222),
+    so there is no working oracle: beam size 1 must reproduce the greedy tokens exactly, a wider beam must return, per
+    sample, K distinct hypotheses sorted by score whose best is at least as likely as the greedy sequence, and the
+    per-step selection kernel is checked against torch.topk on the same candidate scores."""
+    from sam_textvqa_b200 import ops
+    g, mmt, tb, _, _ = golden
+    from sam_textvqa_b200.registry import registry
+    registry.EOS_IDX = 2
+    # narrow pointer-net weights: the golden model's copy logits reach +-100, where log sigmoid saturates in fp32 and
+    # the beam criterion (sam/beam_search.py:90) can no longer tell candidates apart that the greedy arg-max can
+    state = synth.seeded_state(sam4c_state_shapes(mmt, tb, V), 0, ptr_std=0.02)
+    model = _model(mmt, tb, state).eval()
+    ops.clear_weight_cache()
+    with torch.no_grad():
+        bg = golden_batch(g)
+        greedy_scores = model(bg)["textvqa_scores"]
+        greedy = bg["train_prev_inds"].clone()                     # BOS + the first D-1 greedy tokens
+        model.set_beam_size(1)
+        b1 = golden_batch(g)
+        model(b1, use_beam_search=True)
+        assert b1["complete_seqs"].shape == greedy.shape and b1["topkscores"].shape == (greedy.shape[0], 1)
+        # identical up to (and including) the first EOS: a completed beam pads with EOS, greedy keeps decoding
+        for row_b, row_g in zip(b1["complete_seqs"].tolist(), greedy.tolist()):
+            n = row_g.index(2) + 1 if 2 in row_g[1:] else len(row_g)
+            assert row_b[:n] == row_g[:n]
+        K = 3
+        model.set_beam_size(K)
+        b3 = golden_batch(g)
+        model(b3, use_beam_search=True)
+        B, D = greedy.shape
+        seqs, sc = b3["complete_seqs"].view(B, K, D), b3["topkscores"].view(B, K)
+        assert (sc[:, :-1] >= sc[:, 1:]).all()
+        assert all(len({tuple(s) for s in seqs[b].tolist()}) == K for b in range(B))
+        ls = torch.nn.functional.logsigmoid(greedy_scores)
+        for b in range(B):                                          # log-probability of the greedy sequence, EOS-terminated
+            tot, row = 0.0, greedy[b].tolist()
+            for t in range(D):
+                tok = row[t + 1] if t + 1 < D else int(greedy_scores[b, t].argmax())
+                tot += float(ls[b, t, tok])
+                if tok == 2:
+                    break
+            assert float(sc[b, 0]) >= tot - 1e-3, (b, float(sc[b, 0]), tot)
+    # the selection kernel against torch.topk
+    gen = torch.Generator().manual_seed(3)
+    Bq, Kq, ncls = 5, 4, 777
+    s = (3 * torch.randn(Bq * Kq, 2, ncls, generator=gen)).to(DEV)
+    beam = torch.randn(Bq * Kq, generator=gen).to(DEV)
+    done = (torch.rand(Bq * Kq, generator=gen) < 0.3).to(torch.uint8).to(DEV)
+    pp, npos, val = ops.beam_step(s[:, 1, :], 2 * ncls, beam, done, 2, False, Bq, Kq)
+    cur = torch.nn.functional.logsigmoid(s[:, 1, :]) + beam[:, None]
+    fin = torch.full_like(cur, float("-inf"))
+    fin[:, 2] = beam
+    cur = torch.where(done.bool()[:, None], fin, cur)
+    v, i = cur.view(Bq, Kq * ncls).topk(Kq, dim=-1)
+    assert torch.allclose(val.view(Bq, Kq), v, atol=1e-5)
+    assert torch.equal(npos.view(Bq, Kq), i % ncls)
+    assert torch.equal(pp.view(Bq, Kq), i // ncls + torch.arange(Bq, device=DEV)[:, None] * Kq)
+    model.train()
+
+
+def test_device_argmax_and_token_hits_match_torch():
+    from sam_textvqa_b200 import ops
+    gen = torch.Generator().manual_seed(9)
+    s = torch.randn(7, 12, 5050, generator=gen).to(DEV)
+    s[0, 0, 17] = s[0, 0, 4000] = 99.0                              # a tie: the first maximum wins
+    t = (torch.rand(7, 12, 5050, generator=gen) < 0.01).float().to(DEV)
+    idx, hit = ops.argmax_rows(s, t)
+    assert torch.equal(idx, s.argmax(-1)) and int(idx[0, 0]) == 17
+    assert torch.equal(hit, torch.gather(t, -1, idx[..., None])[..., 0])

@@ -1,5 +1,3 @@
 cd /root/repo
-OUT=gpurun_out; TAG=r02e
-timeout 600 ncu --clock-control none --metrics gpu__time_duration.sum -c 6000 --csv --log-file $OUT/${TAG}_launches.csv python bench.py --profile-only > $OUT/${TAG}_launches.out 2>&1
-python tools/summarize_launches.py $OUT/${TAG}_launches.csv 1 > $OUT/${TAG}_launches_summary.txt 2>&1
-head -60 $OUT/${TAG}_launches_summary.txt; gzip -f $OUT/${TAG}_launches.csv
+OUT=gpurun_out
+timeout 900 python -m pytest tests/test_gpu_model.py -m gpu -x -q -k "beam or argmax or greedy or cached" > $OUT/r02h_pytest.log 2>&1; echo "rc=$?" >> $OUT/r02h_pytest.log; tail -30 $OUT/r02h_pytest.log

@@ -16,6 +16,7 @@ ap.add_argument("--B", type=int, default=128)
 ap.add_argument("--p", type=float, default=0.1)
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--context", type=int, default=3)
+ap.add_argument("--only", type=int, default=0, help="one point of the sweep: number of objects O (B=64)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 HBM = 6514.2
@@ -54,7 +55,9 @@ def run(B, T, O, R, D, spatial=True):
           % (B, L, T, O, R, D, spatial, args.p, tf, bytes_f / tf / 1e3, 100 * bytes_f / tf / 1e3 / HBM, HBM, fl_f / tf / 1e6,
              tb, bytes_b / tb / 1e3, 100 * bytes_b / tb / 1e3 / HBM, fl_b / tb / 1e6), flush=True)
 
-if args.sweep:
+if args.only:
+    run(64, 20, args.only, 50, 12)
+elif args.sweep:
     for O in (36, 186, 442, 954):          # joint tokens 106 / 256 / 512 / 1024 (BASELINE config 5), B=64
         run(64, 20, O, 50, 12)
 else:

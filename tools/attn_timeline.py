@@ -9,17 +9,18 @@ from sam_textvqa_b200.sa_m4c import pack_relation_bits
 dev = torch.device("cuda:0")
 B, T, O, R, D = 128, 20, 100, 50, 12
 A, L, H, d = O + R, T + O + R + D, 12, 768
-qkv = torch.randn(B * L, 3 * d, device=dev).bfloat16()
+qkv = torch.randn(B * L, 3 * d, device=dev).half()
 valid = torch.ones(B, L, dtype=torch.uint8, device=dev); valid[:, -D:] = 0
 dims = (B, L, H, T, A, D)
 allow = ops.build_attn_mask(valid, None, dims, False, 0)
 p = float(os.environ.get("P", "0.1"))
 bwd = os.environ.get("BWD", "0") == "1"
 w = torch.randn(B * L, d, device=dev).bfloat16()
+keep = ops.build_attn_keep(dims, p, (1, 1), dev) if p > 0 else None
 for _ in range(3):
-    ctx, lse = ops.attention_fwd(qkv, valid, None, dims, False, 0, p, (1, 1), allow)
+    ctx, lse = ops.attention_fwd(qkv, valid, None, dims, False, 0, p, (1, 1), allow, keep=keep)
     if bwd:
-        ops.attention_bwd(w, qkv, ctx, lse, valid, None, dims, False, 0, p, (1, 1), allow)
+        ops.attention_bwd(w, qkv, ctx, lse, valid, None, dims, False, 0, p, (1, 1), allow, keep=keep)
 torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 4096)()
 lib = _lib.lib()
@@ -32,8 +33,8 @@ if bwd:
     names = {20: "ew:top", 21: "ew:s_full", 22: "ew:computed", 23: "ew:stage_free", 24: "ew:arrived", 25: "ew:drained",
              26: "mma:top", 27: "mma:blk_done", 28: "mma:issued"}
     t0 = tl[20, 0]
-    for it in range(12):
-        print("block %d: " % it + "  ".join("%s=%d" % (names[s], tl[s, it] - t0) for s in sorted(names)))
+    for it in range(20):
+        print("sub %d: " % it + "  ".join("%s=%d" % (names[s], tl[s, it] - t0) for s in sorted(names)))
 else:
     t0 = tl[8, 0]
     for it in range(10):
