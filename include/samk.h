@@ -126,6 +126,8 @@ int samk_gemm_16(const void* A, int a_dtype, int a_mn_major, long long lda, cons
  * GEMM over the 3x longer K reproduces fp32 products to ~2^-16 ("bf16x3" parity mode). */
 int samk_cast_bf16(const float* x, long long ldx, void* y, long long ldy, int rows, int cols, void* stream);
 int samk_cast_16(const float* x, long long ldx, void* y, long long ldy, int y_dtype, int rows, int cols, void* stream);
+/* both 16-bit copies of an fp32 matrix in one pass (a weight: half for the forward product, bf16 for dgrad) */
+int samk_cast_dual(const float* x, long long ldx, void* y_f16, void* y_bf16, long long ldy, int rows, int cols, void* stream);
 /* contiguous copy between fp32 and a 16-bit format (either direction; e.g. the bf16 wire format of the gradient
  * all-reduce that replaces nn.DataParallel's reduction, train.py:111-112) */
 int samk_cast_flat(const void* x, int x_dtype, void* y, int y_dtype, long long n, void* stream);

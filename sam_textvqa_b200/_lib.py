@@ -57,6 +57,7 @@ SIGNATURES = {
                              ctypes.POINTER(GemmEpilogue), c_int, c_int, c_void_p]),
     "samk_cast_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p]),
     "samk_cast_16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
+    "samk_cast_dual": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p]),
     "samk_cast_flat": (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_void_p]),
     "samk_cast_scaled_f16": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
     "samk_split3_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),

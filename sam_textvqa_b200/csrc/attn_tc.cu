@@ -195,9 +195,12 @@ __device__ long long g_timeline[4096];
 #define TL_STAMP(slot, idx) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (idx) < 64) g_timeline[(slot) * 64 + (idx)] = clock64(); } while (0)
 // converged-warp variant (MMA issuer warps: elect.sync needs the warp reconverged afterwards)
 #define TL_STAMP_W(slot, idx) do { TL_STAMP(slot, idx); __syncwarp(); } while (0)
+// any warp of CTA 0 (per-warp arrival skew)
+#define TL_STAMP_ANY(slot, idx) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (idx) < 64 && (slot) < 64) g_timeline[(slot) * 64 + (idx)] = clock64(); } while (0)
 #else
 #define TL_STAMP(slot, idx) do { } while (0)
 #define TL_STAMP_W(slot, idx) do { } while (0)
+#define TL_STAMP_ANY(slot, idx) do { } while (0)
 #endif
 
 template <int KVT> struct Fwd2Cfg {
@@ -1154,12 +1157,15 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
   extern __shared__ uint8_t smem_raw3[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw3) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kBar);
-  uint64_t* in_full = bars; uint64_t* in_empty = bars + 1; uint64_t* s_full = bars + 2;   // s_full[2]
+  // Inputs are tracked per REGION so that the next item's tiles land as soon as the current item has read their
+  // buffers for the last time (the shared memory is full: no second set of input buffers).  Region 2 it = Q / dO16 of
+  // query tile it, region 2 jt + 1 = the K / V chunks of key tile jt.
+  uint64_t* reg_full = bars; uint64_t* reg_empty = bars + 4; uint64_t* s_full = bars + 8;   // reg_full[4], reg_empty[4], s_full[2]
   // sub_done[2], alternating per sub-block: S / dP of a sub-block are ready long before the slower warps finish the
   // previous one, so with a single barrier a fast warp's arrival for sub-block u+1 would complete the phase of u
   // early; with two, running two ahead is impossible (S / dP of u+2 are only produced after sub_done(u))
-  uint64_t* sub_done = bars + 4; uint64_t* stage_free = bars + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  uint64_t* sub_done = bars + 10; uint64_t* stage_free = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = a.L, H = a.H;
@@ -1176,7 +1182,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
 
   if (tid == 0) {
     ptx::prefetch_tensormap(&tmQKV128); ptx::prefetch_tensormap(&tmQKV64); ptx::prefetch_tensormap(&tmDO);
-    ptx::mbar_init(in_full, 1); ptx::mbar_init(in_empty, 1); ptx::mbar_init(&s_full[0], 1); ptx::mbar_init(&s_full[1], 1);
+    for (int r = 0; r < 4; ++r) { ptx::mbar_init(&reg_full[r], 1); ptx::mbar_init(&reg_empty[r], 1); }
+    ptx::mbar_init(&s_full[0], 1); ptx::mbar_init(&s_full[1], 1);
     ptx::mbar_init(&sub_done[0], 16); ptx::mbar_init(&sub_done[1], 16); ptx::mbar_init(stage_free, 1);
     ptx::fence_barrier_init();
   }
@@ -1194,16 +1201,20 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
       int iter = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++iter) {
         const int b = (int)__umulhi((uint32_t)item, magic_h), h = item - b * H;
-        mbar_wait_backoff(in_empty, (iter & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(in_full, n_t * 2 * 16384 + kv_chunks * 2 * 8192);
-        // in the order the first products need them
-        ptx::tma_load_2d(smem + SM::kQ, &tmQKV128, in_full, h * TDH, b * L);
-        for (int c = 0; c < kv_chunks; ++c) ptx::tma_load_2d(smem + SM::kK + c * 8192, &tmQKV64, in_full, (H + h) * TDH, b * L + c * 64);
-        ptx::tma_load_2d(smem + SM::kDO, &tmDO, in_full, h * TDH, b * L);
-        for (int c = 0; c < kv_chunks; ++c) ptx::tma_load_2d(smem + SM::kV + c * 8192, &tmQKV64, in_full, (2 * H + h) * TDH, b * L + c * 64);
-        if (n_t > 1) {
-          ptx::tma_load_2d(smem + SM::kQ + 16384, &tmQKV128, in_full, h * TDH, b * L + 128);
-          ptx::tma_load_2d(smem + SM::kDO + 16384, &tmDO, in_full, h * TDH, b * L + 128);
+        const uint32_t par = (uint32_t)(iter & 1) ^ 1u;
+        // regions in the order the products need them; each waits only for ITS buffers (released by the MMA warp right
+        // after the last product of the previous item that reads them)
+        for (int t = 0; t < n_t; ++t) {
+          const int rq = 2 * t, rk = 2 * t + 1;
+          const int c0 = 2 * t, nc = t < n_t - 1 ? 2 : n_last;            // K / V chunks of key tile t
+          mbar_wait_backoff(&reg_empty[rq], par);
+          ptx::mbar_arrive_expect_tx(&reg_full[rq], 2 * 16384);
+          ptx::tma_load_2d(smem + SM::kQ + t * 16384, &tmQKV128, &reg_full[rq], h * TDH, b * L + t * 128);
+          ptx::tma_load_2d(smem + SM::kDO + t * 16384, &tmDO, &reg_full[rq], h * TDH, b * L + t * 128);
+          mbar_wait_backoff(&reg_empty[rk], par);
+          ptx::mbar_arrive_expect_tx(&reg_full[rk], nc * 2 * 8192);
+          for (int c = c0; c < c0 + nc; ++c) ptx::tma_load_2d(smem + SM::kK + c * 8192, &tmQKV64, &reg_full[rk], (H + h) * TDH, b * L + c * 64);
+          for (int c = c0; c < c0 + nc; ++c) ptx::tma_load_2d(smem + SM::kV + c * 8192, &tmQKV64, &reg_full[rk], (2 * H + h) * TDH, b * L + c * 64);
         }
       }
     }
@@ -1224,26 +1235,39 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
       constexpr uint32_t idesc_q = ptx::make_idesc_16(128, 64, 0, 1, kFmtF16, kFmtF16);     // dQ: A = dS (K-major), B = K (MN-major)
       // k-step increments of the descriptor start-address field (bytes >> 4)
       constexpr uint64_t kStepK = 32 >> 4, kStepMN = 2048 >> 4;
+      int iter = 0; uint32_t cu = 0;
+      uint32_t have = 0;                                  // regions of the current item whose loads have been awaited
+      auto need = [&](int r) {
+        if (!((have >> r) & 1u)) {
+          mbar_wait_backoff(&reg_full[r], (uint32_t)(iter & 1));
+          ptx::tc_fence_after();
+          have |= 1u << r;
+        }
+      };
+      // last sub-block that reads a region (then its buffers are released to the producer)
+      const int last_q0 = (n_t - 1) * subs_full + n_last - 1, last_q1 = n_sub - 1;
+      const int last_k0 = n_t > 1 ? subs_full - 1 : n_sub - 1, last_k1 = n_sub - 1;
       auto issue_sdp = [&](int u) {
         int jt, it, jh, nh;
         decode_sub(u, jt, it, jh, nh);
+        need(2 * it);
+        need(2 * jt + 1);
         const uint32_t col = (uint32_t)(u & 1) * 128u;
         const uint32_t kb = (uint32_t)(jt * 2 + jh) * 8192u;               // 64-row chunk of K / V
         const uint64_t dq = ptx::make_smem_desc_sw128(sQ + it * 16384, 16, 1024), dk = ptx::make_smem_desc_sw128(sK + kb, 16, 1024);
         const uint64_t dg = ptx::make_smem_desc_sw128(sDO + it * 16384, 16, 1024), dv = ptx::make_smem_desc_sw128(sV + kb, 16, 1024);
         if (ptx::elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) ptx::umma_f16(tmem + col, dq + kk * kStepK, dk + kk * kStepK, idesc_s, kk > 0);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) ptx::umma_f16(tmem + col + 64, dg + kk * kStepK, dv + kk * kStepK, idesc_dp, kk > 0);
+          for (int kk = 0; kk < 4; ++kk) {      // the two accumulation chains alternate: consecutive MMAs are independent
+            ptx::umma_f16(tmem + col, dq + kk * kStepK, dk + kk * kStepK, idesc_s, kk > 0);
+            ptx::umma_f16(tmem + col + 64, dg + kk * kStepK, dv + kk * kStepK, idesc_dp, kk > 0);
+          }
           ptx::umma_commit(&s_full[u & 1]);
         }
         __syncwarp();
       };
-      int iter = 0; uint32_t cu = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++iter) {
-        mbar_wait_backoff(in_full, iter & 1);
-        ptx::tc_fence_after();
+        have = 0;
         issue_sdp(0);
         if (n_sub > 1) issue_sdp(1);
         for (int u = 0; u < n_sub; ++u, ++cu) {
@@ -1263,25 +1287,31 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
           // the products that release the staging tiles go first, the S / dP two sub-blocks ahead last
           if (ptx::elect_one()) {
             if (block_end) {
-              // block (jt, it) complete: dV_jt[j,d] += sum_i Pd[i,j] dO[i,d] ; dK_jt[j,d] += sum_i dS[i,j] Q[i,d]
+              // block (jt, it) complete: dV_jt[j,d] += sum_i Pd[i,j] dO[i,d] ; dK_jt[j,d] += sum_i dS[i,j] Q[i,d];
+              // the three accumulation chains (dV, dK, dQ) are interleaved so that consecutive MMAs are independent
 #pragma unroll
-              for (int kk = 0; kk < 8; ++kk)
+              for (int kk = 0; kk < 8; ++kk) {
                 ptx::umma_f16(tmem + kDVcol, a_p + kk * kStepMN, b_do + kk * kStepMN, idesc_dv, kk > 0 ? 1u : first_kv);
-#pragma unroll
-              for (int kk = 0; kk < 8; ++kk)
                 ptx::umma_f16(tmem + kDKcol, a_dst + kk * kStepMN, b_q + kk * kStepMN, idesc_dk, kk > 0 ? 1u : first_kv);
-            }
+                if (kk < 4)
+                  ptx::umma_f16(tmem + kDQcol + it * 64, a_ds + kk * kStepK, b_k + kk * kStepMN, idesc_q, kk > 0 ? 1u : first_q);
+              }
+              ptx::umma_commit(stage_free);
+            } else {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              ptx::umma_f16(tmem + kDQcol + it * 64, a_ds + kk * kStepK, b_k + kk * kStepMN, idesc_q, kk > 0 ? 1u : first_q);
-            if (block_end) ptx::umma_commit(stage_free);
+              for (int kk = 0; kk < 4; ++kk)
+                ptx::umma_f16(tmem + kDQcol + it * 64, a_ds + kk * kStepK, b_k + kk * kStepMN, idesc_q, kk > 0 ? 1u : first_q);
+            }
+            // buffers nobody reads any more in this item go back to the producer (next item's loads start now)
+            if (u == last_q0) ptx::umma_commit(&reg_empty[0]);
+            if (u == last_k0) ptx::umma_commit(&reg_empty[1]);
+            if (n_t > 1 && u == last_q1) ptx::umma_commit(&reg_empty[2]);
+            if (n_t > 1 && u == last_k1) ptx::umma_commit(&reg_empty[3]);
           }
           __syncwarp();
           if (u + 2 < n_sub) issue_sdp(u + 2);
           TL_STAMP_W(28, (int)cu);
         }
-        if (ptx::elect_one()) ptx::umma_commit(in_empty);
-        __syncwarp();
       }
     }
   } else {
@@ -1298,41 +1328,39 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
     // per-row scalars and allow bits of the next item are fetched one item ahead.  This thread's 16 key columns
     // of sub-block (jt, jh) are keys jt*128 + jh*64 + slice*16 .. +15: bits (jh*64 + slice*16) & 31 .. of word
     // 4 jt + 2 jh + slice/2 of its allow row; aw_nx[t][jt] holds them for jh = 0 (low half) and jh = 1 (high half)
-    float lse2_nx[2], dlt_nx[2];
-    uint32_t aw_nx[2][2], kw_nx[2][2];      // kw: dropout keep bits, same packing as the allow bits
+    // Row scalars (lse, delta) of the next item are fetched one item ahead; the allow / keep words one SUB-BLOCK ahead
+    // (two registers in flight instead of sixteen: an item-ahead prefetch of every word spilled, and a spill store
+    // right behind a load waits for the load).  Nothing touches a fetched value before the following sub-block / item.
+    float lse_raw[2], dlt_raw[2];
     auto fetch_rows = [&](int item_) {
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        lse2_nx[t] = INFINITY; dlt_nx[t] = 0.f; aw_nx[t][0] = aw_nx[t][1] = 0u; kw_nx[t][0] = kw_nx[t][1] = 0xffffffffu;
-      }
+      for (int t = 0; t < 2; ++t) { lse_raw[t] = INFINITY; dlt_raw[t] = 0.f; }
       if (item_ >= n_items) return;
       const int b_ = (int)__umulhi((uint32_t)item_, magic_h), h_ = item_ - b_ * H;
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const int i = t * 128 + lrow;
         if (t < n_t && i < L) {
-          lse2_nx[t] = __ldg(a.lse + ((size_t)b_ * H + h_) * L + i) * kLog2e;
-          dlt_nx[t] = __ldg(a.delta + ((size_t)b_ * H + h_) * L + i);
-          const uint32_t* ar = a.allow + (((size_t)b_ * a.Hm + (a.Hm == 1 ? 0 : h_)) * L + i) * a.W;
-#pragma unroll
-          for (int jt = 0; jt < 2; ++jt) {
-            if (jt >= n_t) continue;
-            uint32_t lo = 0u, hi = 0u;
-            const int w0 = 4 * jt + (slice >> 1), w1 = w0 + 2, sh = (slice & 1) * 16;
-            if (w0 < a.W) lo = (__ldg(ar + w0) >> sh) & 0xffffu;
-            if (w1 < a.W) hi = (__ldg(ar + w1) >> sh) & 0xffffu;
-            aw_nx[t][jt] = lo | (hi << 16);
-            if (a.keep) {
-              const uint32_t* kr = a.keep + (((size_t)b_ * H + h_) * L + i) * a.W;
-              uint32_t klo = 0u, khi = 0u;
-              if (w0 < a.W) klo = (__ldg(kr + w0) >> sh) & 0xffffu;
-              if (w1 < a.W) khi = (__ldg(kr + w1) >> sh) & 0xffffu;
-              kw_nx[t][jt] = klo | (khi << 16);
-            }
-          }
+          lse_raw[t] = __ldg(a.lse + ((size_t)b_ * H + h_) * L + i);
+          dlt_raw[t] = __ldg(a.delta + ((size_t)b_ * H + h_) * L + i);
         }
       }
     };
+    // this thread's 16 key columns of sub-block (jt, jh) are keys jt*128 + jh*64 + slice*16 .. +15: bits
+    // (slice & 1) * 16 .. of word 4 jt + 2 jh + slice / 2 of the allow / keep row of query row it*128 + lrow
+    uint32_t aw_nx = 0u, kw_nx = 0xffffffffu;
+    auto fetch_bits = [&](int item_, int u_) {
+      aw_nx = 0u; kw_nx = 0xffffffffu;
+      if (item_ >= n_items) return;
+      int jt_, it_, jh_, nh_;
+      decode_sub(u_, jt_, it_, jh_, nh_);
+      const int i = it_ * 128 + lrow, w = 4 * jt_ + 2 * jh_ + (slice >> 1);
+      if (i >= L || w >= a.W) return;
+      const int b_ = (int)__umulhi((uint32_t)item_, magic_h), h_ = item_ - b_ * H;
+      aw_nx = __ldg(a.allow + (((size_t)b_ * a.Hm + (a.Hm == 1 ? 0 : h_)) * L + i) * a.W + w);
+      if (a.keep) kw_nx = __ldg(a.keep + (((size_t)b_ * H + h_) * L + i) * a.W + w);
+    };
+    fetch_bits(blockIdx.x, 0);
     fetch_rows(blockIdx.x);
     uint32_t cs0 = 0, cs1 = 0, cf = 0, cg = 0;     // s_full[0/1], stage_free completion counters; sub-blocks done
     int iter = 0;
@@ -1340,12 +1368,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
       const int b = (int)__umulhi((uint32_t)item, magic_h), h = item - b * H;
       const float inv_s = __ldg(a.inv_scale + item);           // item = b H + h: leave the scaled domain at the drains
       float lse2[2], dlt[2];
-      uint32_t aw[2][2], kwd[2][2];
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        lse2[t] = lse2_nx[t]; dlt[t] = dlt_nx[t]; aw[t][0] = aw_nx[t][0]; aw[t][1] = aw_nx[t][1];
-        kwd[t][0] = kw_nx[t][0]; kwd[t][1] = kw_nx[t][1];
-      }
+      for (int t = 0; t < 2; ++t) { lse2[t] = lse_raw[t] * kLog2e; dlt[t] = dlt_raw[t]; }
       fetch_rows(item + gridDim.x);
       for (int u = 0; u < n_sub; ++u) {
         int jt, it, jh, nh;
@@ -1354,14 +1378,15 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
         const bool active = i < L;
         const bool warp_active = it * 128 + quarter * 32 < L;
         const float my_lse2 = it ? lse2[1] : lse2[0], my_dlt = it ? dlt[1] : dlt[0];
-        const uint32_t my_aw = it ? (jt ? aw[1][1] : aw[1][0]) : (jt ? aw[0][1] : aw[0][0]);
-        const uint32_t awc = active ? ((my_aw >> (16 * jh)) & 0xffffu) : 0u;
-        const uint32_t my_kw = it ? (jt ? kwd[1][1] : kwd[1][0]) : (jt ? kwd[0][1] : kwd[0][0]);
-        const uint32_t kwc = (my_kw >> (16 * jh)) & 0xffffu;
+        const uint32_t aw_raw = aw_nx, kw_raw = kw_nx;          // fetched during the previous sub-block
+        if (u + 1 < n_sub) fetch_bits(item, u + 1); else fetch_bits(item + gridDim.x, 0);
+        const uint32_t awc = active ? ((aw_raw >> ((slice & 1) * 16)) & 0xffffu) : 0u;
+        const uint32_t kwc = (kw_raw >> ((slice & 1) * 16)) & 0xffffu;
         if (warp == 2 && lane == 0) TL_STAMP(20, (int)(cs0 + cs1));
         if (u & 1) { ptx::mbar_wait(&s_full[1], cs1 & 1); ++cs1; } else { ptx::mbar_wait(&s_full[0], cs0 & 1); ++cs0; }
         ptx::tc_fence_after();
         if (warp == 2 && lane == 0) TL_STAMP(21, (int)(cs0 + cs1) - 1);
+        TL_STAMP_ANY(30 + (warp - 2), (int)(cs0 + cs1) - 1);
         uint32_t pk[8], dk_[8];                               // packed Pd / dS of the 16 columns
         if (warp_active) {
           uint32_t rs[16], rd[16];
@@ -1413,6 +1438,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
         if (lane == 0) ptx::mbar_arrive(&sub_done[cg & 1]);
         ++cg;
         if (warp == 2 && lane == 0) TL_STAMP(24, (int)(cs0 + cs1) - 1);
+        TL_STAMP_ANY(46 + (warp - 2), (int)(cs0 + cs1) - 1);
         if (jh == nh - 1) {
           ++cf;                                               // one stage_free completion per block
           if (it == n_t - 1) {

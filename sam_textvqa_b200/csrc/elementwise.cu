@@ -68,6 +68,18 @@ __global__ void cast_kernel(const float* __restrict__ x, long long ldx, __nv_bfl
   }
 }
 
+// one read of an fp32 matrix, two 16-bit copies: half (forward operand) and bf16 (dgrad operand) of a weight
+__global__ void cast_dual_kernel(const float* __restrict__ x, long long ldx, __half* __restrict__ yh, __nv_bfloat16* __restrict__ yb,
+                                 long long ldy, int rows, int cols, int vec) {
+  const int c4 = cols >> 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)rows * c4; i += (size_t)gridDim.x * blockDim.x) {
+    int r = (int)(i / c4), c = (int)(i % c4) * 4;
+    float4 v = ld4(x + (size_t)r * ldx + c, vec);
+    *reinterpret_cast<uint2*>(yh + (size_t)r * ldy + c) = make_uint2(pack_f16(v.x, v.y), pack_f16(v.z, v.w));
+    *reinterpret_cast<uint2*>(yb + (size_t)r * ldy + c) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+
 // x fp32 [rows, cols] -> three bf16 planes.  hi = bf16(x), lo = bf16(x - hi).
 // order 0: (hi,hi,lo)   order 1: (hi,lo,hi).   along_rows 0: y[r, s*cols + c]; 1: y[s*rows + r, c]
 __global__ void split3_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy,
@@ -1065,6 +1077,15 @@ int samk_cast_16(const float* x, long long ldx, void* y, long long ldy, int y_dt
   if (!rows || !cols) return SAMK_OK;
   cast_kernel<<<grid_for((long long)rows * cols / 4, 256), 256, 0, (cudaStream_t)stream>>>(
       x, ldx, (__nv_bfloat16*)y, ldy, rows, cols, (ldx % 4 == 0 && al16(x)) ? 1 : 0, y_dtype == SAMK_DT_F16 ? 1 : 0);
+  return check_launch(__func__);
+}
+
+int samk_cast_dual(const float* x, long long ldx, void* y_f16, void* y_bf16, long long ldy, int rows, int cols, void* stream) {
+  SAMK_REQUIRE(x && y_f16 && y_bf16 && rows >= 0 && cols >= 0, "bad argument");
+  SAMK_REQUIRE(cols % 4 == 0 && ldy % 4 == 0 && ((uintptr_t)y_f16 & 7) == 0 && ((uintptr_t)y_bf16 & 7) == 0, "cols/ldy must be multiples of 4");
+  if (!rows || !cols) return SAMK_OK;
+  cast_dual_kernel<<<grid_for((long long)rows * cols / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, ldx, (__half*)y_f16, (__nv_bfloat16*)y_bf16, ldy, rows, cols, (ldx % 4 == 0 && al16(x)) ? 1 : 0);
   return check_launch(__func__);
 }
 

@@ -346,7 +346,19 @@ def weight_operand(params, mn_major, split=None, kdim=None, fmt="f16"):
         w = params[0] if len(params) == 1 else torch.cat(list(params), dim=0)
         if kdim is not None and kdim != w.shape[1]:
             w = w[:, :kdim]
-        op = operand(w.detach(), "b", mn_major, fmt=fmt, split=split)
+        w = w.detach()
+        if not split and cacheable and w.dtype == torch.float32 and w.stride(1) == 1 and w.shape[1] % 4 == 0:
+            # product mode: the forward reads the half copy, dgrad the bf16 copy -- both from ONE pass over the weight
+            rows, cols = w.shape
+            yh = torch.empty(rows, _ceil8(cols), dtype=torch.float16, device=w.device)
+            yb = torch.empty(rows, _ceil8(cols), dtype=torch.bfloat16, device=w.device)
+            check(lib().samk_cast_dual(ptr(w), w.stride(0), ptr(yh), ptr(yb), yh.stride(0), rows, cols, stream_ptr()), "cast_dual")
+            _count()
+            ops_ = {"f16": Operand(yh, yh.stride(0), 1), "bf16": Operand(yb, yb.stride(0), 1)}
+            for f_, o_ in ops_.items():
+                cache[slot[:-1] + (f_,)] = (stamp, o_, tuple(params))
+            return ops_[fmt]
+        op = operand(w, "b", mn_major, fmt=fmt, split=split)
     if cacheable:
         cache[slot] = (stamp, op, tuple(params))      # the parameters stay alive with the entry: ids cannot be reused
     return op

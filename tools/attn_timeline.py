@@ -35,6 +35,10 @@ if bwd:
     t0 = tl[20, 0]
     for it in range(20):
         print("sub %d: " % it + "  ".join("%s=%d" % (names[s], tl[s, it] - t0) for s in sorted(names)))
+    print("per-warp (warp 2..17 = quarter w%4, slice (w-2)//4): cycles after warp 2's top of the same sub")
+    for it in range(8):
+        print("sub %d s_full: " % it + " ".join("%5d" % (tl[30 + w, it] - tl[20, it]) for w in range(16)))
+        print("sub %d arrive: " % it + " ".join("%5d" % (tl[46 + w, it] - tl[20, it]) for w in range(16)))
 else:
     t0 = tl[8, 0]
     for it in range(10):
