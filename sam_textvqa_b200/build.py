@@ -29,15 +29,30 @@ def _newest_dep():
     return max(os.path.getmtime(p) for p in paths)
 
 
+def _source_hash():
+    """sha256 over every file the library is built from (sources, headers, flags): the shipped .so is reused only
+    when it was built from exactly these bytes, whatever the file times say."""
+    import hashlib
+    h = hashlib.sha256(" ".join(FLAGS).encode())
+    paths = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(os.path.dirname(HERE), "include", "samk.h")]
+    for p in paths:
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def build(force=False, verbose=False):
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest_dep():
+    stamp = OUT + ".sha256"
+    want = _source_hash()
+    if not force and os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read().strip() == want:
         return OUT
     os.makedirs(OBJ, exist_ok=True)
 
     def compile_one(src):
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
         if (not force and os.path.exists(obj) and os.path.getmtime(obj) >= _newest_dep()):
-            return obj, ""
+            return obj, ""          # (objects are an mtime cache; the library itself is keyed on the content hash)
         r = subprocess.run([NVCC] + FLAGS + ["-c", src, "-o", obj], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s\n%s" % (src, r.stdout, r.stderr))
@@ -52,6 +67,8 @@ def build(force=False, verbose=False):
     r = subprocess.run([NVCC, "-shared", "-o", OUT] + objs + ["-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    with open(OUT + ".sha256", "w") as f:
+        f.write(want + "\n")
     return OUT
 
 

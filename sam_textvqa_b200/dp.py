@@ -173,7 +173,8 @@ class GradExchange(object):
             wire_dtype = torch.bfloat16 if os.environ.get("SAMK_DP_WIRE", "f32") == "bf16" else torch.float32
         self.wire_dtype = wire_dtype
         self.wire = torch.empty_like(grads.flat, dtype=wire_dtype) if wire_dtype != torch.float32 else None
-        self.kernels_per_call = 0 if self.wire is None else 2
+        self.chunks = int(os.environ.get("SAMK_DP_CHUNKS", "1"))    # measured at N=2: 4 chunks 0.78 ms exposed, 1 chunk 0.52 ms
+        self.kernels_per_call = 0 if self.wire is None else 2 * self.chunks
 
     def all_reduce(self):
         if self.overlapped or self.world <= 1 or not (dist.is_available() and dist.is_initialized()):
@@ -183,9 +184,20 @@ class GradExchange(object):
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
             return
         from . import ops
-        ops.cast_flat(flat, self.wire)
-        dist.all_reduce(self.wire, op=dist.ReduceOp.SUM, group=self.group)
-        ops.cast_flat(self.wire, flat)
+        # pack | all-reduce | unpack, optionally as a pipeline over SAMK_DP_CHUNKS chunks (the collective of chunk c on
+        # NCCL's stream while chunk c+1 is packed and chunk c-1 unpacked); one chunk measured fastest
+        n = flat.numel()
+        C = max(1, min(self.chunks, n // (1 << 20)))
+        step = (n + C - 1) // C
+        step = (step + 1023) // 1024 * 1024                 # 16-byte aligned chunk starts in both formats
+        bounds = [(lo, min(n, lo + step)) for lo in range(0, n, step)]
+        works = []
+        for lo, hi in bounds:
+            ops.cast_flat(flat[lo:hi], self.wire[lo:hi])
+            works.append(dist.all_reduce(self.wire[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for (lo, hi), w in zip(bounds, works):
+            w.wait()                                        # stream-side wait: the caller's stream waits for that chunk
+            ops.cast_flat(self.wire[lo:hi], flat[lo:hi])
 
     def describe(self):
         import os
@@ -197,7 +209,8 @@ class GradExchange(object):
                                   "the persistent kernels' grids" % (ov["bucket"] >> 20, os.environ.get("NCCL_MAX_CTAS", "default"),
                                                                      os.environ.get("SAMK_DP_RESERVE_SMS", "8")),
                     "wire_dtype": "float32", "bytes": n * 4, "average": "folded into the loss scale (no pass over the buffer)"}
-        return {"collective": "ncclAllReduce(sum) over the flat gradient buffer, after the step",
+        return {"collective": "ncclAllReduce(sum) over the flat gradient buffer, after the step" +
+                              ("" if self.wire is None else ", pack | all-reduce | unpack pipelined over %d chunks" % self.chunks),
                 "wire_dtype": str(self.wire_dtype).replace("torch.", ""),
                 "bytes": n * (4 if self.wire is None else 2), "average": "folded into the loss scale (no pass over the buffer)"}
 

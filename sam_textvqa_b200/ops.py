@@ -604,6 +604,8 @@ class BertEmbedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ids, word, pos, type_, gamma, beta, eps, p):
         _cuda(ids, word)
+        if ids.dtype != torch.long:
+            raise TypeError("question_indices must be int64 (got %s)" % ids.dtype)
         ids = ids.contiguous()
         B, T = ids.shape
         d = word.shape[1]

@@ -80,8 +80,68 @@ class FlatAdam(object):
         check(lib().samk_sumsq(ptr(self.grads.flat), self.grads.flat.numel(), ptr(self._sumsq), stream_ptr()), "sumsq")
         return self._sumsq.sqrt().float()[0]
 
+    def _check_grad_views(self):
+        """`model.zero_grad()` of torch 2.x sets .grad to None (train.py:144): the next backward then allocates fresh
+        gradients while this optimizer reads the flat buffer.  Re-attach the views (a detached gradient that already
+        holds values is copied in) so the reference loop keeps working."""
+        off = 0
+        flat = self.grads.flat
+        for p in self.grads.params:
+            n = p.numel()
+            g = p.grad
+            if g is None:
+                p.grad = flat[off:off + n].view_as(p)
+            elif g.data_ptr() != flat.data_ptr() + 4 * off:
+                flat[off:off + n].view_as(p).copy_(g)
+                p.grad = flat[off:off + n].view_as(p)
+            off += n
+
+    def state_dict(self):
+        """torch.optim.Adam-compatible: per-parameter `step`, `exp_avg`, `exp_avg_sq` (views of the flat buffers) and the
+        param groups (train.py:179-181 saves optimizer_state_dict)."""
+        state, groups, idx, off = {}, [], 0, 0
+        offs = {}
+        for p in self.grads.params:
+            offs[id(p)] = off
+            off += p.numel()
+        for g in self.param_groups:
+            ids = []
+            for p in g["params"]:
+                o, n = offs[id(p)], p.numel()
+                state[idx] = {"step": torch.tensor(float(self.step_count)), "exp_avg": self.exp_avg[o:o + n].view_as(p),
+                              "exp_avg_sq": self.exp_avg_sq[o:o + n].view_as(p)}
+                ids.append(idx)
+                idx += 1
+            groups.append({"lr": g["lr"], "initial_lr": g["initial_lr"], "betas": self.betas, "eps": self.eps, "weight_decay": 0,
+                           "amsgrad": False, "params": ids})
+        return {"state": state, "param_groups": groups, "max_grad_norm": self.max_grad_norm}
+
+    def load_state_dict(self, sd):
+        idx, off = 0, 0
+        offs = {}
+        for p in self.grads.params:
+            offs[id(p)] = off
+            off += p.numel()
+        steps = []
+        for g, sg in zip(self.param_groups, sd["param_groups"]):
+            g["lr"] = float(sg["lr"])
+            g["initial_lr"] = float(sg.get("initial_lr", sg["lr"]))
+            for p in g["params"]:
+                st = sd["state"].get(idx, sd["state"].get(str(idx)))
+                if st is not None:
+                    o, n = offs[id(p)], p.numel()
+                    self.exp_avg[o:o + n].view_as(p).copy_(st["exp_avg"])
+                    self.exp_avg_sq[o:o + n].view_as(p).copy_(st["exp_avg_sq"])
+                    steps.append(int(float(st["step"])))
+                idx += 1
+        if steps:
+            if len(set(steps)) != 1:
+                raise ValueError("FlatAdam keeps one step count for all parameters; the state has %s" % sorted(set(steps)))
+            self.step_count = steps[0]
+
     def step(self):
         """clip_gradients + optimizer.step() of train.py:139-142.  The gradients are left unscaled."""
+        self._check_grad_views()
         self.step_count += 1
         sumsq = None
         if self.max_grad_norm is not None:

@@ -434,3 +434,75 @@ def test_device_argmax_and_token_hits_match_torch():
     idx, hit = ops.argmax_rows(s, t)
     assert torch.equal(idx, s.argmax(-1)) and int(idx[0, 0]) == 17
     assert torch.equal(hit, torch.gather(t, -1, idx[..., None])[..., 0])
+
+
+def test_bench_batch_size_parity_on_a_slice_of_128_samples():
+    """The benchmarked geometry (shipped c3 stack, B = 128, V = 5000, no dropout): samples are independent, so the
+    logits of the first 6 samples of the 128-sample batch must equal the CPU oracle run on those 6 samples alone --
+    in the product mode within the 1e-3 bar with identical arg-max, strict mode far below."""
+    from sam_textvqa_b200 import ops, spatial_utils
+    from sam_textvqa_b200.registry import registry
+    from sam_textvqa_b200.sa_m4c import SAM4C, BertConfig
+    Vb, B, n = 5000, 128, 6
+    registry.answer_vocab = ["w%d" % i for i in range(Vb)]
+    try:
+        mmt, tb = c3_config(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, obj_drop=0.0, ocr_drop=0.0)
+        tb = dict(tb, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+        state = synth.seeded_state(sam4c_state_shapes(mmt, tb, Vb), 4)
+        model = SAM4C(BertConfig.from_dict(mmt), BertConfig.from_dict(tb))
+        model.load_state_dict(state, strict=True)
+        model = model.to(DEV).train()
+        graph_fn = lambda boxes: spatial_utils.build_graph_batch(boxes, 0.5)[0]
+        batch = synth.make_batch(B, V=Vb, seed=17, contexts=(3,), graph_fn=graph_fn)
+        small = {k: (v[:n] if torch.is_tensor(v) else v) for k, v in batch.items()}
+        small["spatial_adj_matrices"] = {k: v[:n] for k, v in batch["spatial_adj_matrices"].items()}
+        ref, _, _ = sam4c_oracle.forward(state, small, mmt, tb, train=True)
+        live = ref > -5000
+        for prec, tol in (("f16", 1e-3), ("bf16x3", 1e-4)):
+            ops.set_precision(prec)
+            ops.clear_weight_cache()
+            bd = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+            bd["spatial_adj_matrices"] = {k: v.to(DEV) for k, v in batch["spatial_adj_matrices"].items()}
+            with torch.no_grad():
+                scores = model(bd)["textvqa_scores"][:n].cpu()
+            err = rel_err(scores, ref, live)
+            print("B=128 slice [%s]: logits rel err %.3e" % (prec, err))
+            assert err < tol, prec
+            assert torch.equal(scores.argmax(-1), ref.argmax(-1)), prec
+    finally:
+        ops.set_precision("f16")
+        registry.answer_vocab = ["w%d" % i for i in range(V)]
+
+
+@pytest.mark.parametrize("O,B", [(186, 2), (442, 1)])
+def test_long_sequence_stack_vs_oracle(O, B):
+    """BASELINE config 4 lengths at model level: joint tokens 256 / 512 (L = 268 / 524: several key tiles per row in the
+    forward kernel, the L > 256 backward kernel), two layers (n, s): logits and one deep gradient against the oracle."""
+    from sam_textvqa_b200 import ops, spatial_utils
+    mmt, tb = c3_config(layer_type_list=["n", "s"], mix_list=["none", "share3"], hidden_dropout_prob=0.0,
+                        attention_probs_dropout_prob=0.0, obj_drop=0.0, ocr_drop=0.0)
+    tb = dict(tb, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    state = synth.seeded_state(sam4c_state_shapes(mmt, tb, V), 6)
+    model = _model(mmt, tb, state).train()
+    graph_fn = lambda boxes: spatial_utils.build_graph_batch(boxes, 0.5)[0]
+    batch = synth.make_batch(B, O=O, V=V, seed=O, contexts=(1, 3), graph_fn=graph_fn)
+    P = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+    ref, _, _ = sam4c_oracle.forward(P, batch, mmt, tb, train=True)
+    sam4c_oracle.bce_with_mask_loss(ref, batch["targets"], batch["train_loss_mask"]).backward()
+    ref = ref.detach()
+    live = ref > -5000
+    name = "mmt.encoder.normal_layers.0.attention.self.key.weight"
+    try:
+        for prec, tol, gtol in (("f16", 1e-3, 3e-2), ("bf16x3", 1e-4, 2e-3)):
+            ops.set_precision(prec)
+            ops.clear_weight_cache()
+            model.zero_grad()
+            bd = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+            scores = model(bd)["textvqa_scores"]
+            assert rel_err(scores.detach().cpu(), ref, live) < tol, prec
+            assert torch.equal(scores.argmax(-1).cpu(), ref.argmax(-1)), prec
+            ops.bce_with_mask_loss(scores, bd["targets"], bd["train_loss_mask"]).backward()
+            got = dict(model.named_parameters())[name].grad.detach().cpu()
+            assert rel_err(got, P[name].grad) < gtol, prec
+    finally:
+        ops.set_precision("f16")

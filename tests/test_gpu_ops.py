@@ -390,3 +390,32 @@ def test_fused_clip_adam_matches_torch_adam_and_clip_grad_norm(ops):
     assert ours[0].data.data_ptr() == opt.flat_params.data_ptr()       # parameters are views of the flat buffer
     assert ours[0]._version >= 4                                        # weight-operand caches see the updates
     assert opt.step_count == 4
+
+
+def test_flat_adam_state_dict_round_trip_and_detached_grads(ops):
+    """train.py:144 / :179-181: `model.zero_grad()` (set_to_none) between steps and an optimizer state_dict that
+    torch.optim.Adam can load."""
+    from sam_textvqa_b200 import optim
+    g = torch.Generator().manual_seed(2)
+    ps = [torch.nn.Parameter(torch.randn(64, 32, generator=g).to(DEV)), torch.nn.Parameter(torch.randn(32, generator=g).to(DEV))]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    groups = [{"params": ps}]
+    grads = optim.flat_grad_buffer_for(groups)
+    opt = optim.FlatAdam(groups, grads, lr=1e-2)
+    ropt = torch.optim.Adam(ref, lr=1e-2)
+    for it in range(3):
+        for p in ps:
+            p.grad = None                                  # what model.zero_grad() does in torch 2.x
+        loss = sum((p * p).sum() for p in ps)
+        loss.backward()                                    # fresh .grad tensors, not views of the flat buffer
+        sum((p * p).sum() for p in ref).backward()
+        opt.step()
+        ropt.step()
+        ropt.zero_grad()
+        for p, q in zip(ps, ref):
+            assert (p.detach() - q.detach()).abs().max().item() < 1e-6, it
+    sd = opt.state_dict()
+    ropt2 = torch.optim.Adam([torch.nn.Parameter(p.detach().clone()) for p in ps], lr=1e-2)
+    ropt2.load_state_dict({"state": sd["state"], "param_groups": sd["param_groups"]})      # Adam accepts it
+    opt.load_state_dict(sd)
+    assert opt.step_count == 3
