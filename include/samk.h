@@ -154,6 +154,14 @@ int samk_layernorm_bwd(const float* dy, const float* x, const float* gamma, floa
                        float* dbeta, float* dbias, float* partials, int rows, int cols, float* dxd_amax, void* stream);
 /* floats of scratch for `partials` (NULL = reduce with atomics instead of the 2-stage reduction) */
 long long samk_layernorm_bwd_partials(int cols);
+/* The same backward in two calls: _main leaves the block partial sums of dgamma / dbeta / dbias in `partials` (required),
+ * _finalize (same rows, cols) adds them into the three [cols] buffers.  Nothing inside a backward pass reads those sums, so
+ * a caller may issue _finalize on a second stream, beside the GEMM that follows (each call then needs its own scratch). */
+int samk_layernorm_bwd_main(const float* dy, const float* x, const float* gamma, float eps, float* dx, void* dxd,
+                            int dxd_dtype, float drop_p, unsigned long long seed, unsigned long long offset, float* dgamma,
+                            float* dbeta, float* dbias, float* partials, int rows, int cols, float* dxd_amax, void* stream);
+int samk_layernorm_bwd_finalize(const float* partials, int rows, int cols, float* dgamma, float* dbeta, float* dbias,
+                                void* stream);
 /* out = dropout(a + b) (b may be NULL); also the dropout backward with a = dout */
 int samk_dropout_add(const float* a, const float* b, float* out, void* out2, int out2_dtype, int rows, int cols,
                      float drop_p, unsigned long long seed, unsigned long long offset, void* stream);
@@ -256,7 +264,8 @@ typedef struct samk_attn_params {
   float* dq_accum;            /* tensor-core backward: fp32 [B*L, H*64] scratch for the dQ reduction */
   int q_begin;                /* forward only: compute query rows >= q_begin (rounded down to the kernel's
                                  row tile); 0 = all rows.  Used by the cached greedy decoder (decoder rows only). */
-  int delta_ready;            /* reserved (0) */
+  int bwd_phase;              /* tensor-core backward: 0 = whole backward; 2 = only the preparation kernel (do_f16, do_inv_scale,
+                                 delta from dctx and ctx); 1 = the rest, after a phase-2 call on the same workspaces */
   const uint32_t* keep_bits;  /* tensor-core path with drop_p > 0: [B, H, L, ceil(L/32)] dropout keep bits of the
                                  attention probabilities from samk_attn_build_keep (same (seed, offset) stream as the
                                  exact kernel draws inline); shared by the forward and the backward launch */

@@ -32,7 +32,7 @@ class AttnParams(ctypes.Structure):
         ("delta", c_void_p), ("dtype", c_int), ("grad_dtype", c_int), ("B", c_int), ("H", c_int), ("head_dim", c_int), ("T", c_int),
         ("A", c_int), ("D", c_int), ("key_valid", c_void_p), ("rel_bits", c_void_p), ("quadrant_mask", ctypes.c_uint),
         ("spatial", c_int), ("scale", c_float), ("drop_p", c_float), ("drop_seed", c_ull), ("drop_offset", c_ull),
-        ("allow_bits", c_void_p), ("dq_accum", c_void_p), ("q_begin", c_int), ("delta_ready", c_int),
+        ("allow_bits", c_void_p), ("dq_accum", c_void_p), ("q_begin", c_int), ("bwd_phase", c_int),
         ("keep_bits", c_void_p), ("do_f16", c_void_p), ("do_inv_scale", c_void_p),
     ]
 
@@ -67,6 +67,9 @@ SIGNATURES = {
     "samk_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_float, c_ull,
                                    c_ull, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "samk_layernorm_bwd_partials": (c_ll, [c_int]),
+    "samk_layernorm_bwd_main": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_float, c_ull,
+                                        c_ull, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "samk_layernorm_bwd_finalize": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "samk_dropout_add": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_ull, c_ull, c_void_p]),
     "samk_colsum": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p]),
     "samk_colsum3": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -385,6 +385,7 @@ int attn_simt_bwd(const samk_attn_params* p, cudaStream_t stream) {
   if (rc) return rc;
   if (!p->ctx || !p->lse || !p->dctx || !p->dqkv || !p->delta) { set_error("samk_attn_bwd: null pointer"); return SAMK_ERR_ARG; }
   if (!a.B || !a.m.L) return SAMK_OK;
+  if (p->bwd_phase == 2) return SAMK_OK;        // this path has no separate preparation
   dim3 grid((a.m.L + OWN - 1) / OWN, a.H, a.B);
   if ((rc = ensure_smem(attn_rows_kernel<true>, kRowsSmem))) return rc;
   if ((rc = ensure_smem(attn_dkv_kernel, kDkvSmem))) return rc;

@@ -1489,12 +1489,13 @@ __global__ void attn_dq_store_kernel(const float* __restrict__ acc, __nv_bfloat1
 // host
 // ---------------------------------------------------------------------------------------------
 static int fill_tc(TcArgs& a, const samk_attn_params* p) {
-  if (!p->allow_bits) { set_error("samk_attn: tensor-core path needs allow_bits (samk_attn_build_mask)"); return SAMK_ERR_ARG; }
+  const bool prep_only = p->bwd_phase == 2;      // the preparation kernel reads dctx and ctx only
+  if (!p->allow_bits && !prep_only) { set_error("samk_attn: tensor-core path needs allow_bits (samk_attn_build_mask)"); return SAMK_ERR_ARG; }
   a.ctx = p->ctx; a.lse = p->lse; a.delta = p->delta; a.dqkv = p->dqkv; a.dq_accum = p->dq_accum;
   a.inv_scale = p->do_inv_scale;
   a.allow = p->allow_bits; a.Hm = p->spatial ? p->H : 1;
   a.keep = p->drop_p > 0.f ? p->keep_bits : nullptr;
-  if (p->drop_p > 0.f && !p->keep_bits) { set_error("samk_attn: tensor-core path with dropout needs keep_bits (samk_attn_build_keep)"); return SAMK_ERR_ARG; }
+  if (p->drop_p > 0.f && !p->keep_bits && !prep_only) { set_error("samk_attn: tensor-core path with dropout needs keep_bits (samk_attn_build_keep)"); return SAMK_ERR_ARG; }
   a.B = p->B; a.H = p->H; a.L = p->T + p->A + p->D; a.W = (a.L + 31) / 32;
   a.scale = p->scale; a.scale_log2 = p->scale * kLog2e;
   a.drop_thresh = p->drop_p > 0.f ? drop_threshold(p->drop_p) : 0u;
@@ -1607,9 +1608,14 @@ int attn_tc_bwd(const samk_attn_params* p, cudaStream_t stream) {
   if (!a.B || !a.L) return SAMK_OK;
   const long long rows = (long long)a.B * a.L;
   const int hd = a.H * TDH;
-  attn_bwd_prep_kernel<<<a.B * a.H, 256, 0, stream>>>((const __nv_bfloat16*)p->dctx, (const __half*)p->ctx, (__half*)p->do_f16,
-                                                     p->delta, p->do_inv_scale, a.H, a.L);
-  if ((rc = check_launch("samk_attn_bwd(prep)"))) return rc;
+  // bwd_phase: 0 = whole backward, 1 = the preparation already ran on these workspaces, 2 = preparation only (a caller
+  // may run it on a second stream, beside the weight-gradient product that sits between the two in a layer's backward)
+  if (p->bwd_phase != 1) {
+    attn_bwd_prep_kernel<<<a.B * a.H, 256, 0, stream>>>((const __nv_bfloat16*)p->dctx, (const __half*)p->ctx, (__half*)p->do_f16,
+                                                       p->delta, p->do_inv_scale, a.H, a.L);
+    if ((rc = check_launch("samk_attn_bwd(prep)"))) return rc;
+  }
+  if (p->bwd_phase == 2) return SAMK_OK;
   CUtensorMap tqkv, tdo;
   if ((rc = make_tmap_bf16_2d(&tqkv, p->qkv, rows, 3 * hd, 3 * hd, 64, 128))) return rc;
   if ((rc = make_tmap_bf16_2d(&tdo, p->do_f16, rows, hd, hd, 64, 128))) return rc;

@@ -1121,26 +1121,56 @@ int samk_layernorm_fwd(const float* x, const float* gamma, const float* beta, fl
   return check_launch(__func__);
 }
 
-int samk_layernorm_bwd(const float* dy, const float* x, const float* gamma, float eps, float* dx, void* dxd,
-                       int dxd_dtype, float drop_p, unsigned long long seed, unsigned long long offset, float* dgamma,
-                       float* dbeta, float* dbias, float* partials, int rows, int cols, float* dxd_amax, void* stream) {
-  SAMK_REQUIRE(dy && x && gamma && rows >= 0, "bad argument");
-  SAMK_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 1024, "cols must be a multiple of 4, <= 1024");
+static int ln_bwd_grid(int rows) {
+  int grid = grid_for(rows, kLnBwdWarps * 4);
+  if (grid > 592) grid = 592;   // partials workspace is sized for 592 blocks (samk_layernorm_bwd_partials)
+  return grid;
+}
+
+static int ln_bwd_launch(const float* dy, const float* x, const float* gamma, float eps, float* dx, void* dxd,
+                         int dxd_dtype, float drop_p, unsigned long long seed, unsigned long long offset, float* dgamma,
+                         float* dbeta, float* dbias, float* partials, int rows, int cols, float* dxd_amax, void* stream,
+                         bool finalize, const char* who) {
+  if (!(dy && x && gamma && rows >= 0)) { set_error("%s: bad argument", who); return SAMK_ERR_ARG; }
+  if (!(cols > 0 && cols % 4 == 0 && cols <= 1024)) { set_error("%s: cols must be a multiple of 4, <= 1024", who); return SAMK_ERR_ARG; }
   if (dxd_amax && cudaMemsetAsync(dxd_amax, 0, sizeof(float), (cudaStream_t)stream) != cudaSuccess) {
-    set_error("%s: memset failed", __func__);
+    set_error("%s: memset failed", who);
     return SAMK_ERR_CUDA;
   }
   if (!rows) return SAMK_OK;
-  int grid = grid_for(rows, kLnBwdWarps * 4);
-  if (grid > 592) grid = 592;   // partials workspace is sized for 592 blocks (samk_layernorm_bwd_partials)
+  const int grid = ln_bwd_grid(rows);
   const int smem = kLnBwdWarps * 3 * cols * (int)sizeof(float);
   launch_maybe_pdl(layernorm_bwd_kernel, dim3(grid), dim3(kLnBwdWarps * 32), (size_t)smem, (cudaStream_t)stream,
                    pdl_level() >= 2, dy, x, gamma, eps, dx, dxd, dxd_dtype,
                    drop_p > 0.f ? drop_threshold(drop_p) : 0u, drop_keep_scale(drop_p), seed, offset, dgamma, dbeta,
                    dbias, partials, rows, cols, reinterpret_cast<unsigned int*>(dxd_amax));
-  int rc = check_launch(__func__);
-  if (rc || !partials) return rc;
+  int rc = check_launch(who);
+  if (rc || !partials || !finalize) return rc;
   ln_bwd_finalize_kernel<<<dim3((cols + 31) / 32, 3), 1024, 0, (cudaStream_t)stream>>>(partials, grid, cols, dgamma, dbeta, dbias);
+  return check_launch(who);
+}
+
+int samk_layernorm_bwd(const float* dy, const float* x, const float* gamma, float eps, float* dx, void* dxd,
+                       int dxd_dtype, float drop_p, unsigned long long seed, unsigned long long offset, float* dgamma,
+                       float* dbeta, float* dbias, float* partials, int rows, int cols, float* dxd_amax, void* stream) {
+  return ln_bwd_launch(dy, x, gamma, eps, dx, dxd, dxd_dtype, drop_p, seed, offset, dgamma, dbeta, dbias, partials, rows, cols,
+                       dxd_amax, stream, true, __func__);
+}
+
+int samk_layernorm_bwd_main(const float* dy, const float* x, const float* gamma, float eps, float* dx, void* dxd,
+                            int dxd_dtype, float drop_p, unsigned long long seed, unsigned long long offset, float* dgamma,
+                            float* dbeta, float* dbias, float* partials, int rows, int cols, float* dxd_amax, void* stream) {
+  if (!partials) { set_error("%s: needs the partials workspace", __func__); return SAMK_ERR_ARG; }
+  return ln_bwd_launch(dy, x, gamma, eps, dx, dxd, dxd_dtype, drop_p, seed, offset, dgamma, dbeta, dbias, partials, rows, cols,
+                       dxd_amax, stream, false, __func__);
+}
+
+int samk_layernorm_bwd_finalize(const float* partials, int rows, int cols, float* dgamma, float* dbeta, float* dbias,
+                                void* stream) {
+  SAMK_REQUIRE(partials && rows >= 0 && cols > 0 && cols % 4 == 0 && cols <= 1024, "bad argument");
+  if (!rows) return SAMK_OK;
+  ln_bwd_finalize_kernel<<<dim3((cols + 31) / 32, 3), 1024, 0, (cudaStream_t)stream>>>(partials, ln_bwd_grid(rows), cols, dgamma,
+                                                                                      dbeta, dbias);
   return check_launch(__func__);
 }
 

@@ -22,8 +22,11 @@ namespace samk {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter, each takes half the columns
-constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
+// Epilogue warps per CTA (template parameter EW): 8 = two warps per TMEM lane quarter, each draining half of the tile's
+// columns; 16 = four per quarter, a quarter of the columns each.  The epilogue of the K = 768 shapes is longer than their
+// main loop and latency-bound (two warps per scheduler), so those shapes take 16 warps and give up one pipeline stage
+// for the extra transpose tiles.
+constexpr int gemm_threads(int ew) { return 64 + 32 * ew; }
 
 // Epilogue feature bits.  A kernel instantiation carries either a compile-time mask (EPI >= 0: the hot
 // combinations of the SA-M4C layers, dead branches removed -- a fully dynamic epilogue is ~100 KB of
@@ -346,13 +349,13 @@ __device__ __forceinline__ void chunk_finish(const EpiArgs& ep, const ChunkIn<ST
   }
 }
 
-template <int BN, int CL = 1> struct GemmCfg {
-  static constexpr int kStages = (BN == 256 && CL == 1) ? 4 : 6;
+template <int BN, int CL = 1, int EW = 8> struct GemmCfg {
+  static constexpr int kStages = ((BN == 256 && CL == 1) ? 4 : 6) - (EW > 8 ? 1 : 0);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (BN / CL) * BK * 2;      // CTA pair: each CTA holds half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingOff = kStages * kStageBytes + 256;       // after the barriers
-  static constexpr int kSmemBytes = kStagingOff + kEpiWarps * kStageBytesPerWarp /*epilogue transposes*/ + 1024 /*align slack*/;
+  static constexpr int kSmemBytes = kStagingOff + EW * kStageBytesPerWarp /*epilogue transposes*/ + 1024 /*align slack*/;
   static constexpr int kTmemCols = 2 * BN;  // 256 or 512: power of two
 };
 
@@ -363,11 +366,11 @@ template <int BN, int CL = 1> struct GemmCfg {
 //   of operands from shared memory (the port the staged epilogue also needs).  All TMA loads of a stage complete on
 //   the leader's full barrier; MMA completion is multicast to both CTAs' empty / accumulator-full barriers; both
 //   CTAs' epilogue warps release the accumulator on the leader's barrier.
-template <int BN, int A_MN, int B_MN, int CL, int EPI, bool STAGED>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN, int A_MN, int B_MN, int CL, int EPI, bool STAGED, int EW = 8>
+__global__ void __launch_bounds__(gemm_threads(EW), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const EpiArgs ep, int M, int N, int K, int split_k, uint32_t ab_fmt) {
-  using Cfg = GemmCfg<BN, CL>;
+  using Cfg = GemmCfg<BN, CL, EW>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -396,7 +399,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < Cfg::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-      for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], CL * kEpiWarps); }
+      for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], CL * EW); }
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -520,7 +523,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ===================== epilogue =====================
     const int lane_grp = warp & 3;          // TMEM lane quarter this warp may access (warp id % 4)
-    const int col_half = (warp - 2) >> 2;   // which half of the tile's columns this warp drains
+    const int col_half = (warp - 2) >> 2;   // which part (1 / (EW/4)) of the tile's columns this warp drains
     const float alpha = ((epi_flags<EPI>(ep) & F_ALPHA) && ep.alpha_dev) ? ep.alpha * __ldg(ep.alpha_dev) : ep.alpha;
     int acc = 0; uint32_t acc_phase = 0;
     for (int w = work0; w < num_work; w += work_stride) {
@@ -531,7 +534,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool has_k = min(kb_total, kb0 + kb_per) > kb0;
       const int row0 = m0 + lane_grp * 32;
       const uint32_t stage = ptx::smem_u32(smem + Cfg::kStagingOff) + (warp - 2) * kStageBytesPerWarp;
-      constexpr int kChunks = BN / 64;               // 32-column chunks per warp
+      constexpr int kChunks = BN / (8 * EW);         // 32-column chunks per warp
       const int cbase = col_half * kChunks;
       const bool live = (has_k || !(epi_flags<EPI>(ep) & F_ATOMIC)) && row0 < M;
       // operands of chunk i+1 are fetched from global memory while chunk i is finished (the first one even
@@ -682,11 +685,11 @@ int sm_count() {
 }
 void set_sm_reserved(int n) { g_sm_reserved = n; }
 
-template <int BN, int A_MN, int B_MN, int CL, int EPI, bool STAGED>
+template <int BN, int A_MN, int B_MN, int CL, int EPI, bool STAGED, int EW = 8>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiArgs& ep, int M, int N, int K, int split_k,
                      uint32_t ab_fmt, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CL>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CL, EPI, STAGED>;
+  using Cfg = GemmCfg<BN, CL, EW>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CL, EPI, STAGED, EW>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) {
@@ -703,7 +706,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiArgs
   if (work < clusters) clusters = work;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * CL);
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(gemm_threads(EW));
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -730,6 +733,18 @@ static int gemm_2cta() {
     g_gemm_2cta = s ? (s[0] == '1' ? 1 : 0) : 1;     // measured faster on every layer shape (tools/gemm_bench.py)
   }
   return g_gemm_2cta;
+}
+
+// Which specialised epilogues run with 16 epilogue warps on CTA-pair tiles: bit i = entry i of kSpecs (samk_gemm_16).
+// SAMK_GEMM_EW16=<mask> overrides the default (measured per shape with tools/gemm_bench.py).
+constexpr int kDefaultEw16Mask = 0x45;   // q|k|v projection, FFN1 (train: GELU pair, inference: GELU)
+static int g_gemm_ew16 = -1;
+static int gemm_ew16_mask() {
+  if (g_gemm_ew16 < 0) {
+    const char* s = getenv("SAMK_GEMM_EW16");
+    g_gemm_ew16 = s ? (int)strtol(s, nullptr, 0) : kDefaultEw16Mask;
+  }
+  return g_gemm_ew16;
 }
 
 // the epilogue combinations of the SA-M4C layers that get a compile-time specialised kernel
@@ -843,8 +858,13 @@ extern "C" int samk_gemm_16(const void* A, int a_dtype, int a_mn, long long lda,
                                 {0, 0, M_F32_BIAS_RES}, {0, 0, M_GELU}, {0, 0, M_F32}, {0, 1, M_BF16}, {0, 1, M_MULAUX},
                                 {0, 1, M_F32_RES}, {0, 1, M_F32}, {1, 1, M_ATOMIC}};   // keep in step with SAMK_SPEC below
   bool spec = false;
-  for (const Spec& sp : kSpecs) spec = spec || (sp.am == (a_mn ? 1 : 0) && sp.bm == (b_mn ? 1 : 0) && sp.mask == flags);
+  int spec_idx = -1, si = 0;
+  for (const Spec& sp : kSpecs) {
+    if (sp.am == (a_mn ? 1 : 0) && sp.bm == (b_mn ? 1 : 0) && sp.mask == flags) { spec = true; spec_idx = si; }
+    ++si;
+  }
   const bool pair = gemm_2cta() && spec && bn == 256 && M >= 2 * BM;
+  const bool ew16 = pair && ((gemm_ew16_mask() >> spec_idx) & 1);
   if (b_mn) rc = make_tmap_bf16_2d(&tb, B, K, N, ldb, 64, BK);
   else rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, BK, pair ? bn / 2 : bn);
   if (rc) return rc;
@@ -853,6 +873,7 @@ extern "C" int samk_gemm_16(const void* A, int a_dtype, int a_mn, long long lda,
   // row-per-thread layout for every combination below (tools/gemm_bench.py)
 #define SAMK_SPEC(AM_, BM_, MASK_)                                                                        \
   if (a_mn == AM_ && b_mn == BM_ && flags == (MASK_)) {                                                    \
+    if (ew16) return launch_tc<256, AM_, BM_, 2, MASK_, true, 16>(ta, tb, ep, M, N, K, split_k, ab_fmt, stream);  \
     if (pair) return launch_tc<256, AM_, BM_, 2, MASK_, true>(ta, tb, ep, M, N, K, split_k, ab_fmt, stream);      \
     if (bn == 256) return launch_tc<256, AM_, BM_, 1, MASK_, true>(ta, tb, ep, M, N, K, split_k, ab_fmt, stream); \
     return launch_tc<128, AM_, BM_, 1, MASK_, true>(ta, tb, ep, M, N, K, split_k, ab_fmt, stream);                \

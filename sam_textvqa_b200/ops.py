@@ -122,7 +122,20 @@ def _ln_partials(dev, cols):
     return ws[cols]
 
 
-def _ln_bwd(dy, x, gamma, eps, dx, dxd, p, drop, dg, db, dbias, rows, cols, amax=None):
+def _ln_bwd(dy, x, gamma, eps, dx, dxd, p, drop, dg, db, dbias, rows, cols, amax=None, side_final=False):
+    """side_final: the reduction of the block partial sums into dgamma / dbeta / dbias runs on the side branch (beside
+    the GEMM the caller issues next; joined by the caller's join_side()) from a scratch buffer of its own."""
+    if side_final and _SIDE_BRANCH and rows > 0:
+        part = torch.empty(int(lib().samk_layernorm_bwd_partials(cols)), dtype=torch.float32, device=dy.device)
+        check(lib().samk_layernorm_bwd_main(ptr(dy), ptr(x), ptr(gamma), eps, ptr(dx), ptr(dxd),
+                                            _dt(dxd) if dxd is not None else 0, p, drop[0], drop[1], ptr(dg), ptr(db),
+                                            ptr(dbias), ptr(part), rows, cols, ptr(amax), stream_ptr()), "layernorm_bwd_main")
+        with side_branch():
+            check(lib().samk_layernorm_bwd_finalize(ptr(part), rows, cols, ptr(dg), ptr(db), ptr(dbias), stream_ptr()),
+                  "layernorm_bwd_finalize")
+            _state(dy.device).side_keep.append(part)       # alive until the branch is joined
+        _count(2)
+        return
     check(lib().samk_layernorm_bwd(ptr(dy), ptr(x), ptr(gamma), eps, ptr(dx), ptr(dxd),
                                    _dt(dxd) if dxd is not None else 0, p, drop[0], drop[1], ptr(dg), ptr(db),
                                    ptr(dbias), ptr(_ln_partials(dy.device, cols)), rows, cols, ptr(amax), stream_ptr()),
@@ -233,6 +246,7 @@ class _State(object):
         self.ln_ws = {}
         self.side_stream = None
         self.side_open = False
+        self.side_keep = []            # tensors a side-branch kernel still reads (released by join_side)
 
 
 _states = {}
@@ -307,15 +321,18 @@ def operand(x2d, role, mn_major, fmt="f16", split=None):
     return Operand(y, y.stride(0), 1)
 
 
-def scaled_f16(x2d, amax=None):
+def scaled_f16(x2d, amax=None, out=None):
     """(Operand over half(x * S), device pointer to 1/S) for a gradient tensor x2d (bf16 or fp32, contiguous): S is the
     power of two, found on the device, that puts max|x| into [2^11, 2^12).  The consumer passes the pointer as
     `alpha_dev` of its GEMM.  Used where a gradient meets a big saved f16 activation in a weight-gradient product.
     amax: device float already holding max|x| (written by the kernel that produced x), saves the reduction pass."""
     _cuda(x2d)
     assert x2d.is_contiguous() and x2d.numel() % 4 == 0
-    y = torch.empty(x2d.shape, dtype=torch.float16, device=x2d.device)
-    sc = torch.empty(4, dtype=torch.float32, device=x2d.device)
+    if out is not None:          # (half [shape of x2d], 4 floats) allocated by the caller, e.g. before it forks a side branch
+        y, sc = out
+    else:
+        y = torch.empty(x2d.shape, dtype=torch.float16, device=x2d.device)
+        sc = torch.empty(4, dtype=torch.float32, device=x2d.device)
     check(lib().samk_cast_scaled_f16(ptr(x2d), _dt(x2d), x2d.numel(), ptr(amax), ptr(y), ptr(sc), stream_ptr()),
           "cast_scaled_f16")
     _count(1 if amax is not None else 2)
@@ -442,6 +459,11 @@ def colsum_into(x2d, out):
 # declared final, so they run beside the tensor-bound dgrad / wgrad GEMMs (a parallel branch of the captured graph;
 # colsum_kernel uses no shared memory so that its blocks fit on an SM whose shared memory a GEMM CTA owns).
 _SIDE_BRANCH = os.environ.get("SAMK_SIDE_BRANCH", "1") != "0"
+# also on the branch (SAMK_SIDE_OVERLAP=0 keeps them in line): LayerNorm-backward parameter-gradient reductions, the scaled
+# half copies of dY for the weight-gradient products, the attention-backward preparation kernel
+# (bit 0: after LayerNorm 2, beside the FFN2 dgrad; bit 1: after LayerNorm 1, beside the out-projection dgrad; bit 2: the
+#  attention preparation, beside the out-projection weight-gradient product)
+_SIDE_OVERLAP = int(os.environ.get("SAMK_SIDE_OVERLAP", "0")) if _SIDE_BRANCH else 0
 
 
 class side_branch(object):
@@ -471,6 +493,7 @@ def join_side():
     if st.side_open:
         st.side_open = False
         torch.cuda.current_stream().wait_stream(st.side_stream)
+    del st.side_keep[:]
 
 
 # ---- simple differentiable ops -----------------------------------------------------------------------
@@ -759,11 +782,40 @@ def attention_fwd(qkv, valid, rel, dims, spatial, quad_mask, p, drop, allow=None
     return ctx_t, lse
 
 
-def attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, allow=None, keep=None):
+def attention_bwd_workspaces(qkv, lse, dims):
+    """(do16, inv_scale, delta) of the tensor-core backward, or None when the path has no separate preparation"""
+    B, L, H, T, A, D = dims
+    if not uses_tensor_core_attention(qkv.dtype):
+        return None
+    return (torch.empty(B * L, H * 64, dtype=torch.float16, device=qkv.device),
+            torch.empty(B * H, dtype=torch.float32, device=qkv.device), torch.empty_like(lse))
+
+
+def attention_bwd_prepare(dctx, qkv, ctx_t, lse, dims, ws):
+    """First kernel of the tensor-core backward on its own (dO re-expressed in half with one exact scale per (sample,
+    head), delta = rowsum(dO . O)): needs only dctx and ctx, so a layer's backward issues it on the side branch beside
+    the weight-gradient product that sits between the out-projection dgrad and the attention backward.  Returns the
+    ws: attention_bwd_workspaces(...) (allocated on the caller's stream); hand it to attention_bwd(prepared=ws)."""
+    B, L, H, T, A, D = dims
+    do16, inv_scale, delta = ws
+    ap = _lib.AttnParams()
+    ap.qkv, ap.ctx, ap.lse = qkv.data_ptr(), ctx_t.data_ptr(), lse.data_ptr()
+    ap.dtype, ap.grad_dtype = _dt(qkv), _dt(dctx)
+    ap.dctx, ap.dqkv, ap.delta = dctx.data_ptr(), dctx.data_ptr(), delta.data_ptr()     # (dqkv is not touched in this phase)
+    ap.B, ap.H, ap.head_dim, ap.T, ap.A, ap.D = B, H, 64, T, A, D
+    ap.scale = 1.0 / math.sqrt(64.0)
+    ap.do_f16, ap.do_inv_scale = do16.data_ptr(), inv_scale.data_ptr()
+    ap.bwd_phase = 2
+    check(lib().samk_attn_bwd(ctypes.byref(ap), _ATTN_IMPL, stream_ptr()), "attn_bwd(prepare)")
+    return ws
+
+
+def attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, allow=None, keep=None, prepared=None):
     """dctx [B*L, H*64] (bf16 in the product mode) -> dq|dk|dv [B*L, 3*H*64] in the same dtype."""
     B, L, H, T, A, D = dims
     dq_accum = do16 = inv_scale = None
     tc = uses_tensor_core_attention(qkv.dtype)
+    delta = None
     if tc:
         if allow is None:
             allow = build_attn_mask(valid, rel, dims, spatial, quad_mask)
@@ -771,14 +823,19 @@ def attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p
             keep = build_attn_keep(dims, p, drop, qkv.device)
         if L > 256:      # long sequences: key-tile CTAs reduce dQ through an fp32 buffer
             dq_accum = torch.empty(B * L, H * 64, dtype=torch.float32, device=qkv.device)
-        do16 = torch.empty(B * L, H * 64, dtype=torch.float16, device=qkv.device)     # dO in half, one scale per (b, h)
-        inv_scale = torch.empty(B * H, dtype=torch.float32, device=qkv.device)
+        if prepared is not None:
+            do16, inv_scale, delta = prepared
+        else:
+            do16 = torch.empty(B * L, H * 64, dtype=torch.float16, device=qkv.device)     # dO in half, one scale per (b, h)
+            inv_scale = torch.empty(B * H, dtype=torch.float32, device=qkv.device)
     dqkv = torch.empty(qkv.shape, dtype=dctx.dtype, device=qkv.device)
-    delta = torch.empty_like(lse)
+    if delta is None:
+        delta = torch.empty_like(lse)
     ap = _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, dctx, dqkv, delta,
                       allow=allow, dq_accum=dq_accum, keep=keep)
     if tc:
         ap.do_f16, ap.do_inv_scale = do16.data_ptr(), inv_scale.data_ptr()
+        ap.bwd_phase = 1 if prepared is not None else 0
     if attn_profile is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -971,14 +1028,23 @@ class BertLayerFn(torch.autograd.Function):
         dy2 = torch.empty(M, d, dtype=torch.float32, device=dev)      # grad wrt (dropout(dense)+a)
         dY2 = torch.empty(M, d, dtype=gdt, device=dev)                 # grad wrt dense output
         amax2 = torch.empty(2, dtype=torch.float32, device=dev) if half else None     # max|dY2|, max|dY1|
-        _ln_bwd(dout, y2, g2, eps, dy2, dY2, p_hid, ctx.drops[2], Gg2, Gb2, Go2b, M, d, amax=amax2)
+        # (side branch, beside the dgrad GEMM below: the reduction of the LayerNorm parameter gradients and the scaled
+        #  half copy of dY2 that the weight-gradient product reads)
+        _ln_bwd(dout, y2, g2, eps, dy2, dY2, p_hid, ctx.drops[2], Gg2, Gb2, Go2b, M, d, amax=amax2, side_final=bool(_SIDE_OVERLAP & 1))
+        if half and (_SIDE_OVERLAP & 1):
+            out_h = (torch.empty(M, d, dtype=torch.float16, device=dev), torch.empty(4, dtype=torch.float32, device=dev))
+            with side_branch():
+                dY2h, inv2 = scaled_f16(dY2, amax2, out=out_h)
         # ---- FFN2: dgrad (fused with the stored GELU') and wgrad
         dh = torch.empty(M, F, dtype=gdt, device=dev)
         gemm(operand(dY2, "a", False, fmt=wfmt), False, weight_operand([o2w], True, fmt=wfmt), True, M, F, d, dh, act=4, aux=h)
+        if _SIDE_OVERLAP & 1:
+            join_side()
         with side_branch():                       # b_1 gradient beside the GEMMs that follow
             colsum_into(dh, Gib)
         if half:
-            dY2h, inv2 = scaled_f16(dY2, amax2)
+            if not (_SIDE_OVERLAP & 1):
+                dY2h, inv2 = scaled_f16(dY2, amax2)
             gemm(dY2h, True, operand(g, "b", True), True, d, F, M, Go2w, accumulate=True, alpha_dev=inv2)
         else:
             gemm(operand(dY2, "a", True), True, operand(g, "b", True), True, d, F, M, Go2w, accumulate=True)
@@ -990,18 +1056,34 @@ class BertLayerFn(torch.autograd.Function):
         # ---- LN1 backward (+ dropout mask of the attention output dense, + b_o gradient)
         dy1 = torch.empty(M, d, dtype=torch.float32, device=dev)
         dY1 = torch.empty(M, d, dtype=gdt, device=dev)
-        _ln_bwd(da, y1, g1, eps, dy1, dY1, p_hid, ctx.drops[1], Gg1, Gb1, Gob, M, d, amax=amax2[1:] if half else None)
+        _ln_bwd(da, y1, g1, eps, dy1, dY1, p_hid, ctx.drops[1], Gg1, Gb1, Gob, M, d, amax=amax2[1:] if half else None,
+                side_final=bool(_SIDE_OVERLAP & 2))
+        if half and (_SIDE_OVERLAP & 2):
+            out_h = (torch.empty(M, d, dtype=torch.float16, device=dev), torch.empty(4, dtype=torch.float32, device=dev))
+            with side_branch():
+                dY1h, inv1 = scaled_f16(dY1, amax2[1:], out=out_h)
         # ---- attention output dense
         dctx = torch.empty(M, d, dtype=gdt, device=dev)
         gemm(operand(dY1, "a", False, fmt=wfmt), False, weight_operand([ow], True, fmt=wfmt), True, M, d, d, dctx)
+        prepared = None
+        if _SIDE_OVERLAP & 2:
+            join_side()
+        if _SIDE_OVERLAP & 4:
+            prepared = attention_bwd_workspaces(qkv, lse, dims)
+            if prepared is not None:
+                with side_branch():               # attention-backward preparation beside the weight-gradient product
+                    attention_bwd_prepare(dctx, qkv, ctx_t, lse, dims, prepared)
         if half:
-            dY1h, inv1 = scaled_f16(dY1, amax2[1:])
+            if not (_SIDE_OVERLAP & 2):
+                dY1h, inv1 = scaled_f16(dY1, amax2[1:])
             gemm(dY1h, True, operand(ctx_t, "b", True), True, d, d, M, Gow, accumulate=True, alpha_dev=inv1)
         else:
             gemm(operand(dY1, "a", True), True, operand(ctx_t, "b", True), True, d, d, M, Gow, accumulate=True)
+        if _SIDE_OVERLAP & 4:
+            join_side()
         # ---- attention core
         dqkv = attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p_attn, ctx.drops[0], allow,
-                             keep=keep)
+                             keep=keep, prepared=prepared)
         # ---- fused q|k|v projection: one dgrad, three wgrads (separate parameter gradients)
         with side_branch():                       # q, k, v bias gradients beside the dgrad / wgrad below
             check(lib().samk_colsum3(ptr(dqkv), _dt(dqkv), dqkv.stride(0), M, d, ptr(Gqb), ptr(Gkb), ptr(Gvb),
