@@ -286,11 +286,14 @@ def run_samk(args):
     # Measured at N=2 (profiles/r02_dp_experiments.txt): 13.23 ms/step against 12.64 ms for the plain exchange after the
     # step -- the 8 reserved SMs cost 0.25 ms and the last bucket (TextBERT + its 94 MB embedding table, final only when
     # the backward pass ends) stays exposed at the capped NCCL bandwidth -- so it is opt-in.
-    overlap = world > 1 and os.environ.get("SAMK_DP_OVERLAP", "0") == "1"
+    # SAMK_DP_TRANSPORT=peer: the same bucketed exchange, but through samk_exchange_sum (csrc/exchange.cu: NVSwitch
+    # multicast / NVLink peer memory, blocks small enough to share SMs with the backward GEMMs) -- no SM reservation.
+    transport = os.environ.get("SAMK_DP_TRANSPORT", "peer")
+    overlap = world > 1 and (os.environ.get("SAMK_DP_OVERLAP", "0") == "1" or transport == "peer")
     if world > 1:
         os.environ.setdefault("SAMK_DP_WIRE", "bf16")     # 193 MB on the wire instead of 387 MB (SAMK_DP_WIRE=f32: exact sum)
-    reserve = int(os.environ.get("SAMK_DP_RESERVE_SMS", "8"))
-    if overlap:
+    reserve = int(os.environ.get("SAMK_DP_RESERVE_SMS", "8")) if transport != "peer" else 0
+    if overlap and transport != "peer":
         os.environ.setdefault("NCCL_MAX_CTAS", str(reserve))
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -316,9 +319,23 @@ def run_samk(args):
     grads = optim.flat_grad_buffer_for(groups)
     opt = optim.FlatAdam(groups, grads, lr=1e-4, max_grad_norm=0.25)
     if overlap:
-        grads.enable_overlap(average=False, bucket_bytes=int(os.environ.get("SAMK_DP_BUCKET_MB", "32")) << 20)
-        from sam_textvqa_b200._lib import lib as _samk_lib
-        _samk_lib().samk_reserve_sms(reserve)
+        wire_dt = torch.bfloat16 if os.environ.get("SAMK_DP_WIRE", "bf16") == "bf16" else torch.float32
+        try:
+            grads.enable_overlap(average=False, bucket_bytes=int(os.environ.get("SAMK_DP_BUCKET_MB", "32")) << 20,
+                                 transport=transport, wire_dtype=wire_dt)
+            ok = torch.ones(1, device=dev)
+        except Exception as exc:               # e.g. no peer access / symmetric memory on this box: say so, use the library path
+            print("bench: peer exchange unavailable on rank %d (%r)" % (rank, exc), file=sys.stderr, flush=True)
+            ok = torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok) == 0.0:                   # all ranks take the same path
+            ops.grad_ready_hook = None
+            if hasattr(grads, "_ov"):
+                del grads._ov
+            overlap, transport, reserve = False, "nccl", 0
+        if reserve:
+            from sam_textvqa_b200._lib import lib as _samk_lib
+            _samk_lib().samk_reserve_sms(reserve)
     exchange = dp.GradExchange(grads, world, overlapped=overlap) if world > 1 else None
     B = args.batch
 
@@ -418,6 +435,9 @@ def run_samk(args):
     launches = ops.launch_count - l0
     if graphed is not None:                    # replays do not pass through the Python counters
         launches = (graphed.kernels_per_replay + (exchange.kernels_per_call if exchange else 0)) * args.steps
+    if overlap and grads._ov.get("peer") is not None:
+        torch.cuda.synchronize()
+        grads._ov["peer"].check()              # a rank that missed a barrier would have produced garbage, not a number
 
     # ---- end to end: every step's inputs come from pinned host memory; the copy of step i+1 runs on a
     # side stream while step i computes (double-buffered device staging), and every step's loss is read

@@ -236,6 +236,27 @@ int samk_sumsq(const float* x, long long n, double* out_accum, void* stream);
 int samk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, double lr, double beta1,
                    double beta2, double eps, int step, const double* grad_sumsq, double max_norm, void* stream);
 
+/* ---- gradient exchange over NVLink peer memory ---------------------------------------------------
+ * Replaces the gradient reduction of nn.DataParallel (/root/reference/train.py:111-112): flat[lo:hi] = SUM over the ranks
+ * of flat[lo:hi], through a symmetric "wire" allocation that every rank maps from every other rank (and, on NVSwitch,
+ * once more as a multicast address: the switch then adds the ranks' copies, multimem.ld_reduce / multimem.st).
+ * Five small launches on `stream` (pack | barrier | reduce this rank's shard | barrier | unpack); no shared memory and few
+ * registers, so the blocks run on SMs whose shared memory the backward GEMMs own.  Every rank must issue the same calls
+ * in the same order.  lo, hi: multiples of 8 elements (bf16 wire) / 4 (f32 wire); the wire holds element i of the flat
+ * index space at offset i.  A rank that does not arrive within timeout_clocks sets *error (no hang). */
+typedef struct samk_peer_wire {
+  int rank, world;
+  int wire_dtype;                     /* SAMK_DT_BF16 (sum accumulated in fp32, rounded once) or SAMK_DT_F32 */
+  void* const* wire_peers;            /* HOST array [world]: the wire allocation of rank r as mapped here; [rank] = local copy */
+  void* wire_mc;                      /* multicast mapping of the wire allocation, or NULL (peer loads / stores instead) */
+  unsigned int* const* flag_peers;    /* HOST array [world]: a symmetric pad of >= world uint32 per rank, zeroed before the
+                                         first call (by every rank, followed by a host-side barrier) */
+  unsigned int* epoch;                /* local device uint32, zeroed before the first call */
+  int* error;                         /* local device int, zeroed before the first call */
+  long long timeout_clocks;           /* 0 = 4e9 SM clocks */
+} samk_peer_wire;
+int samk_exchange_sum(const samk_peer_wire* w, float* flat, long long lo, long long hi, void* stream);
+
 /* ---- masked multi-head attention -------------------------------------------------------------
  * Replaces SpatialBertSelfAttention.forward steps (1),(3)-(7) (sa_m4c.py:475-552, 562-598) and
  * the BertSelfAttention of the 'n' layers / TextBert (sa_m4c.py:743, 391); the [B,L,L,H] masks are

@@ -37,6 +37,12 @@ class AttnParams(ctypes.Structure):
     ]
 
 
+class PeerWire(ctypes.Structure):
+    _fields_ = [("rank", c_int), ("world", c_int), ("wire_dtype", c_int), ("wire_peers", ctypes.POINTER(c_void_p)),
+                ("wire_mc", c_void_p), ("flag_peers", ctypes.POINTER(c_void_p)), ("epoch", c_void_p), ("error", c_void_p),
+                ("timeout_clocks", c_ll)]
+
+
 # name -> (restype, argtypes); must list every symbol include/samk.h declares
 SIGNATURES = {
     "samk_version": (c_int, []),
@@ -59,6 +65,7 @@ SIGNATURES = {
     "samk_cast_16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
     "samk_cast_dual": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p]),
     "samk_cast_flat": (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_void_p]),
+    "samk_exchange_sum": (c_int, [ctypes.POINTER(PeerWire), c_void_p, c_ll, c_ll, c_void_p]),
     "samk_cast_scaled_f16": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
     "samk_split3_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
     "samk_l2norm": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),

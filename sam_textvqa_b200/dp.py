@@ -22,7 +22,8 @@ class FlatGradBuffer(object):
         self.params = [p for p in params if p.requires_grad]
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._storage = torch.zeros((total + 63) // 64 * 64, dtype=torch.float32, device=dev)   # (padding: whole wire vectors)
+        self.flat = self._storage[:total]
         off = 0
         for p in self.params:
             n = p.numel()
@@ -51,10 +52,17 @@ class FlatGradBuffer(object):
     # PrevPredEmbeddings) is ready after its last report; the number of reports per parameter is learned in
     # the first step.  Maximal runs of ready, not yet reduced parameters are all-reduced on a side stream as
     # soon as they reach `bucket_bytes`, so the NVLink exchange runs under the rest of the backward pass.
-    def enable_overlap(self, group=None, average=False, bucket_bytes=48 << 20):
+    def enable_overlap(self, group=None, average=False, bucket_bytes=48 << 20, transport="nccl", wire_dtype=torch.bfloat16):
+        """transport "nccl": bucketed ncclAllReduce on a side stream; "peer": samk_exchange_sum over NVLink peer memory
+        (PeerWire; collective call -- every rank enables it at the same point)."""
         from . import ops
         self._ov = {"group": group, "average": average, "bucket": int(bucket_bytes), "expected": None,
-                    "seen": {}, "stream": None, "works": []}
+                    "seen": {}, "stream": None, "works": [], "peer": None}
+        if transport == "peer" and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            assert not average, "the peer exchange sums; fold 1/N into the loss scale (global_loss_scale)"
+            self._ov["peer"] = PeerWire(self.flat.numel(), wire_dtype, group)
+        elif transport not in ("nccl", "peer"):
+            self._ov["peer"] = transport                   # an object with .vec and .exchange_sum(storage, lo, hi) (tests)
         self._index = {id(p): i for i, p in enumerate(self.params)}
         offs, off = [], 0
         for p in self.params:
@@ -106,18 +114,49 @@ class FlatGradBuffer(object):
             j = i
             while j < n and not ov["sent"][j] and (ov["ready"][j] or final):
                 j += 1
+            nxt = j
+            if ov["peer"] is not None and not final:
+                # bucket edges on wire-vector boundaries (parameters whose sizes are not multiples of 8 wait for
+                # their neighbours; whatever is left goes out with the final flush)
+                vec = ov["peer"].vec
+                while i < j and self._offs[i] % vec:
+                    i += 1
+                while j > i and self._offs[j] % vec:
+                    j -= 1
+                if j <= i:
+                    i = nxt
+                    continue
             lo, hi = self._offs[i], self._offs[j]
             if final or (hi - lo) * 4 >= ov["bucket"]:
                 self._launch(lo, hi)
                 for k in range(i, j):
                     ov["sent"][k] = True
-            i = j
+            i = nxt
 
     def _launch(self, lo, hi):
         ov = self._ov
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(ov["group"]) == 1:
+        if ov["peer"] is None and (not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(ov["group"]) == 1):
             return
         view = self.flat[lo:hi]
+        peer = ov["peer"]
+        if peer is not None:
+            vec = peer.vec
+            plo, phi = lo, hi
+            if phi == self.flat.numel():
+                phi = (phi + vec - 1) // vec * vec       # (the storage behind `flat` is padded, see __init__)
+            if plo % vec == 0 and phi % vec == 0:
+                if view.is_cuda:
+                    if ov["stream"] is None:
+                        ov["stream"] = torch.cuda.Stream()
+                    ev = torch.cuda.Event()
+                    ev.record()                          # everything enqueued so far produced this slice
+                    with torch.cuda.stream(ov["stream"]):
+                        ov["stream"].wait_event(ev)
+                        peer.exchange_sum(self._storage, plo, phi)
+                else:
+                    peer.exchange_sum(self._storage, plo, phi)
+                return
+            # an unaligned leftover (never with the shipped model): the library collective below
         if view.is_cuda:
             if ov["stream"] is None:
                 ov["stream"] = torch.cuda.Stream()
@@ -154,6 +193,75 @@ class FlatGradBuffer(object):
         if average:
             self.flat.div_(dist.get_world_size(group))
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+class PeerWire(object):
+    """Symmetric wire buffer + flag pads for `samk_exchange_sum` (csrc/exchange.cu): the SUM of a range of the flat
+    gradient buffer over the ranks through NVLink peer memory -- NVSwitch multicast (`multimem.ld_reduce` /
+    `multimem.st`) when the allocation has a multicast mapping, peer loads / stores otherwise.  The kernels are small
+    enough to share SMs with the persistent GEMMs, so the exchange of a finished bucket runs UNDER the rest of the
+    backward pass (FlatGradBuffer.enable_overlap(transport="peer")).  torch's symmetric-memory allocator provides the
+    mappings (plumbing); the data path is ours.  Collective: every rank constructs it at the same point."""
+
+    def __init__(self, n_elems, wire_dtype=torch.bfloat16, group=None, use_multicast=None, timeout_clocks=0):
+        import ctypes
+        import os
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        group = group if group is not None else dist.group.WORLD
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.group, self.wire_dtype = group, wire_dtype
+        self.vec = 8 if wire_dtype == torch.bfloat16 else 4
+        self.n = (int(n_elems) + 63) // 64 * 64
+        self.wire = symm.empty(self.n, dtype=wire_dtype, device=dev)
+        self.hdl = symm.rendezvous(self.wire, group)
+        self.flags = symm.empty(64, dtype=torch.int32, device=dev)
+        self.flags.zero_()
+        self.fhdl = symm.rendezvous(self.flags, group)
+        self.state = torch.zeros(2, dtype=torch.int32, device=dev)          # [epoch, error]
+        self.rank, self.world = int(self.hdl.rank), int(self.hdl.world_size)
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        if use_multicast is None:
+            use_multicast = os.environ.get("SAMK_XCHG_MULTICAST", "1") != "0"
+        self.multicast = bool(mc) and use_multicast
+        self._wire_ptrs = (ctypes.c_void_p * self.world)(*[int(x) for x in self.hdl.buffer_ptrs])
+        self._flag_ptrs = (ctypes.c_void_p * self.world)(*[int(x) for x in self.fhdl.buffer_ptrs])
+        pw = _lib.PeerWire()
+        pw.rank, pw.world = self.rank, self.world
+        pw.wire_dtype = _lib.DT_BF16 if wire_dtype == torch.bfloat16 else _lib.DT_F32
+        pw.wire_peers = ctypes.cast(self._wire_ptrs, ctypes.POINTER(ctypes.c_void_p))
+        pw.wire_mc = mc if self.multicast else None
+        pw.flag_peers = ctypes.cast(self._flag_ptrs, ctypes.POINTER(ctypes.c_void_p))
+        pw.epoch = self.state.data_ptr()
+        pw.error = self.state.data_ptr() + 4
+        pw.timeout_clocks = int(timeout_clocks)
+        self._pw = pw
+        self.launches_per_call = 5
+        self.log = []                                                        # (lo, hi) of every call (tests, describe)
+        torch.cuda.synchronize()
+        dist.barrier(group)                                                  # every pad is zeroed before anyone signals
+
+    def exchange_sum(self, flat, lo, hi):
+        """flat[lo:hi] (fp32, local) <- sum over the ranks, on the current stream.  lo, hi: multiples of self.vec."""
+        import ctypes
+        from . import _lib
+        from ._lib import check, lib, stream_ptr
+        assert flat.dtype == torch.float32 and flat.is_contiguous() and hi <= self.n
+        if len(self.log) < 4096:
+            self.log.append((int(lo), int(hi)))
+        check(lib().samk_exchange_sum(ctypes.byref(self._pw), flat.data_ptr(), int(lo), int(hi), stream_ptr()), "exchange_sum")
+        from . import ops
+        ops._count(self.launches_per_call)
+
+    def check(self):
+        """raises when a rank did not arrive at a barrier in time (call after a synchronize, outside the timed region)"""
+        err = int(self.state[1].item())
+        if err:
+            raise RuntimeError("samk_exchange_sum: rank %d did not arrive in time (seen from rank %d)" % (err - 1, self.rank))
+
+    def describe(self):
+        return ("NVSwitch multicast (multimem.ld_reduce / multimem.st)" if self.multicast else "NVLink peer loads / stores") + \
+            ", %s on the wire" % str(self.wire_dtype).replace("torch.", "")
 
 
 class GradExchange(object):
@@ -202,6 +310,14 @@ class GradExchange(object):
     def describe(self):
         import os
         n = self.grads.flat.numel()
+        if self.overlapped and self.grads._ov.get("peer") is not None:
+            ov = self.grads._ov
+            peer = ov["peer"]
+            return {"collective": "samk_exchange_sum per bucket (>= %d MB of finished gradients) on a side branch of the captured "
+                                  "step, under the backward pass: pack | barrier | reduce own shard | barrier | unpack; %s; "
+                                  "no SMs reserved" % (ov["bucket"] >> 20, peer.describe()),
+                    "wire_dtype": str(peer.wire_dtype).replace("torch.", ""), "bytes": n * (2 if peer.vec == 8 else 4),
+                    "average": "folded into the loss scale (no pass over the buffer)"}
         if self.overlapped:
             ov = self.grads._ov
             return {"collective": "bucketed ncclAllReduce(sum) on a side stream under the backward pass (captured in the step's "

@@ -204,3 +204,48 @@ def test_warmup_schedule_matches_reference_formula_and_flat_adam_needs_gpu():
         optim.FlatAdam(groups, grads, lr=1e-4)
     with pytest.raises(ValueError):          # layout not grouped
         optim.FlatAdam(groups, FlatGradBuffer([w, b]), lr=1e-4)
+
+
+def test_peer_exchange_buckets_are_whole_wire_vectors_and_cover_every_gradient_once():
+    """Bucket logic of the overlapped exchange with the peer transport (dp.FlatGradBuffer._flush / _launch): every range
+    handed to samk_exchange_sum starts and ends on a wire-vector boundary (8 bf16 elements), parameters whose sizes
+    are not multiples of 8 wait for their neighbours, and after finish_step every element went out exactly once."""
+    from sam_textvqa_b200 import dp, ops
+
+    class Stub(object):
+        vec = 8
+
+        def __init__(self):
+            self.ranges = []
+
+        def exchange_sum(self, storage, lo, hi):
+            self.ranges.append((lo, hi))
+
+    sizes = [24, 5, 3, 64, 7, 9, 40, 13]                       # offsets 0 24 29 32 96 103 112 152 -> 165 elements
+    params = [torch.nn.Parameter(torch.zeros(n)) for n in sizes]
+    buf = dp.FlatGradBuffer(params)
+    assert buf._storage.numel() % 64 == 0 and buf.flat.numel() == sum(sizes)
+    stub = Stub()
+    saved = ops.grad_ready_hook
+    try:
+        buf.enable_overlap(bucket_bytes=8 * 4, transport=stub)
+        for step in range(2):                                  # step 0 learns the report counts
+            buf.begin_step()
+            for p in reversed(params):                         # backward order
+                ops.grad_ready_hook([p])
+            if step == 0:
+                buf._ov["expected"] = [buf._ov["seen"].get(i, 0) for i in range(len(params))]
+            else:
+                before_final = list(stub.ranges)
+                buf._flush(final=True)
+    finally:
+        ops.grad_ready_hook = saved
+    total = buf.flat.numel()
+    padded = (total + 7) // 8 * 8
+    assert before_final, "nothing went out before the final flush"
+    covered = [0] * padded
+    for lo, hi in stub.ranges:
+        assert lo % 8 == 0 and hi % 8 == 0 and lo < hi <= padded, (lo, hi)
+        for i in range(lo, hi):
+            covered[i] += 1
+    assert covered == [1] * padded, stub.ranges

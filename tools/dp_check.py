@@ -54,8 +54,28 @@ def main():
 
     shard = dp.shard_batch(full, rank, world)
     scale = dp.global_loss_scale(shard["train_loss_mask"].to(dev))
-    loss = run(shard, scale)
-    dp.GradExchange(grads, world).all_reduce()
+    transport = os.environ.get("SAMK_DP_TRANSPORT", "nccl")
+    buckets = 0
+    if transport == "peer":
+        # overlapped, bucketed exchange through samk_exchange_sum: step 1 learns the report counts (plain all-reduce),
+        # step 2 sends finished buckets under the backward pass
+        grads.enable_overlap(average=False, bucket_bytes=4 << 20, transport="peer")
+        for _ in range(2):
+            grads.zero()
+            grads.begin_step()
+            bd = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in shard.items()}
+            loss = ops.bce_with_mask_loss(model(bd)["textvqa_scores"], bd["targets"], bd["train_loss_mask"]) * scale
+            loss.backward()
+            n0 = ops.launch_count
+            grads.finish_step()
+        loss = loss.detach()
+        torch.cuda.synchronize()
+        grads._ov["peer"].check()
+        buckets = len(getattr(grads._ov["peer"], "log", []))
+        ops.grad_ready_hook = None
+    else:
+        loss = run(shard, scale)
+        dp.GradExchange(grads, world).all_reduce()
     dist.all_reduce(loss)                      # the global loss is the sum of the scaled local ones
     got = grads.flat.clone()
     out = None
@@ -63,7 +83,7 @@ def main():
         ref_loss = run(full, 1.0)
         want = grads.flat
         out = {"world": world, "precision": precision, "loss_dp": float(loss), "loss_single": float(ref_loss),
-               "grad_rel_err": rel_err(got, want), "grad_norm": float(want.norm()),
+               "grad_rel_err": rel_err(got, want), "grad_norm": float(want.norm()), "transport": transport, "buckets": buckets,
                "nccl": ".".join(str(x) for x in torch.cuda.nccl.version())}
     dist.barrier()
     if out is not None:
