@@ -222,7 +222,10 @@ class PeerWire(object):
         self.rank, self.world = int(self.hdl.rank), int(self.hdl.world_size)
         mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
         if use_multicast is None:
-            use_multicast = os.environ.get("SAMK_XCHG_MULTICAST", "1") != "0"
+            # measured (profiles/r02_dp_experiments.txt): two ranks are faster with plain peer loads / stores (each rank
+            # reads half of one peer's buffer), four and eight with the switch doing the additions
+            env = os.environ.get("SAMK_XCHG_MULTICAST")
+            use_multicast = (env != "0") if env is not None else self.world > 2
         self.multicast = bool(mc) and use_multicast
         self._wire_ptrs = (ctypes.c_void_p * self.world)(*[int(x) for x in self.hdl.buffer_ptrs])
         self._flag_ptrs = (ctypes.c_void_p * self.world)(*[int(x) for x in self.fhdl.buffer_ptrs])
