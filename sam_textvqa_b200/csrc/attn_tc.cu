@@ -648,15 +648,29 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   // item -> (query tile, b, h): tiles ascending (the short last tile of every sample comes last); that tile is loaded
   // shifted up on odd iterations so its rows alternate between the lower and the upper TMEM lane quarters
+  // chunked (magic_bh == 0): the (sample, head) pairs are taken gridDim.x at a time -- tile 0 of the whole chunk, then
+  // tile 1 of the same chunk, ... -- so a pair's K/V rows are read again from L2 (a chunk's K/V is ~14 MB), not from DRAM,
+  // and with the static round-robin schedule every CTA still alternates between full and short tiles.
   auto decode = [&](int item, int iter, int& b, int& h, int& q_start, int& q_lo) {
-    const int qi = (int)__umulhi((uint32_t)item, magic_bh);       // exact for item < 2^32 / n_bh
-    const int bh = item - qi * n_bh;
+    int qi, bh;
+    if (magic_bh) {
+      qi = (int)__umulhi((uint32_t)item, magic_bh);               // exact for item < 2^32 / n_bh
+      bh = item - qi * n_bh;
+    } else {
+      const int G = (int)gridDim.x, per = G * (n_qt - a.q_tile0);
+      const int c = item / per, r = item - c * per;
+      const int m = min(G, n_bh - c * G);                         // pairs in this chunk (the last one may be short)
+      qi = r / m;
+      bh = c * G + (r - qi * m);
+    }
     const int qt = a.q_tile0 + qi;
     b = (int)__umulhi((uint32_t)bh, magic_h);
     h = bh - b * H;
     q_lo = qt * 128;
     q_start = qt * 128;
-    if ((iter & 1) && qt == n_qt - 1 && L >= 128 && L - qt * 128 <= 64) q_start = L - 128;
+    // (chunked order: a CTA meets the short tile every (n_qt - q_tile0)-th iteration, so the flip follows that count)
+    const bool flip = magic_bh ? (iter & 1) : ((iter / (n_qt - a.q_tile0)) & 1);
+    if (flip && qt == n_qt - 1 && L >= 128 && L - qt * 128 <= 64) q_start = L - 128;
   };
 
   if (warp == 0) {
@@ -1557,7 +1571,10 @@ static int launch_fwd3(const samk_attn_params* p, const TcArgs& a, cudaStream_t 
   int sms = sm_count();
   if (sms <= 0) sms = 148;
   const int grid = (int)(n_items < 2 * sms ? n_items : 2 * sms);
-  const uint32_t magic_bh = (uint32_t)(((1ull << 32) + n_bh - 1) / n_bh), magic_h = (uint32_t)(((1ull << 32) + a.H - 1) / a.H);
+  static int order = -1;                       // SAMK_ATTN_ORDER: 1 = chunked (default), 0 = all tiles 0, then all tiles 1, ...
+  if (order < 0) { const char* e = getenv("SAMK_ATTN_ORDER"); order = e ? atoi(e) : 1; }
+  const uint32_t magic_bh = order == 1 ? 0u : (uint32_t)(((1ull << 32) + n_bh - 1) / n_bh);
+  const uint32_t magic_h = (uint32_t)(((1ull << 32) + a.H - 1) / a.H);
   attn_fwd3_kernel<KVT><<<grid, kFwd3Threads, Fwd3Cfg<KVT>::kSmem, stream>>>(tq, tkv, a, n_bh, (int)n_items, magic_bh, magic_h);
   return check_launch("samk_attn_fwd(tc v3)");
 }
