@@ -165,6 +165,48 @@ __device__ __forceinline__ void gelu_pair(float x, float& g, float& dg) {
   g = x * cdf;
   dg = fmaf(x * 0.39894228040143267794f, e, cdf);
 }
+// Two elements at a time on the packed fp32 pipe (fma.rn.f32x2 / mul.rn.f32x2, SASS FFMA2 / FMUL2 on sm_100a): the same
+// operations in the same order as gelu_pair -- bit-identical results -- with 14 packed + 8 scalar instructions per
+// pair instead of 36 scalar ones.  The GEMM epilogues that evaluate GELU are issue-bound.
+__device__ __forceinline__ unsigned long long f2_pack(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long f2_splat(float a) { return f2_pack(a, a); }
+
+__device__ __forceinline__ void gelu_pair2(float x0, float x1, float& g0, float& g1, float& d0, float& d1) {
+  const unsigned long long x = f2_pack(x0, x1);
+  const unsigned long long z = f2_mul(f2_pack(fabsf(x0), fabsf(x1)), f2_splat(0.70710678118654752440f));
+  float u0, u1;
+  f2_unpack(f2_fma(f2_splat(0.3275911f), z, f2_splat(1.0f)), u0, u1);
+  const unsigned long long t = f2_pack(ptx_rcp(u0), ptx_rcp(u1));
+  float a0, a1;
+  f2_unpack(f2_mul(f2_mul(x, x), f2_splat(-0.72134752044448170368f)), a0, a1);
+  const unsigned long long e = f2_pack(ptx_ex2(a0), ptx_ex2(a1));
+  // the polynomial with all coefficients negated: np = -poly, so that erf_abs = fma(np * t, e, 1) = fma(-poly * t, e, 1)
+  unsigned long long np = f2_fma(t, f2_splat(-1.061405429f), f2_splat(1.453152027f));
+  np = f2_fma(t, np, f2_splat(-1.421413741f));
+  np = f2_fma(t, np, f2_splat(0.284496736f));
+  np = f2_fma(t, np, f2_splat(-0.254829592f));
+  const unsigned long long erf_abs = f2_fma(f2_mul(np, t), e, f2_splat(1.0f));
+  const unsigned long long cdf = f2_fma(f2_pack(copysignf(0.5f, x0), copysignf(0.5f, x1)), erf_abs, f2_splat(0.5f));
+  f2_unpack(f2_mul(x, cdf), g0, g1);
+  f2_unpack(f2_fma(f2_mul(x, f2_splat(0.39894228040143267794f)), e, cdf), d0, d1);
+}
 __device__ __forceinline__ float gelu_erf(float x) { float g, d; gelu_pair(x, g, d); return g; }
 __device__ __forceinline__ float dgelu_erf(float x) { float g, d; gelu_pair(x, g, d); return d; }
 

@@ -128,14 +128,14 @@ __device__ __forceinline__ void epi_compute(const EpiArgs& ep, EpiRow& e, const 
   if (F & F_GELU_PAIR) {
     // out = gelu(v), pre = gelu'(v): one erf and one exp serve both (backward then only multiplies)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) gelu_pair(v[i], v[i], w[i]);
+    for (int i = 0; i < 8; i += 2) gelu_pair2(v[i], v[i + 1], v[i], v[i + 1], w[i], w[i + 1]);
   } else if (F & F_PRE) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) w[i] = v[i];
   }
   if (F & F_GELU) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+    for (int i = 0; i < 8; i += 2) { float d0, d1; gelu_pair2(v[i], v[i + 1], v[i], v[i + 1], d0, d1); }
   } else if (F & (F_MULAUX | F_DGELU)) {
     float x[8];
     if ((F & F_AUX_BF16) && full) {
