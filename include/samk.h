@@ -253,7 +253,7 @@ typedef struct samk_peer_wire {
                                          first call (by every rank, followed by a host-side barrier) */
   unsigned int* epoch;                /* local device uint32, zeroed before the first call */
   int* error;                         /* local device int, zeroed before the first call */
-  long long timeout_clocks;           /* 0 = 4e9 SM clocks */
+  long long timeout_clocks;           /* 0 = 2e10 SM clocks (~10 s); after the first miss no barrier waits again */
 } samk_peer_wire;
 int samk_exchange_sum(const samk_peer_wire* w, float* flat, long long lo, long long hi, void* stream);
 

@@ -8,6 +8,11 @@
 
 namespace samk {
 
+int sm_count();
+// SMs the grids are sized for (the device's count minus samk_reserve_sms; 148 on a B200)
+static int n_sms() { const int n = sm_count(); return n > 0 ? n : 148; }
+
+
 constexpr int kRowThreads = 256;           // 8 warps per block
 constexpr int kMaxVec = 8;                 // float4 per lane -> cols <= 1024
 
@@ -876,7 +881,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 
 static inline int grid_for(long long work, int per_block) {
   long long g = (work + per_block - 1) / per_block;
-  int cap = 148 * 16;
+  int cap = n_sms() * 16;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 static inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
@@ -1213,7 +1218,7 @@ int samk_colsum(const void* x, int x_dtype, long long ld, int rows, int cols, fl
   }
   const int gx = (cols / 4 + 63) / 64;
   const int threads = colsum_threads(), nrl = threads / 64;
-  int gy = (148 * 1024 / threads + gx - 1) / gx;       // 148 x 1024 threads in all
+  int gy = (n_sms() * 1024 / threads + gx - 1) / gx;   // 1024 threads per SM in all
   if (gy > (rows + nrl - 1) / nrl) gy = (rows + nrl - 1) / nrl;
   if (gy < 1) gy = 1;
   dim3 grid(gx, gy);
@@ -1230,7 +1235,7 @@ int samk_colsum3(const void* x, int x_dtype, long long ld, int rows, int part_co
   const int cols = 3 * part_cols;
   const int gx = (cols / 4 + 63) / 64;
   const int threads = colsum_threads(), nrl = threads / 64;
-  int gy = (148 * 1024 / threads + gx - 1) / gx;       // 148 x 1024 threads in all
+  int gy = (n_sms() * 1024 / threads + gx - 1) / gx;   // 1024 threads per SM in all
   if (gy > (rows + nrl - 1) / nrl) gy = (rows + nrl - 1) / nrl;
   if (gy < 1) gy = 1;
   dim3 grid(gx, gy);
@@ -1259,7 +1264,7 @@ int samk_bert_embed_bwd(const float* dout, const long long* ids, const float* wo
   SAMK_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 1024 && T > 0, "bad size");
   if (!rows) return SAMK_OK;
   // few blocks: each reduces its rows' hot-column gradients in shared memory before touching global memory
-  bert_embed_bwd_kernel<<<grid_for(rows, 32) < 148 ? grid_for(rows, 32) : 148, kRowThreads, 0, (cudaStream_t)stream>>>(
+  bert_embed_bwd_kernel<<<grid_for(rows, 32) < n_sms() ? grid_for(rows, 32) : n_sms(), kRowThreads, 0, (cudaStream_t)stream>>>(
       dout, ids, word, pos, type, gamma, eps, dword, dpos, dtype, dgamma, dbeta, rows, T, cols,
       drop_p > 0.f ? drop_threshold(drop_p) : 0u, drop_keep_scale(drop_p), seed, offset);
   return check_launch(__func__);
@@ -1302,7 +1307,7 @@ int samk_prevpred_bwd(const float* dout, const long long* prev, const float* cls
   g.d_cls_w = grads10[0]; g.d_ocr_in = grads10[1]; g.d_pos = grads10[2]; g.d_type = grads10[3];
   g.d_ans_g = grads10[4]; g.d_ans_b = grads10[5]; g.d_ocr_g = grads10[6]; g.d_ocr_b = grads10[7];
   g.d_emb_g = grads10[8]; g.d_emb_b = grads10[9];
-  const int grid = grid_for((long long)B * D, 16) < 148 ? grid_for((long long)B * D, 16) : 148;
+  const int grid = grid_for((long long)B * D, 16) < n_sms() ? grid_for((long long)B * D, 16) : n_sms();
   prevpred_bwd_kernel<<<grid, kRowThreads, 8 * cols * sizeof(float), (cudaStream_t)stream>>>(p, dout, g);
   return check_launch(__func__);
 }

@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(32) xchg_barrier_kernel(FlagPtrs flags, unsign
     const unsigned int* mine = flags.p[rank] + t;
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(mine) - e) < 0) {
-      if (clock64() - t0 > timeout_clocks) { atomicExch(error, 1 + t); break; }
+      // (once a rank has been missed the results are void anyway: later barriers do not wait again)
+      if (*reinterpret_cast<volatile int*>(error) != 0 || clock64() - t0 > timeout_clocks) { atomicCAS(error, 0, 1 + t); break; }
       __nanosleep(200);
     }
   }
@@ -197,7 +198,7 @@ extern "C" int samk_exchange_sum(const samk_peer_wire* w, float* flat, long long
   FlagPtrs fp;
   for (int r = 0; r < kMaxWorld; ++r) fp.p[r] = r < w->world ? w->flag_peers[r] : nullptr;
   const int blocks = xchg_blocks();
-  const long long timeout = w->timeout_clocks > 0 ? w->timeout_clocks : 4000000000ll;
+  const long long timeout = w->timeout_clocks > 0 ? w->timeout_clocks : 20000000000ll;     // ~10 s
   // 1: pack
   if (bf16) xchg_copy_kernel<true, true><<<blocks, kXchgThreads, 0, stream>>>(flat + lo, wl, n / 4);
   else xchg_copy_kernel<false, true><<<blocks, kXchgThreads, 0, stream>>>(flat + lo, wl, n / 4);

@@ -845,7 +845,8 @@ extern "C" int samk_gemm_16(const void* A, int a_dtype, int a_mn, long long lda,
   {
     const int m_tiles = (M + BM - 1) / BM;
     const long long w256 = (long long)m_tiles * ((N + 255) / 256) * split_k;
-    if (N <= 128 || w256 < 148) bn = 128;
+    const int sms_ = sm_count() > 0 ? sm_count() : 148;
+    if (N <= 128 || w256 < sms_) bn = 128;
   }
   CUtensorMap ta, tb;
   int rc;

@@ -210,6 +210,8 @@ class PeerWire(object):
         from . import _lib
         group = group if group is not None else dist.group.WORLD
         dev = torch.device("cuda", torch.cuda.current_device())
+        if os.environ.get("SAMK_XCHG_FORCE_FAIL", "0") == "1":          # (exercises the callers' fallback to the library path)
+            raise RuntimeError("peer exchange disabled by SAMK_XCHG_FORCE_FAIL")
         self.group, self.wire_dtype = group, wire_dtype
         self.vec = 8 if wire_dtype == torch.bfloat16 else 4
         self.n = (int(n_elems) + 63) // 64 * 64
