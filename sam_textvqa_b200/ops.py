@@ -488,6 +488,17 @@ class side_branch(object):
         return False
 
 
+def branch_stream(i=0):
+    """extra compute streams of this device (sa_m4c.SAM4C.forward runs TextBert and the OCR encoder on them beside
+    the region encoder)"""
+    st = _state()
+    if getattr(st, "branches", None) is None:
+        st.branches = {}
+    if i not in st.branches:
+        st.branches[i] = torch.cuda.Stream(device=torch.cuda.current_device())
+    return st.branches[i]
+
+
 def join_side():
     st = _state()
     if st.side_open:
@@ -508,7 +519,17 @@ class LinearFn(torch.autograd.Function):
         N = weight.shape[0]
         K = kdim
         split = True if strict else None
-        x_op = operand(x2d[:, :K] if x2d.shape[1] != K else x2d, "a", False, split=split)
+        xs = x2d[:, :K] if x2d.shape[1] != K else x2d
+        if (_PRECISION == "f16" and not strict and xs.dtype == torch.float32 and weight.requires_grad and M >= 1024
+                and K % 4 == 0 and xs.stride(1) == 1 and cached_copy(xs, torch.float16) is None):
+            # the half copy this product reads and the bf16 copy its weight-gradient product will read, from ONE pass
+            # over the fp32 input (region / OCR features: 180 MB per step)
+            yh = torch.empty(M, _ceil8(K), dtype=torch.float16, device=xs.device)
+            yb = torch.empty(M, _ceil8(K), dtype=torch.bfloat16, device=xs.device)
+            check(lib().samk_cast_dual(ptr(xs), xs.stride(0), ptr(yh), ptr(yb), yh.stride(0), M, K, stream_ptr()), "cast_dual")
+            _count()
+            remember_act(xs, yh, yb)
+        x_op = operand(xs, "a", False, split=split)
         w_op = weight_operand([weight], False, split=split, kdim=K)
         y = torch.empty(M, N, dtype=torch.float32, device=x2d.device)
         gemm(x_op, False, w_op, False, M, N, K, y, bias=bias)
