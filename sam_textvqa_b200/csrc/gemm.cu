@@ -50,6 +50,9 @@ enum : int {
   F_OUT_F16 = 1 << 14,
   F_PRE_F16 = 1 << 15,
   F_AUX_F16 = 1 << 16,
+  // fp32 output whose rows are only 8-byte aligned (pitch % 2 == 0, e.g. the [B*D, V+R = 5050] score buffer the classifier
+  // writes its V columns into): everything else as F_VEC, the output goes out as four 8-byte stores per 8 columns
+  F_OUT_V2 = 1 << 17,
 };
 constexpr int EPI_DYNAMIC = -1;
 
@@ -225,7 +228,9 @@ __device__ __forceinline__ void epi_store(const EpiArgs& ep, const EpiRow& e, co
     }
   } else {
     float* p = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col;
-    if (full) {
+    if (full && (F & F_OUT_V2)) {
+      _Pragma("unroll") for (int i = 0; i < 8; i += 2) *reinterpret_cast<float2*>(p + i) = make_float2(v[i], v[i + 1]);
+    } else if (full) {
       *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
       *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
     } else {
@@ -759,6 +764,7 @@ constexpr int M_GELU = F_OUT_BF16 | F_OUT_F16 | F_BIAS | F_GELU | F_VEC;        
 constexpr int M_MULAUX = F_OUT_BF16 | F_MULAUX | F_AUX_BF16 | F_VEC;                      // FFN2 dgrad * gelu' (bf16: unpacked by a shift)
 constexpr int M_F32_RES = F_RES | F_VEC;                                                  // FFN1 / qkv dgrad + skip grad
 constexpr int M_F32 = F_VEC;
+constexpr int M_F32_BIAS_V2 = F_BIAS | F_VEC | F_OUT_V2;                                  // classifier columns of the score buffer
 constexpr int M_ATOMIC = F_ATOMIC | F_ALPHA | F_VEC;                                      // wgrad accumulation (alpha: 1 / gradient scale)
 
 }  // namespace samk
@@ -811,10 +817,13 @@ extern "C" int samk_gemm_16(const void* A, int a_dtype, int a_mn, long long lda,
     ep.part_rows = e->part_rows; ep.out1 = e->out_part1; ep.out2 = e->out_part2;
   }
   auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
-  const bool vec_ok = (N % 8 == 0) && al16(ep.out) && (!ep.out1 || (al16(ep.out1) && al16(ep.out2))) && (ep.ldo % 8 == 0) &&
-                      (!ep.bias || al16(ep.bias)) &&
-                      (!ep.pre || (al16(ep.pre) && ep.ldpre % 8 == 0)) && (!ep.aux || (al16(ep.aux) && ep.ldaux % 8 == 0)) &&
-                      (!ep.residual || (al16(ep.residual) && ep.ldres % 4 == 0));
+  const bool rest_ok = (N % 8 == 0) && (!ep.out1 || (al16(ep.out1) && al16(ep.out2))) && (!ep.bias || al16(ep.bias)) &&
+                       (!ep.pre || (al16(ep.pre) && ep.ldpre % 8 == 0)) && (!ep.aux || (al16(ep.aux) && ep.ldaux % 8 == 0)) &&
+                       (!ep.residual || (al16(ep.residual) && ep.ldres % 4 == 0));
+  const bool vec_ok = rest_ok && al16(ep.out) && (ep.ldo % 8 == 0);
+  // 8-byte aligned fp32 rows: vector path with 8-byte output stores
+  const bool vec2_ok = rest_ok && !vec_ok && e->out_dtype == SAMK_DT_F32 && !e->atomic_add && !ep.out1 &&
+                       ((uintptr_t)ep.out & 7) == 0 && (ep.ldo % 2 == 0);
   int flags = 0;
   if (e->out_dtype != SAMK_DT_F32) flags |= F_OUT_BF16 | (e->out_dtype == SAMK_DT_F16 ? F_OUT_F16 : 0);
   if (ep.bias) flags |= F_BIAS;
@@ -830,6 +839,7 @@ extern "C" int samk_gemm_16(const void* A, int a_dtype, int a_mn, long long lda,
   if (e->atomic_add) flags |= F_ATOMIC;
   if (ep.alpha != 1.0f || ep.alpha_dev || e->atomic_add) flags |= F_ALPHA;   // (accumulating launches always: one specialisation)
   if (vec_ok) flags |= F_VEC;
+  if (vec2_ok) flags |= F_VEC | F_OUT_V2;
   ep.flags = flags;
   if (K == 0 && !e->atomic_add) split_k = 1;
 
@@ -857,7 +867,7 @@ extern "C" int samk_gemm_16(const void* A, int a_dtype, int a_mn, long long lda,
   struct Spec { int am, bm, mask; };
   static const Spec kSpecs[] = {{0, 0, M_QKV}, {0, 0, M_OUTPROJ}, {0, 0, M_FFN1}, {0, 0, M_BF16}, {0, 0, M_F32_BIAS},
                                 {0, 0, M_F32_BIAS_RES}, {0, 0, M_GELU}, {0, 0, M_F32}, {0, 1, M_BF16}, {0, 1, M_MULAUX},
-                                {0, 1, M_F32_RES}, {0, 1, M_F32}, {1, 1, M_ATOMIC}};   // keep in step with SAMK_SPEC below
+                                {0, 1, M_F32_RES}, {0, 1, M_F32}, {1, 1, M_ATOMIC}, {0, 0, M_F32_BIAS_V2}};   // keep in step with SAMK_SPEC below
   bool spec = false;
   int spec_idx = -1, si = 0;
   for (const Spec& sp : kSpecs) {
@@ -892,6 +902,7 @@ extern "C" int samk_gemm_16(const void* A, int a_dtype, int a_mn, long long lda,
   SAMK_SPEC(0, 1, M_F32_RES)
   SAMK_SPEC(0, 1, M_F32)
   SAMK_SPEC(1, 1, M_ATOMIC)
+  SAMK_SPEC(0, 0, M_F32_BIAS_V2)
 #undef SAMK_SPEC
 
   // anything else: runtime-flag epilogue

@@ -116,10 +116,13 @@ def _grads_done(*params):
 
 
 def _ln_partials(dev, cols):
+    """scratch of the LayerNorm backward's two-stage reduction: one buffer per (width, STREAM) -- the input encoders and
+    TextBert run their backward passes on different streams at the same time (sa_m4c.SAM4C.forward)"""
     ws = _state(dev).ln_ws
-    if cols not in ws:
-        ws[cols] = torch.empty(int(lib().samk_layernorm_bwd_partials(cols)), dtype=torch.float32, device=dev)
-    return ws[cols]
+    key = (cols, torch.cuda.current_stream().cuda_stream)
+    if key not in ws:
+        ws[key] = torch.empty(int(lib().samk_layernorm_bwd_partials(cols)), dtype=torch.float32, device=dev)
+    return ws[key]
 
 
 def _ln_bwd(dy, x, gamma, eps, dx, dxd, p, drop, dg, db, dbias, rows, cols, amax=None, side_final=False):

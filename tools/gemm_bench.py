@@ -58,3 +58,11 @@ gw1 = torch.zeros(3072, 768, device=dev)
 run("ffn1_wgrad", lambda: g(O(dy3072), True, O(x768b), True, 3072, 768, M, gw1, accumulate=True), 2 * M * 3072 * 768)
 gw2 = torch.zeros(768, 768, device=dev)
 run("sq_wgrad", lambda: g(O(dy768h), True, O(x768), True, 768, 768, M, gw2, accumulate=True), 2 * M * 768 * 768)
+# classifier head: 1536 decoder rows x 5000 answers, 3-term split (K = 3 x 768), fp32 into the [rows, 5050] score buffer
+Mc, Vc, Rc = 1536, 5000, 50
+xs3, wc3 = bf(Mc, 2304), bf(Vc, 2304)
+scores = torch.empty(Mc, Vc + Rc, device=dev)
+bV = f32(Vc)
+run("cls_fwd_5050", lambda: g(O(xs3), False, O(wc3), False, Mc, Vc, 2304, scores[:, :Vc], bias=bV), 2 * Mc * Vc * 2304)
+scores8 = torch.empty(Mc, Vc + Rc + 6, device=dev)
+run("cls_fwd_5056", lambda: g(O(xs3), False, O(wc3), False, Mc, Vc, 2304, scores8[:, :Vc], bias=bV), 2 * Mc * Vc * 2304)
