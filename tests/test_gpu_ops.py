@@ -419,3 +419,27 @@ def test_flat_adam_state_dict_round_trip_and_detached_grads(ops):
     ropt2.load_state_dict({"state": sd["state"], "param_groups": sd["param_groups"]})      # Adam accepts it
     opt.load_state_dict(sd)
     assert opt.step_count == 3
+
+
+@pytest.mark.parametrize("B,D,R,dq", [(5, 12, 50, 768), (3, 1, 7, 64), (2, 20, 33, 1024)])
+def test_pointer_scores_forward_and_backward_match_torch(ops, B, D, R, dq):
+    """OcrPtrNet scoring (sa_m4c.py:878-897): scores[b,t,V+r] = q.k / sqrt(dq) + (1 - mask) * -1e4 written into the
+    pointer columns of the shared [B*D, V+R] buffer, and the gradients of q and k (block-per-sample kernels)."""
+    from sam_textvqa_b200._lib import check, lib, ptr, stream_ptr
+    V = 24
+    g = torch.Generator().manual_seed(B * 131 + D)
+    q = torch.randn(B, D, dq, generator=g).to(DEV)
+    k = torch.randn(B, R, dq, generator=g).to(DEV)
+    mask = (torch.rand(B, R, generator=g) > 0.3).long().to(DEV)
+    out = torch.full((B * D, V + R), 7.0, device=DEV)
+    check(lib().samk_ptr_scores_fwd(ptr(q), ptr(k), ptr(mask), ptr(out), V + R, V, B, D, R, dq, stream_ptr()), "ptr fwd")
+    ref = torch.einsum("btc,brc->btr", q.double(), k.double()) / dq ** 0.5 + (1.0 - mask.double())[:, None, :] * -10000.0
+    got = out.view(B, D, V + R)
+    assert torch.all(got[..., :V] == 7.0)                               # the vocabulary columns are not touched
+    assert (got[..., V:].double() - ref).abs().max().item() < 2e-3 * max(1.0, ref[ref > -5000].abs().max().item())
+    ds = torch.randn(B * D, V + R, generator=g).to(DEV)
+    dq_, dk_ = torch.empty_like(q), torch.empty_like(k)
+    check(lib().samk_ptr_scores_bwd(ptr(ds), V + R, V, ptr(q), ptr(k), ptr(dq_), ptr(dk_), B, D, R, dq, stream_ptr()), "ptr bwd")
+    dsr = ds.view(B, D, V + R)[..., V:].double() / dq ** 0.5
+    assert rel_err(dq_.cpu(), torch.einsum("btr,brc->btc", dsr, k.double()).float().cpu()) < 1e-5
+    assert rel_err(dk_.cpu(), torch.einsum("btr,btc->brc", dsr, q.double()).float().cpu()) < 1e-5
