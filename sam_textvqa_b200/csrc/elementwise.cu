@@ -725,53 +725,44 @@ prevpred_bwd_kernel(PrevPredParams p, const float* __restrict__ dout, PrevPredGr
 // ---------------------------------------------------------------------------------------------
 // Pointer network scores (sa_m4c.py:878-897): out[b,t,V+r] = q[b,t,:].k[b,r,:]/sqrt(dq) + (1-mask[b,r])*-1e4
 // ---------------------------------------------------------------------------------------------
-// One block per sample, one warp per decoding step: the warp keeps its query row in registers and walks the sample's R key
-// rows, which all D warps of the block read at about the same time (L1 hits after the first) -- q and k come from L2
-// once per sample instead of once per (t, r) pair.
-__global__ void __launch_bounds__(512)
-ptr_scores_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const long long* __restrict__ mask,
-                      float* __restrict__ out, long long ldo, int col_off, int B, int D, int R, int dq, float inv_sqrt) {
-  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int t = warp; t < D; t += nw) {
-    const float* qr = q + ((size_t)b * D + t) * dq;
-    float4 qv[kMaxVec];
-#pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
-      const int c = 4 * (lane + 32 * i);
-      qv[i] = c < dq ? *reinterpret_cast<const float4*>(qr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    float* orow = out + ((size_t)b * D + t) * ldo + col_off;
-    for (int r = 0; r < R; ++r) {
-      const float* kr = k + ((size_t)b * R + r) * dq;
-      float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-      for (int i = 0; i < kMaxVec; ++i) {
-        const int c = 4 * (lane + 32 * i);
-        if (c < dq) {
-          const float4 w = *reinterpret_cast<const float4*>(kr + c);
-          s0 += qv[i].x * w.x + qv[i].y * w.y;
-          s1 += qv[i].z * w.z + qv[i].w * w.w;
-        }
-      }
-      const float s = warp_sum(s0 + s1);
-      if (lane == 0) orow[r] = s * inv_sqrt + (1.0f - (float)mask[(size_t)b * R + r]) * -10000.0f;
-    }
+__global__ void ptr_scores_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                      const long long* __restrict__ mask, float* __restrict__ out, long long ldo,
+                                      int col_off, int B, int D, int R, int dq, float inv_sqrt) {
+  // one warp per (b, t, r)
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int total = B * D * R;
+  if (warp >= total) return;
+  const int b = warp / (D * R), t = (warp / R) % D, r = warp % R;
+  const float* qr = q + ((size_t)b * D + t) * dq;
+  const float* kr = k + ((size_t)b * R + r) * dq;
+  float s = 0.f;
+  for (int c = lane * 4; c < dq; c += 128) {
+    float4 a = *reinterpret_cast<const float4*>(qr + c), w = *reinterpret_cast<const float4*>(kr + c);
+    s += a.x * w.x + a.y * w.y + a.z * w.z + a.w * w.w;
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    float m = (1.0f - (float)mask[(size_t)b * R + r]) * -10000.0f;
+    out[((size_t)b * D + t) * ldo + col_off + r] = s * inv_sqrt + m;
   }
 }
 
 // dq[b,t,:] = inv * sum_r ds[b,t,r] k[b,r,:] ; dk[b,r,:] = inv * sum_t ds[b,t,r] q[b,t,:]
-// Same decomposition: one block per sample; warp t accumulates its dq row over the sample's key rows, then the warps
-// share out the R rows of dk, each summed over the sample's D query rows (both operands of a sample stay in L1).
-__global__ void __launch_bounds__(512)
-ptr_scores_bwd_kernel(const float* __restrict__ ds, long long ldds, int col_off, const float* __restrict__ q,
-                      const float* __restrict__ k, float* __restrict__ dq_, float* __restrict__ dk_, int B, int D, int R, int dq,
-                      float inv_sqrt) {
-  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int t = warp; t < D; t += nw) {
-    float4 acc[kMaxVec];
+__global__ void ptr_scores_bwd_kernel(const float* __restrict__ ds, long long ldds, int col_off,
+                                      const float* __restrict__ q, const float* __restrict__ k, float* __restrict__ dq_,
+                                      float* __restrict__ dk_, int B, int D, int R, int dq, float inv_sqrt) {
+  // one warp per output row: first B*D rows of dq then B*R rows of dk
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nq = B * D, nk = B * R;
+  if (warp >= nq + nk) return;
+  // all column chunks of the row are accumulated together: kMaxVec independent loads in flight per step of the
+  // (short, latency-bound) contraction loop
+  float4 acc[kMaxVec];
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* dsr = ds + ((size_t)b * D + t) * ldds + col_off;
+  for (int i = 0; i < kMaxVec; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (warp < nq) {
+    const int b = warp / D;
+    const float* dsr = ds + (size_t)warp * ldds + col_off;
     for (int r = 0; r < R; ++r) {
       const float w = dsr[r] * inv_sqrt;
       const float* kr = k + ((size_t)b * R + r) * dq;
@@ -787,13 +778,10 @@ ptr_scores_bwd_kernel(const float* __restrict__ ds, long long ldds, int col_off,
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) {
       const int c = 4 * (lane + 32 * i);
-      if (c < dq) *reinterpret_cast<float4*>(dq_ + ((size_t)b * D + t) * dq + c) = acc[i];
+      if (c < dq) *reinterpret_cast<float4*>(dq_ + (size_t)warp * dq + c) = acc[i];
     }
-  }
-  for (int r = warp; r < R; r += nw) {
-    float4 acc[kMaxVec];
-#pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    const int row = warp - nq, b = row / R, r = row % R;
     for (int t = 0; t < D; ++t) {
       const float w = ds[((size_t)b * D + t) * ldds + col_off + r] * inv_sqrt;
       const float* qr = q + ((size_t)b * D + t) * dq;
@@ -809,7 +797,7 @@ ptr_scores_bwd_kernel(const float* __restrict__ ds, long long ldds, int col_off,
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) {
       const int c = 4 * (lane + 32 * i);
-      if (c < dq) *reinterpret_cast<float4*>(dk_ + ((size_t)b * R + r) * dq + c) = acc[i];
+      if (c < dq) *reinterpret_cast<float4*>(dk_ + (size_t)row * dq + c) = acc[i];
     }
   }
 }
@@ -1326,19 +1314,19 @@ int samk_prevpred_bwd(const float* dout, const long long* prev, const float* cls
 
 int samk_ptr_scores_fwd(const float* q, const float* k, const long long* ocr_mask, float* out, long long ldo,
                         int col_off, int B, int D, int R, int dq, void* stream) {
-  SAMK_REQUIRE(q && k && ocr_mask && out && dq % 4 == 0 && dq <= 1024, "bad argument (ptr_query_size <= 1024, a multiple of 4)");
-  if (!B || !D || !R) return SAMK_OK;
-  const int warps_f = D < 16 ? D : 16;
-  ptr_scores_fwd_kernel<<<(unsigned)B, 32 * warps_f, 0, (cudaStream_t)stream>>>(q, k, ocr_mask, out, ldo, col_off, B, D, R, dq, 1.0f / sqrtf((float)dq));
+  SAMK_REQUIRE(q && k && ocr_mask && out && dq % 4 == 0, "bad argument");
+  long long warps = (long long)B * D * R;
+  if (!warps) return SAMK_OK;
+  ptr_scores_fwd_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(q, k, ocr_mask, out, ldo, col_off, B, D, R, dq, 1.0f / sqrtf((float)dq));
   return check_launch(__func__);
 }
 
 int samk_ptr_scores_bwd(const float* dscores, long long ldds, int col_off, const float* q, const float* k, float* dq_,
                         float* dk_, int B, int D, int R, int dq, void* stream) {
   SAMK_REQUIRE(dscores && q && k && dq_ && dk_ && dq % 4 == 0 && dq <= 1024, "bad argument (ptr_query_size <= 1024)");
-  if (!B || !(D + R)) return SAMK_OK;
-  const int warps_b = D < 16 ? (D > 0 ? D : 1) : 16;
-  ptr_scores_bwd_kernel<<<(unsigned)B, 32 * warps_b, 0, (cudaStream_t)stream>>>(dscores, ldds, col_off, q, k, dq_, dk_, B, D, R, dq, 1.0f / sqrtf((float)dq));
+  long long warps = (long long)B * (D + R);
+  if (!warps) return SAMK_OK;
+  ptr_scores_bwd_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(dscores, ldds, col_off, q, k, dq_, dk_, B, D, R, dq, 1.0f / sqrtf((float)dq));
   return check_launch(__func__);
 }
 

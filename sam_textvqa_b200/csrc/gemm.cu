@@ -211,7 +211,10 @@ __device__ __forceinline__ void epi_store(const EpiArgs& ep, const EpiRow& e, co
       base = part == 0 ? ep.out : (part == 1 ? ep.out1 : ep.out2);
     }
     float* p = reinterpret_cast<float*>(base) + (size_t)prow * ep.ldo + col;
-    if (full) {
+    if (full && (F & F_OUT_V2)) {
+      _Pragma("unroll") for (int i = 0; i < 8; i += 2)
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p + i), "f"(v[i]), "f"(v[i + 1]) : "memory");
+    } else if (full) {
       asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
       asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
     } else {
@@ -766,6 +769,7 @@ constexpr int M_F32_RES = F_RES | F_VEC;                                        
 constexpr int M_F32 = F_VEC;
 constexpr int M_F32_BIAS_V2 = F_BIAS | F_VEC | F_OUT_V2;                                  // classifier columns of the score buffer
 constexpr int M_ATOMIC = F_ATOMIC | F_ALPHA | F_VEC;                                      // wgrad accumulation (alpha: 1 / gradient scale)
+constexpr int M_ATOMIC_V2 = M_ATOMIC | F_OUT_V2;                                          // ... into a gradient whose rows are 8-byte aligned (OCR projection: pitch 3002)
 
 }  // namespace samk
 
@@ -822,7 +826,7 @@ extern "C" int samk_gemm_16(const void* A, int a_dtype, int a_mn, long long lda,
                        (!ep.residual || (al16(ep.residual) && ep.ldres % 4 == 0));
   const bool vec_ok = rest_ok && al16(ep.out) && (ep.ldo % 8 == 0);
   // 8-byte aligned fp32 rows: vector path with 8-byte output stores
-  const bool vec2_ok = rest_ok && !vec_ok && e->out_dtype == SAMK_DT_F32 && !e->atomic_add && !ep.out1 &&
+  const bool vec2_ok = rest_ok && !vec_ok && e->out_dtype == SAMK_DT_F32 && !ep.out1 &&
                        ((uintptr_t)ep.out & 7) == 0 && (ep.ldo % 2 == 0);
   int flags = 0;
   if (e->out_dtype != SAMK_DT_F32) flags |= F_OUT_BF16 | (e->out_dtype == SAMK_DT_F16 ? F_OUT_F16 : 0);
@@ -867,7 +871,7 @@ extern "C" int samk_gemm_16(const void* A, int a_dtype, int a_mn, long long lda,
   struct Spec { int am, bm, mask; };
   static const Spec kSpecs[] = {{0, 0, M_QKV}, {0, 0, M_OUTPROJ}, {0, 0, M_FFN1}, {0, 0, M_BF16}, {0, 0, M_F32_BIAS},
                                 {0, 0, M_F32_BIAS_RES}, {0, 0, M_GELU}, {0, 0, M_F32}, {0, 1, M_BF16}, {0, 1, M_MULAUX},
-                                {0, 1, M_F32_RES}, {0, 1, M_F32}, {1, 1, M_ATOMIC}, {0, 0, M_F32_BIAS_V2}};   // keep in step with SAMK_SPEC below
+                                {0, 1, M_F32_RES}, {0, 1, M_F32}, {1, 1, M_ATOMIC}, {0, 0, M_F32_BIAS_V2}, {1, 1, M_ATOMIC_V2}};   // keep in step with SAMK_SPEC below
   bool spec = false;
   int spec_idx = -1, si = 0;
   for (const Spec& sp : kSpecs) {
@@ -903,6 +907,7 @@ extern "C" int samk_gemm_16(const void* A, int a_dtype, int a_mn, long long lda,
   SAMK_SPEC(0, 1, M_F32)
   SAMK_SPEC(1, 1, M_ATOMIC)
   SAMK_SPEC(0, 0, M_F32_BIAS_V2)
+  SAMK_SPEC(1, 1, M_ATOMIC_V2)
 #undef SAMK_SPEC
 
   // anything else: runtime-flag epilogue

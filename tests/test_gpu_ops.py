@@ -443,3 +443,26 @@ def test_pointer_scores_forward_and_backward_match_torch(ops, B, D, R, dq):
     dsr = ds.view(B, D, V + R)[..., V:].double() / dq ** 0.5
     assert rel_err(dq_.cpu(), torch.einsum("btr,brc->btc", dsr, k.double()).float().cpu()) < 1e-5
     assert rel_err(dk_.cpu(), torch.einsum("btr,btc->brc", dsr, q.double()).float().cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_gemm_output_rows_only_8_byte_aligned(ops, accumulate):
+    """fp32 output with an even pitch that is not a multiple of 4 (the classifier columns of the [rows, 5050] score buffer,
+    the OCR projection's [768, 3002] weight gradient): the vector epilogue with 8-byte stores / red.v2 must equal torch."""
+    g = torch.Generator().manual_seed(11)
+    M, N, K, pitch = 512, 264, 192, 270
+    A = (torch.randn(M, K, generator=g) * 0.5).to(DEV).half()
+    B = (torch.randn(N, K, generator=g) * 0.5).to(DEV).half()
+    bias = torch.randn(N, generator=g).to(DEV)
+    buf = torch.full((M, pitch), 3.0, device=DEV)
+    O = lambda t: ops.Operand(t, t.stride(0), 1)
+    ref = A.float() @ B.float().t()
+    if accumulate:
+        At, Bt = A.t().contiguous(), B.t().contiguous()              # stored [K, M] / [K, N]: both MN-major (the wgrad form)
+        ops.gemm(O(At), True, O(Bt), True, M, N, K, buf[:, :N], accumulate=True)
+        want = ref + 3.0
+    else:
+        ops.gemm(O(A), False, O(B), False, M, N, K, buf[:, :N], bias=bias)
+        want = ref + bias
+    assert torch.all(buf[:, N:] == 3.0)
+    assert rel_err(buf[:, :N].cpu(), want.cpu()) < 2e-3
