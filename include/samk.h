@@ -141,6 +141,10 @@ int samk_split3_bf16(const float* x, long long ldx, void* y, long long ldy, int 
 /* F.normalize(x, dim=-1) of sa_m4c.py:208-209,224-238 (normalize=0: plain copy/cast) */
 int samk_l2norm(const float* x, long long ldx, void* y, long long ldy, int y_dtype, int rows, int cols, int normalize,
                 void* stream);
+/* the same with two outputs from one pass over x (the half copy the feature projection reads and the bf16 copy its
+ * weight-gradient product reads: the normalised fp32 features are then never materialised) */
+int samk_l2norm2(const float* x, long long ldx, void* y, long long ldy, int y_dtype, void* y2, long long ldy2, int y2_dtype,
+                 int rows, int cols, int normalize, void* stream);
 /* BertLayerNorm (sa_m4c.py:1016-1028; eps inside the sqrt, biased variance).  y fp32 and/or y2 in
  * y2_dtype and/or y3 in y3_dtype (the f16 copy the next contraction reads and the bf16 copy its weight-gradient
  * product reads, written in the same pass).  Backward: dx fp32; optional dxd = dropout_mask(dx) in dxd_dtype (gradient of the dense

@@ -69,6 +69,7 @@ SIGNATURES = {
     "samk_cast_scaled_f16": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
     "samk_split3_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
     "samk_l2norm": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
+    "samk_l2norm2": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
     "samk_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                    c_int, c_void_p]),
     "samk_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_float, c_ull,

@@ -110,7 +110,7 @@ __global__ void split3_kernel(const float* __restrict__ x, long long ldx, __nv_b
 // F.normalize(x, dim=-1) (sa_m4c.py:208-209, 224-238): y = x / max(||x||_2, 1e-12)
 // ---------------------------------------------------------------------------------------------
 __global__ void l2norm_kernel(const float* __restrict__ x, long long ldx, void* __restrict__ y, long long ldy,
-                              int y_bf16, int rows, int cols, int normalize) {
+                              int y_bf16, void* __restrict__ y2, long long ldy2, int y2_bf16, int rows, int cols, int normalize) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int r = warp; r < rows; r += nwarps) {
@@ -126,6 +126,7 @@ __global__ void l2norm_kernel(const float* __restrict__ x, long long ldx, void* 
       float4 v = *reinterpret_cast<const float4*>(xr + c);
       v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
       store_act(y, y_bf16, (size_t)r * ldy + c, v);
+      if (y2) store_act(y2, y2_bf16, (size_t)r * ldy2 + c, v);
     }
   }
 }
@@ -1112,7 +1113,17 @@ int samk_l2norm(const float* x, long long ldx, void* y, long long ldy, int y_dty
   SAMK_REQUIRE(x && y && rows >= 0 && cols >= 0, "bad argument");
   SAMK_REQUIRE(cols % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && al16(x) && ((uintptr_t)y & 7) == 0, "cols/ld must be multiples of 4");
   if (!rows || !cols) return SAMK_OK;
-  l2norm_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, y_dtype, rows, cols, normalize);
+  l2norm_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, y_dtype, nullptr, 0, 0, rows, cols, normalize);
+  return check_launch(__func__);
+}
+
+int samk_l2norm2(const float* x, long long ldx, void* y, long long ldy, int y_dtype, void* y2, long long ldy2, int y2_dtype,
+                 int rows, int cols, int normalize, void* stream) {
+  SAMK_REQUIRE(x && y && y2 && rows >= 0 && cols >= 0, "bad argument");
+  SAMK_REQUIRE(cols % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldy2 % 4 == 0 && al16(x) && ((uintptr_t)y & 7) == 0 &&
+               ((uintptr_t)y2 & 7) == 0, "cols/ld must be multiples of 4");
+  if (!rows || !cols) return SAMK_OK;
+  l2norm_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, y_dtype, y2, ldy2, y2_dtype, rows, cols, normalize);
   return check_launch(__func__);
 }
 

@@ -555,6 +555,12 @@ class LinearFn(torch.autograd.Function):
         dy_k = operand(dy_act, "a", False, fmt="bf16")          # [M, N] K-major for dgrad
         dy_mn = operand(dy_act, "a", True, fmt="bf16")          # stored [tokens, N]: MN-major for wgrad
         xs = x2d[:, :K] if x2d.shape[1] != K else x2d
+        if xs.dtype == torch.float16:
+            # a half input made by its producer together with a bf16 copy (sa_m4c._feature_buffers): gradients are bf16
+            xb = cached_copy(xs, torch.bfloat16)
+            if xb is None:
+                raise _lib.SamkError("a half input of ops.linear needs a registered bf16 copy for its weight gradient")
+            xs = xb
         x_mn = operand(xs, "b", True, fmt="bf16")
         dx = None
         if ctx.x_needs_grad:
@@ -643,6 +649,20 @@ def l2norm_into(x3d, out2d, col_off, normalize):
     dst = out2d[:, col_off:col_off + x2d.shape[1]]
     check(lib().samk_l2norm(ptr(x2d), x2d.stride(0), ptr(dst), out2d.stride(0), _dt(out2d), x2d.shape[0],
                             x2d.shape[1], 1 if normalize else 0, stream_ptr()), "l2norm")
+    _count()
+
+
+def l2norm_into2(x3d, out_a, out_b, col_off, normalize):
+    """two 16-bit destinations from one pass over x (see samk_l2norm2); out_b may be None"""
+    if out_b is None:
+        return l2norm_into(x3d, out_a, col_off, normalize)
+    _cuda(x3d, out_a, out_b)
+    x2d = x3d.reshape(-1, x3d.shape[-1])
+    assert x2d.stride(1) == 1
+    d = x2d.shape[1]
+    check(lib().samk_l2norm2(ptr(x2d), x2d.stride(0), ptr(out_a[:, col_off:col_off + d]), out_a.stride(0), _dt(out_a),
+                             ptr(out_b[:, col_off:col_off + d]), out_b.stride(0), _dt(out_b), x2d.shape[0], d,
+                             1 if normalize else 0, stream_ptr()), "l2norm2")
     _count()
 
 
