@@ -551,7 +551,12 @@ class LinearFn(torch.autograd.Function):
         dW, db = _gbuf(weight), _gbuf(ctx_bias)
         with side_branch():
             colsum_into(dy, db[0])
-        dy_act = dy if _PRECISION != "f16" else cast_16(dy, torch.bfloat16)[:, :N]
+        if _PRECISION != "f16":
+            dy_act = dy
+        else:
+            dy_act = cached_copy(dy, torch.bfloat16) if dy.shape[1] % 8 == 0 else None      # (written by the LayerNorm backward)
+            if dy_act is None:
+                dy_act = cast_16(dy, torch.bfloat16)[:, :N]
         dy_k = operand(dy_act, "a", False, fmt="bf16")          # [M, N] K-major for dgrad
         dy_mn = operand(dy_act, "a", True, fmt="bf16")          # stored [tokens, N]: MN-major for wgrad
         xs = x2d[:, :K] if x2d.shape[1] != K else x2d
@@ -598,7 +603,14 @@ class LayerNormFn(torch.autograd.Function):
         dy = dy.contiguous()
         dx = torch.empty_like(x2d)
         dg, db = _gbuf(gamma), _gbuf(ctx.beta_ref)
-        _ln_bwd(dy, x2d, gamma, ctx.eps, dx, None, 0.0, (0, 0), dg[0], db[0], None, x2d.shape[0], x2d.shape[1])
+        dxd = None
+        if _PRECISION == "f16" and x2d.shape[0] >= 1024 and x2d.shape[1] % 8 == 0:
+            # the producer of x is a projection whose backward reads dx in bf16 (LinearFn.backward): written by this
+            # kernel in the same pass instead of a separate cast
+            dxd = torch.empty(x2d.shape, dtype=torch.bfloat16, device=x2d.device)
+        _ln_bwd(dy, x2d, gamma, ctx.eps, dx, dxd, 0.0, (0, 0), dg[0], db[0], None, x2d.shape[0], x2d.shape[1])
+        if dxd is not None:
+            remember_act(dx, dxd)
         _grads_done(gamma, ctx.beta_ref)
         return dx, _ret(dg), _ret(db), None
 
@@ -1257,7 +1269,7 @@ class OutputFn(torch.autograd.Function):
         ddec = torch.empty(B * D, d, dtype=torch.float32, device=dev)
         gemm(operand(dsv, "a", False, fmt="bf16"), False, weight_operand([cw], True, fmt="bf16"), True, B * D, d, V, ddec)
         gemm(operand(dsv, "a", True, fmt="bf16"), True, dec_mn, True, V, d, B * D, Gcw, accumulate=True)
-        colsum_into(ds[:, :V], Gcb)
+        colsum_into(dsv if dsv.dtype != torch.float32 else ds[:, :V], Gcb)      # (the bf16 copy: vector loads, half the bytes)
         # pointer query / key projections
         ddec2 = torch.empty(B * D, d, dtype=torch.float32, device=dev)
         gemm(operand(dq_a, "a", False, fmt="bf16"), False, weight_operand([qw], True, fmt="bf16"), True, B * D, d, dq, ddec2, residual=ddec)
