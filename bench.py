@@ -474,8 +474,18 @@ def run_samk(args):
     # ---- end to end: every step's inputs come from pinned host memory; the copy of step i+1 runs on a
     # side stream while step i computes (double-buffered device staging), and every step's loss is read
     # back to the host.  All K uploads and K loss reads are inside the timed region.
+    # With the captured step the uploads land DIRECTLY in the step's static input buffers: the step is captured twice
+    # (two GraphedTrainStep objects, each with its own input buffers) and the replays alternate, so step i+1's upload
+    # runs while step i computes without a device-to-device hop in between (SAMK_BENCH_E2E_GRAPHS=1: one captured step fed
+    # through double-buffered staging + a device-to-device load, the round-1 form).
     copy_stream = torch.cuda.Stream()
-    staged = [({k: torch.empty_like(v) for k, v in resident.items()}, torch.empty_like(resident_adj)) for _ in range(2)]
+    two_graphs = graphed is not None and os.environ.get("SAMK_BENCH_E2E_GRAPHS", "2") == "2"
+    graphs = [graphed]
+    if two_graphs:
+        graphs.append(GraphedTrainStep(model, grads, ex, loss_fn=loss_of, allreduce="overlap" if overlap else None))
+        staged = None
+    else:
+        staged = [({k: torch.empty_like(v) for k, v in resident.items()}, torch.empty_like(resident_adj)) for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
     for ev in consumed:
@@ -484,11 +494,16 @@ def run_samk(args):
     def stage(slot):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])
-            bufs, abuf = staged[slot]
-            for k in names:
-                bufs[k].copy_(pinned[k], non_blocking=True)
-            if not dev_graph:
-                abuf.copy_(pinned_adj, non_blocking=True)
+            if two_graphs:
+                graphs[slot].load(pinned)                        # host (pinned) -> the static inputs of that captured step
+                if not dev_graph:
+                    graphs[slot].load({"spatial_adj_matrices": {"3": pinned_adj}})
+            else:
+                bufs, abuf = staged[slot]
+                for k in names:
+                    bufs[k].copy_(pinned[k], non_blocking=True)
+                if not dev_graph:
+                    abuf.copy_(pinned_adj, non_blocking=True)
             ready[slot].record(copy_stream)
 
     host_loss = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -501,14 +516,18 @@ def run_samk(args):
             torch.cuda.current_stream().wait_event(ready[i % 2])
             if i + 1 < steps:
                 stage((i + 1) % 2)
-            up, a = staged[i % 2]
-            if graphed is not None:                   # inputs are taken by the device-to-device load in front of the replay
+            if two_graphs:
+                loss = graphs[i % 2].run()
+                consumed[i % 2].record()              # (the replay reads its inputs until it ends)
+            elif graphed is not None:                 # inputs are taken by the device-to-device load in front of the replay
+                up, a = staged[i % 2]
                 graphed.load(up)
                 if not dev_graph:
                     graphed.load({"spatial_adj_matrices": {"3": a}})
                 consumed[i % 2].record()
                 loss = graphed.run()
             else:
+                up, a = staged[i % 2]
                 loss = fwd_bwd(up, a)
                 consumed[i % 2].record()
             if exchange is not None:
