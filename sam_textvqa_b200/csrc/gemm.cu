@@ -5,8 +5,9 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128B swizzle, kStages-deep mbarrier ring)
 //   warp 1      MMA issuer     (one elected lane issues tcgen05.mma, accumulators in TMEM,
 //                               two accumulator buffers so the epilogue overlaps the next tile)
-//   warps 2..5  epilogue       (tcgen05.ld TMEM -> registers -> bias / GELU / dropout / residual ->
-//                               global; warp w owns TMEM lanes 32*(w%4)..+31)
+//   warps 2..   epilogue       (8 or 16 warps: tcgen05.ld TMEM -> registers -> shared-memory transpose -> bias / GELU /
+//                               dropout / residual -> coalesced global stores; warp w owns TMEM lanes 32*(w%4)..+31 and
+//                               one column part of the tile)
 // Tile 128 x BN x 64 (BN = 128 or 256).  Either operand may be K-major (row-major [rows,K]) or
 // MN-major (row-major [K,rows]); the second form serves dgrad (B = W as stored) and wgrad
 // (A = dY, B = X, contraction over tokens) without materialising transposes.

@@ -1,12 +1,14 @@
-"""Data-parallel runtime: one process per GPU, parameters replicated, ONE gradient all-reduce per step.
+"""Data-parallel runtime: one process per GPU, parameters replicated, the gradient SUM is the only exchange.
 
 Replaces the reference's single-process `nn.DataParallel` (/root/reference/train.py:111-112), which
 re-broadcasts all 96.6 M parameters and reduces gradients to GPU 0 every step.  Samples are
-independent (LayerNorm only), so the batch dimension is the only partition and the gradient sum
-is the only exchange.
+independent (LayerNorm only), so the batch dimension is the only partition.
 
-All `.grad` tensors are views into one flat fp32 buffer, so the exchange is a single NCCL
-all-reduce over NVLink/NVSwitch with no flatten/unflatten copies, and `zero_grad` is one memset.
+All `.grad` tensors are views into one flat fp32 buffer (`FlatGradBuffer`): no flatten / unflatten copies, `zero_grad`
+is one memset, and the exchange works on ranges of one index space.  Two transports:
+  * `PeerWire` / `FlatGradBuffer.enable_overlap(transport="peer")` -- `samk_exchange_sum` (csrc/exchange.cu): our kernels
+    over NVLink peer memory / NVSwitch multicast, bucket by bucket under the backward pass (the default of bench.py);
+  * NCCL: one all-reduce over the buffer after the step (`GradExchange`), or bucketed on a side stream.
 The loss normaliser `max(sum(loss_mask),1)` is per-replica here; `global_loss_scale` gives the
 factor that makes the summed gradients equal to the reference's global normalisation
 (sam/task_utils.py:28-29 on the gathered scores).
