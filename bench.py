@@ -572,26 +572,53 @@ def run_samk(args):
             ms_noex = timed(lambda: step(resident, resident_adj, do_exchange=False), args.steps)
         allreduce_exposed_ms = ms - ms_noex
 
-    # ---- roofline of the dominant kernel family (tcgen05 GEMM), instrumented extra steps ----
-    ops.gemm_profile = []
-    ops.attn_profile = []
-    saved_hook, ops.grad_ready_hook = ops.grad_ready_hook, None      # no exchange in the instrumented eager steps
-    for _ in range(2):
-        # per-launch events cannot be recorded inside a graph replay, and the eager loop is launch-bound: an event pair
-        # around a kernel the GPU is waiting for also times the host's launch latency.  A spin kernel in front keeps the
-        # GPU busy while the host enqueues the whole step, so the events bracket back-to-back kernel executions.
+    # ---- roofline of the dominant kernel family (tcgen05 GEMM): per-launch CUDA events INSIDE a captured step ----
+    # The step is captured once more with an event pair around every GEMM and attention launch (ops.TimingEvent:
+    # cudaEventRecordExternal nodes of the graph, on the stream the kernels are launched on) and replayed: the durations
+    # are those of the kernels as they run in the replayed step, side branches and all.  Fallback (capture unavailable):
+    # two eager steps behind a spin kernel, as in round 1.
+    saved_hook, ops.grad_ready_hook = ops.grad_ready_hook, None      # no exchange in the instrumented steps
+    prof = aprof = None
+    n_inst = 1
+    roofline_how = "CUDA events recorded inside a captured step (event-record nodes), one replay"
+    if graphed is not None and os.environ.get("SAMK_BENCH_EVENTS", "graph") == "graph":
         try:
-            torch.cuda._sleep(int(4e7))        # ~20 ms at 1.9 GHz; the host needs ~10-15 ms to enqueue a step
-        except Exception:                      # private torch API: without it the figures are only more pessimistic
-            pass
-        fwd_bwd(resident, resident_adj, exchange_inside=False)
-        torch.cuda.synchronize()
+            ops.profile_in_graph = True
+            ops.gemm_profile, ops.attn_profile = [], []
+            inst = GraphedTrainStep(model, grads, ex, loss_fn=loss_of, allreduce=None, warmup=1)
+            for _ in range(3):
+                inst.run()
+            torch.cuda.synchronize()
+            per_g, per_a = len(ops.gemm_profile) // 2, len(ops.attn_profile) // 2      # (1 eager warm-up step + the capture)
+            prof, aprof = ops.gemm_profile[-per_g:], ops.attn_profile[-per_a:]
+            _ = sum(s_.elapsed_time(e_) for s_, e_, _, _ in prof)                      # raises if the events are unreadable
+            del inst
+        except Exception as exc:
+            print("bench: in-graph event timing unavailable (%r); instrumented eager steps instead" % (exc,), file=sys.stderr, flush=True)
+            prof = aprof = None
+        finally:
+            ops.profile_in_graph = False
+            ops.gemm_profile = ops.attn_profile = None
+    if prof is None:
+        n_inst = 2
+        roofline_how = "CUDA events around every launch of two eager steps queued behind a spin kernel"
+        ops.gemm_profile = []
+        ops.attn_profile = []
+        for _ in range(n_inst):
+            # the eager loop is launch-bound: an event pair around a kernel the GPU is waiting for also times the host's
+            # launch latency.  A spin kernel in front keeps the GPU busy while the host enqueues the whole step.
+            try:
+                torch.cuda._sleep(int(4e7))        # ~20 ms at 1.9 GHz; the host needs ~10-15 ms to enqueue a step
+            except Exception:                      # private torch API: without it the figures are only more pessimistic
+                pass
+            fwd_bwd(resident, resident_adj, exchange_inside=False)
+            torch.cuda.synchronize()
+        prof, ops.gemm_profile = ops.gemm_profile, None
+        aprof, ops.attn_profile = ops.attn_profile, None
     ops.grad_ready_hook = saved_hook
-    prof, ops.gemm_profile = ops.gemm_profile, None
-    aprof, ops.attn_profile = ops.attn_profile, None
-    g_ms = sum(s.elapsed_time(e) for s, e, _, _ in prof) / 2
-    g_flop = sum(f for _, _, f, _ in prof) / 2
-    n_gemm = len(prof) // 2
+    g_ms = sum(s.elapsed_time(e) for s, e, _, _ in prof) / n_inst
+    g_flop = sum(f for _, _, f, _ in prof) / n_inst
+    n_gemm = len(prof) // n_inst
     peak_tf, peak_gbs, peak_src = peaks()
     achieved = g_flop / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     # DRAM bytes per launch measured by `ncu --set full` for the big shapes (tools/ncu_summary.py --json)
@@ -613,16 +640,16 @@ def run_samk(args):
         us = tot_ms / cnt * 1e3
         tf = f_ / (us * 1e-6) / 1e12
         Mg, Ng, Kg, amn, bmn = shape
-        item = {"M": Mg, "N": Ng, "K": Kg, "a_mn": amn, "b_mn": bmn, "launches_per_step": cnt // 2,
-                "us_per_launch": us, "achieved": tf, "frac": tf / peak_tf, "share_of_step": tot_ms / 2 / ms if ms > 0 else None,
+        item = {"M": Mg, "N": Ng, "K": Kg, "a_mn": amn, "b_mn": bmn, "launches_per_step": cnt // n_inst,
+                "us_per_launch": us, "achieved": tf, "frac": tf / peak_tf, "share_of_step": tot_ms / n_inst / ms if ms > 0 else None,
                 "operand_MB": (Mg * Kg + Ng * Kg) * 2 / 1e6}
         key = "gemm_%dx%dx%d_%d%d" % (Mg, Ng, Kg, int(amn), int(bmn))
         if key in ncu_traffic and B == 128:
             item["traffic"] = ncu_traffic[key]["dram_bytes"]
             item["traffic_src"] = ncu_traffic[key].get("src")
-            tr_sum += item["traffic"] * (cnt // 2)
-            tr_launches += cnt // 2
-            tr_ms += tot_ms / 2
+            tr_sum += item["traffic"] * (cnt // n_inst)
+            tr_launches += cnt // n_inst
+            tr_ms += tot_ms / n_inst
         if len(by_shape) < 6:
             by_shape.append(item)
     # the north-star kernel: fused masked attention of the MMT layers (L = 182), HBM-bound at this length
@@ -632,7 +659,7 @@ def run_samk(args):
         rows = [(s.elapsed_time(e), nb, fl) for k, L_, s, e, nb, fl in aprof if k == kind and L_ == Lm]
         if rows:
             ms_k = sum(r[0] for r in rows) / len(rows)
-            attention[kind] = {"us_per_launch": ms_k * 1e3, "launches_per_step": len(rows) // 2,
+            attention[kind] = {"us_per_launch": ms_k * 1e3, "launches_per_step": len(rows) // n_inst,
                                "algorithmic_MB": rows[0][1] / 1e6, "achieved_GBs": rows[0][1] / (ms_k * 1e-3) / 1e9,
                                "hbm_frac": rows[0][1] / (ms_k * 1e-3) / 1e9 / peak_gbs,
                                "dense_equiv_TFLOPs": rows[0][2] / (ms_k * 1e-3) / 1e12}
@@ -670,7 +697,7 @@ def run_samk(args):
                      "traffic_note": ("mean DRAM bytes per launch over the %d launches (%.0f %% of the GEMM time) whose shape has "
                                       "an ncu --set full capture in profiles/ncu_traffic.json" % (tr_launches, 100 * tr_ms / g_ms))
                      if tr_launches else "no profiles/ncu_traffic.json",
-                     "peak_source": peak_src + " (sustained bf16)",
+                     "peak_source": peak_src + " (sustained bf16)", "timing": roofline_how,
                      "gemm_ms_per_step": g_ms, "gemm_share_of_step": g_ms / ms if ms > 0 else None,
                      "step_flop_frac_of_peak": value / world * FLOP_PER_SAMPLE / (peak_tf * 1e12),
                      "by_shape": by_shape},

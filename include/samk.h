@@ -240,6 +240,15 @@ int samk_sumsq(const float* x, long long n, double* out_accum, void* stream);
 int samk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, double lr, double beta1,
                    double beta2, double eps, int step, const double* grad_sumsq, double max_norm, void* stream);
 
+/* ---- timing events usable inside a stream capture ------------------------------------------------
+ * samk_timing_event_record on a capturing stream records with cudaEventRecordExternal (an event-record node of the graph);
+ * after a replay + synchronisation samk_timing_event_elapsed_ms gives the time between two of them: per-kernel
+ * durations of the REPLAYED step (bench.py's roofline figures). */
+int samk_timing_event_create(void** ev);
+int samk_timing_event_record(void* ev, void* stream);
+int samk_timing_event_elapsed_ms(void* start, void* end, float* ms);
+int samk_timing_event_destroy(void* ev);
+
 /* ---- gradient exchange over NVLink peer memory ---------------------------------------------------
  * Replaces the gradient reduction of nn.DataParallel (/root/reference/train.py:111-112): flat[lo:hi] = SUM over the ranks
  * of flat[lo:hi], through a symmetric "wire" allocation that every rank maps from every other rank (and, on NVSwitch,

@@ -66,6 +66,10 @@ SIGNATURES = {
     "samk_cast_dual": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p]),
     "samk_cast_flat": (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_void_p]),
     "samk_exchange_sum": (c_int, [ctypes.POINTER(PeerWire), c_void_p, c_ll, c_ll, c_void_p]),
+    "samk_timing_event_create": (c_int, [ctypes.POINTER(c_void_p)]),
+    "samk_timing_event_record": (c_int, [c_void_p, c_void_p]),
+    "samk_timing_event_elapsed_ms": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_float)]),
+    "samk_timing_event_destroy": (c_int, [c_void_p]),
     "samk_cast_scaled_f16": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
     "samk_split3_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
     "samk_l2norm": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),

@@ -73,6 +73,36 @@ int samk_advance_dropout_salt(void* stream) {
   }
   return samk::check_launch("samk_advance_dropout_salt");
 }
+// Timing events that may be recorded INSIDE a stream capture (cudaEventRecordExternal: the record becomes an event-record
+// node of the graph and the event is readable with cudaEventElapsedTime after a replay) -- per-kernel durations of the
+// replayed step, which torch.cuda.Event cannot give.
+int samk_timing_event_create(void** ev) {
+  if (!ev) { samk::set_error("samk_timing_event_create: null pointer"); return SAMK_ERR_ARG; }
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) { samk::set_error("cudaEventCreate: %s", cudaGetErrorString(cudaGetLastError())); return SAMK_ERR_CUDA; }
+  *ev = (void*)e;
+  return SAMK_OK;
+}
+int samk_timing_event_record(void* ev, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &st);
+  const unsigned flags = st == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault;
+  if (cudaEventRecordWithFlags((cudaEvent_t)ev, s, flags) != cudaSuccess) {
+    samk::set_error("cudaEventRecordWithFlags: %s", cudaGetErrorString(cudaGetLastError()));
+    return SAMK_ERR_CUDA;
+  }
+  return SAMK_OK;
+}
+int samk_timing_event_elapsed_ms(void* start, void* end, float* ms) {
+  if (!ms) { samk::set_error("samk_timing_event_elapsed_ms: null pointer"); return SAMK_ERR_ARG; }
+  if (cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)end) != cudaSuccess) {
+    samk::set_error("cudaEventElapsedTime: %s", cudaGetErrorString(cudaGetLastError()));
+    return SAMK_ERR_CUDA;
+  }
+  return SAMK_OK;
+}
+int samk_timing_event_destroy(void* ev) { return cudaEventDestroy((cudaEvent_t)ev) == cudaSuccess ? SAMK_OK : SAMK_ERR_CUDA; }
 int samk_set_dropout_salt(unsigned long long salt, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (samk::set_drop_salt_gemm(salt, s) || samk::set_drop_salt_attn_tc(salt, s) || samk::set_drop_salt_attn_simt(salt, s) ||

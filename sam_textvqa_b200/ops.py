@@ -37,6 +37,39 @@ if _PRECISION not in ("f16", "bf16x3"):
 _GEMM_IMPL = int(os.environ.get("SAMK_GEMM_IMPL", "0"))
 _ATTN_IMPL = int(os.environ.get("SAMK_ATTN_IMPL", "0"))
 launch_count = 0  # kernels launched through this module (bench.py reports it)
+class TimingEvent(object):
+    """CUDA event that may be recorded inside a stream capture (samk_timing_event_*): same record() / elapsed_time()
+    surface as torch.cuda.Event, readable after a replay of the captured graph."""
+
+    def __init__(self):
+        h = ctypes.c_void_p()
+        check(lib().samk_timing_event_create(ctypes.byref(h)), "timing_event_create")
+        self.h = h
+
+    def record(self):
+        check(lib().samk_timing_event_record(self.h, stream_ptr()), "timing_event_record")
+
+    def elapsed_time(self, end):
+        ms = ctypes.c_float()
+        check(lib().samk_timing_event_elapsed_ms(self.h, end.h, ctypes.byref(ms)), "timing_event_elapsed")
+        return ms.value
+
+    def __del__(self):
+        try:
+            lib().samk_timing_event_destroy(self.h)
+        except Exception:
+            pass
+
+
+profile_in_graph = False     # bench.py: the profile lists below take TimingEvent pairs (recorded inside the captured step)
+
+
+def _prof_events():
+    if profile_in_graph:
+        return TimingEvent(), TimingEvent()
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
 gemm_profile = None  # bench.py: list collecting (start_event, end_event, algorithmic_flops, (M, N, K, a_mn, b_mn)) per GEMM launch
 grad_ready_hook = None  # dp.FlatGradBuffer.enable_overlap: called with the parameters a backward op has just finished
 launch_log = None    # bench.py --profile-only: list collecting ("gemm", M, N, K, a_mn, b_mn) / ("attn_fwd" | "attn_bwd", L) in launch order
@@ -439,7 +472,7 @@ def gemm(a, a_mn, b, b_mn, M, N, K, out, bias=None, act=0, pre=None, aux=None, d
     if launch_log is not None:
         launch_log.append(("gemm", int(M), int(N), int(K), bool(a_mn), bool(b_mn)))
     if gemm_profile is not None:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0, ev1 = _prof_events()
         ev0.record()
     check(lib().samk_gemm_16(ptr(a.t), a.dt, 1 if a_mn else 0, a.ld, ptr(b.t), b.dt, 1 if b_mn else 0, b.ld, M, N, Kk,
                              ctypes.byref(ep), split_k, _GEMM_IMPL, stream_ptr()), "gemm")
@@ -824,7 +857,7 @@ def attention_fwd(qkv, valid, rel, dims, spatial, quad_mask, p, drop, allow=None
     ap = _attn_params(qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p, drop, allow=allow, keep=keep)
     ap.q_begin = int(q_begin)
     if attn_profile is not None:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0, ev1 = _prof_events()
         ev0.record()
     if launch_log is not None:
         launch_log.append(("attn_fwd", int(L)))
@@ -893,7 +926,7 @@ def attention_bwd(dctx, qkv, ctx_t, lse, valid, rel, dims, spatial, quad_mask, p
         ap.do_f16, ap.do_inv_scale = do16.data_ptr(), inv_scale.data_ptr()
         ap.bwd_phase = 1 if prepared is not None else 0
     if attn_profile is not None:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0, ev1 = _prof_events()
         ev0.record()
     if launch_log is not None:
         launch_log.append(("attn_bwd", int(L)))
