@@ -5,8 +5,9 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" = one pass of the hot path over one synthetic batch: SAM4C forward in train mode (all
-dropouts at the yml's 0.1) -> masked BCE loss -> backward (-> one NCCL gradient all-reduce when
-N > 1) -> zero_grad.  Workload at every N: BASELINE config[1], the shipped c3 experiment
+dropouts at the yml's 0.1) -> masked BCE loss -> backward (with the gradient exchange of N > 1 ranks:
+samk_exchange_sum over NVLink peer memory, bucket by bucket under the backward pass; SAMK_DP_TRANSPORT=nccl = one
+ncclAllReduce after the step) -> zero_grad; by default the relation graph is built on the device inside the step.  Workload at every N: BASELINE config[1], the shipped c3 experiment
 (layers n,n,s,s,s,s; 20 text + 100 obj + 50 OCR + 12 dec tokens; d=768; V=5000), 128 samples per GPU
 (weak scaling).  `value` is timed with the inputs resident in HBM; `e2e` runs the same step from
 pinned host buffers with the host->device copies and a device->host read of the loss inside the
@@ -17,8 +18,9 @@ The line also carries
             shipped c3 stack (tests/golden/sam4c_c3.npz): logits rel err and argmax identity, plus the other mode;
   extras    (N = 1) throughput of the other precision mode, a full optimizer step, greedy decoding, BASELINE
             configs 0 / 2, the spatial-graph kernel (pairs/s, GB/s);
-  roofline  all tcgen05 GEMM launches of one step against the sustained bf16 peak, per-shape detail with the DRAM
-            bytes ncu measured (profiles/ncu_traffic.json, written by tools/ncu_summary.py from `ncu --set full`).
+  roofline  all tcgen05 GEMM launches of one step against the sustained bf16 peak, timed with CUDA events recorded inside a
+            captured step (ops.TimingEvent), per-shape detail with the DRAM bytes ncu measured (profiles/ncu_traffic.json,
+            written by tools/ncu_summary.py from one ncu pass over a step); `attention`: the same for the north-star kernel.
 
 `--impl reference` times the UNMODIFIED reference (oracle/_ref: a verbatim, git-ignored copy of /root/reference/sam
 made by `python -m oracle.build_ref`, run through the oracle/shim stand-ins for its two un-vendored dependencies) on the
