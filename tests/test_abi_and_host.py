@@ -249,3 +249,34 @@ def test_peer_exchange_buckets_are_whole_wire_vectors_and_cover_every_gradient_o
         for i in range(lo, hi):
             covered[i] += 1
     assert covered == [1] * padded, stub.ranges
+
+
+def test_flat_grad_buffer_views_padding_and_reattachment_on_host():
+    """dp.FlatGradBuffer: every .grad is a view of one flat buffer whose storage is padded to whole wire vectors; zero()
+    clears it and re-attaches views that a caller replaced (optimizer.zero_grad(set_to_none=True), train.py:144)."""
+    from sam_textvqa_b200 import dp
+    params = [torch.nn.Parameter(torch.randn(7, 3)), torch.nn.Parameter(torch.randn(5)), torch.nn.Parameter(torch.randn(2, 2))]
+    buf = dp.FlatGradBuffer(params)
+    assert buf.flat.numel() == 30 and buf._storage.numel() == 64 and buf.flat.data_ptr() == buf._storage.data_ptr()
+    off = 0
+    for p in params:
+        assert p.grad.data_ptr() == buf.flat.data_ptr() + 4 * off and p.grad.shape == p.shape
+        off += p.numel()
+    sum((p * p).sum() for p in params).backward()
+    assert torch.allclose(buf.flat[:21].view(7, 3), 2 * params[0].detach())
+    params[1].grad = None
+    buf.zero()
+    assert float(buf._storage.abs().sum()) == 0.0
+    assert params[1].grad is not None and params[1].grad.data_ptr() == buf.flat.data_ptr() + 4 * 21
+
+
+def test_bench_numa_binding_is_a_no_op_without_topology_information():
+    """bench.bind_to_gpu_numa_node must never raise (no GPU here, single-node VMs on the GPU pool): it returns None."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("samk_bench", os.path.join(root, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    before = os.sched_getaffinity(0)
+    assert mod.bind_to_gpu_numa_node(0) is None
+    assert os.sched_getaffinity(0) == before
